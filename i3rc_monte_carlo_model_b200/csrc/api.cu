@@ -1,0 +1,1450 @@
+// C ABI of include/i3rc_b200.h: host side of the B200 integrator (handle, validation with the reference's
+// status texts, device memory, kernel launches).  No CPU fallback: without a CUDA device every compute entry
+// point returns I3RC_FAILURE.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/i3rc_b200.h"
+#include "kernels.cuh"
+#include "tables.cuh"
+
+using namespace i3rc;
+
+namespace {
+
+std::string g_message;  // message of failures that happen before a handle exists
+
+inline float h_spacing(float x) {
+  if (x == 0.0f) return F_TINY;
+  int e;
+  (void)frexpf(fabsf(x), &e);
+  float s = ldexpf(1.0f, e - 24);
+  return s < F_TINY ? F_TINY : s;
+}
+
+struct HostTable {
+  int kind = 0, nEntries = 0, nAngles = 0;
+  std::vector<int> offsets;
+  std::vector<float> coefs, angles, values;
+  // device copies
+  int* d_offsets = nullptr;
+  float *d_coefs = nullptr, *d_angles = nullptr, *d_values = nullptr;
+  std::vector<int> nodesPerEntry;
+  int maxNodes = 0;
+};
+struct DevMatrix {
+  float* d = nullptr;
+  int nSteps = 0, nEntries = 0;
+};
+
+}  // namespace
+
+struct i3rc_integrator {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int numSMs = 148;
+  // MCRT:50-142
+  bool readyToCompute = false, computeIntensity = false;
+  int minForwardTableSize = 9001, minInverseTableSize = 9001;
+  bool useRayTracing = true, useRussianRoulette = true;
+  float RussianRouletteW = 1.0f, surfaceAlbedo = 0.0f;
+  bool xyRegular = false, zRegular = false;
+  float deltaX = 0, deltaY = 0, deltaZ = 0;
+  int nx = 0, ny = 0, nz = 0, nc = 0;
+  std::vector<float> xe, ye, ze;
+  float *d_xe = nullptr, *d_ye = nullptr, *d_ze = nullptr;
+  float *d_ext = nullptr, *d_cum = nullptr, *d_ssa = nullptr;
+  int* d_pf = nullptr;
+  float maxExt = 0.0f;
+  bool useSurfaceBDRF = false;
+  int surf_nx = 0, surf_ny = 0;
+  float *d_surf_x = nullptr, *d_surf_y = nullptr, *d_surf_p = nullptr;
+  std::vector<float> surf_x, surf_y, surf_p;
+  std::vector<HostTable> tables;
+  std::vector<DevMatrix> inv, fwd, fwdOrig;
+  TableDesc* d_tableDesc = nullptr;
+  bool tableDescDirty = true;
+  int nDir = 0;
+  std::vector<float> dirs;  // [nDir][DIR_STRIDE]
+  float* d_dirs = nullptr;
+  bool useHybrid = false;
+  float hybridWidth = 7.0f;
+  int numOrdersOrig = 0;
+  bool useRRIntensity = false;
+  float zetaMin = 0.3f;
+  bool limitContrib = false;
+  float maxContrib = 3.402823466e+38f;
+  bool trackByComponent = false;
+  // tallies
+  float *d_fluxUp = nullptr, *d_fluxDown = nullptr, *d_fluxAbs = nullptr, *d_volAbs = nullptr;
+  float *d_intensity = nullptr, *d_intByComp = nullptr, *d_excess = nullptr;
+  unsigned long long *d_counters = nullptr, *d_next = nullptr;
+  double* d_scratch = nullptr;  // slab sums
+  size_t scratchN = 0;
+  float* d_fscratch = nullptr;
+  size_t fscratchN = 0;
+  // source arrays (I3RC_SRC_ARRAYS)
+  float* d_srcArrays = nullptr;
+  size_t srcArraysN = 0;
+  // batch moments
+  double* d_stats = nullptr;
+  size_t statsN = 0;
+  bool statsVolume = false;
+  int statsNDir = 0;
+  // timing
+  std::vector<cudaEvent_t> ev;
+  size_t evUsed = 0;
+  double traceMs = 0.0;
+  long long traceLaunches = 0, otherLaunches = 0;
+  // tuning
+  int blockSize = 128, blocksPerSM = 0, kSteps = 8;
+  // nccl
+  void* nccl = nullptr;
+  void* ncclLib = nullptr;
+  std::string message;
+  i3rc_counters counters{};
+};
+
+namespace {
+
+#define CUDA_OK(h, call)                                                        \
+  do {                                                                          \
+    cudaError_t e_ = (call);                                                    \
+    if (e_ != cudaSuccess) {                                                    \
+      (h)->message = std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call; \
+      return I3RC_FAILURE;                                                      \
+    }                                                                           \
+  } while (0)
+
+int fail(i3rc_integrator* h, const char* m) {
+  h->message = m;
+  return I3RC_FAILURE;
+}
+
+template <typename T>
+cudaError_t upload(T** dst, const T* src, size_t n, cudaStream_t st) {
+  if (*dst) cudaFree(*dst);
+  *dst = nullptr;
+  cudaError_t e = cudaMalloc((void**)dst, sizeof(T) * (n ? n : 1));
+  if (e != cudaSuccess) return e;
+  if (n && src) e = cudaMemcpyAsync(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, st);
+  return e;
+}
+template <typename T>
+void dfree(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+bool have_device() {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess && n > 0;
+}
+
+void free_table(HostTable& t) {
+  dfree(t.d_offsets);
+  dfree(t.d_coefs);
+  dfree(t.d_angles);
+  dfree(t.d_values);
+}
+void free_matrix(DevMatrix& m) {
+  dfree(m.d);
+  m.nSteps = m.nEntries = 0;
+}
+
+int alloc_tallies(i3rc_integrator* h) {
+  size_t ncol = (size_t)h->nx * h->ny, ncell = ncol * h->nz;
+  CUDA_OK(h, cudaMalloc(&h->d_fluxUp, sizeof(float) * ncol));
+  CUDA_OK(h, cudaMalloc(&h->d_fluxDown, sizeof(float) * ncol));
+  CUDA_OK(h, cudaMalloc(&h->d_fluxAbs, sizeof(float) * ncol));
+  CUDA_OK(h, cudaMalloc(&h->d_volAbs, sizeof(float) * ncell));
+  CUDA_OK(h, cudaMalloc(&h->d_counters, sizeof(unsigned long long) * CNT_N));
+  CUDA_OK(h, cudaMalloc(&h->d_next, sizeof(unsigned long long)));
+  CUDA_OK(h, cudaMemsetAsync(h->d_fluxUp, 0, sizeof(float) * ncol, h->stream));
+  CUDA_OK(h, cudaMemsetAsync(h->d_fluxDown, 0, sizeof(float) * ncol, h->stream));
+  CUDA_OK(h, cudaMemsetAsync(h->d_fluxAbs, 0, sizeof(float) * ncol, h->stream));
+  CUDA_OK(h, cudaMemsetAsync(h->d_volAbs, 0, sizeof(float) * ncell, h->stream));
+  CUDA_OK(h, cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * CNT_N, h->stream));
+  return I3RC_SUCCESS;
+}
+
+int ensure_scratch(i3rc_integrator* h, size_t nDoubles) {
+  if (h->scratchN < nDoubles) {
+    dfree(h->d_scratch);
+    CUDA_OK(h, cudaMalloc(&h->d_scratch, sizeof(double) * nDoubles));
+    h->scratchN = nDoubles;
+  }
+  return I3RC_SUCCESS;
+}
+int ensure_fscratch(i3rc_integrator* h, size_t n) {
+  if (h->fscratchN < n) {
+    dfree(h->d_fscratch);
+    CUDA_OK(h, cudaMalloc(&h->d_fscratch, sizeof(float) * n));
+    h->fscratchN = n;
+  }
+  return I3RC_SUCCESS;
+}
+
+// common part of the two new_Integrator forms once the dense arrays are on the device (MCRT:193-254)
+int finish_new_integrator(i3rc_integrator* h) {
+  const int nx = h->nx, ny = h->ny, nz = h->nz;
+  const std::vector<float>&x = h->xe, &y = h->ye, &z = h->ze;
+  float dX = x[1] - x[0], dY = y[1] - y[0], dZ = z[1] - z[0];
+  bool xyReg = true, zReg = true;
+  for (int i = 0; i < nx; i++)
+    if (!(fabsf((x[i + 1] - x[i]) - dX) <= 2.0f * h_spacing(x[i + 1]))) xyReg = false;
+  for (int i = 0; i < ny; i++)
+    if (!(fabsf((y[i + 1] - y[i]) - dY) <= 2.0f * h_spacing(y[i + 1]))) xyReg = false;
+  for (int i = 0; i < nz; i++)
+    if (!(fabsf((z[i + 1] - z[i]) - dZ) <= h_spacing(z[i + 1]))) zReg = false;
+  h->xyRegular = xyReg;
+  h->zRegular = zReg;
+  if (xyReg) {
+    h->deltaX = dX;
+    h->deltaY = dY;
+  }
+  if (zReg) h->deltaZ = dZ;
+  CUDA_OK(h, upload(&h->d_xe, x.data(), x.size(), h->stream));
+  CUDA_OK(h, upload(&h->d_ye, y.data(), y.size(), h->stream));
+  CUDA_OK(h, upload(&h->d_ze, z.data(), z.size(), h->stream));
+  size_t ncell = (size_t)nx * ny * nz;
+  unsigned int* d_max = nullptr;
+  CUDA_OK(h, cudaMalloc(&d_max, sizeof(unsigned int)));
+  CUDA_OK(h, cudaMemsetAsync(d_max, 0, sizeof(unsigned int), h->stream));
+  k_bump_and_max<<<(unsigned)((ncell + 255) / 256), 256, 0, h->stream>>>(ncell, h->d_cum + (size_t)(h->nc - 1) * ncell,
+                                                                        h->d_ext, d_max);
+  h->otherLaunches++;
+  unsigned int bits = 0;
+  CUDA_OK(h, cudaMemcpyAsync(&bits, d_max, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_max);
+  memcpy(&h->maxExt, &bits, sizeof(float));
+  h->tables.resize(h->nc);
+  h->inv.resize(h->nc);
+  h->fwd.resize(h->nc);
+  h->fwdOrig.resize(h->nc);
+  int rc = alloc_tallies(h);
+  if (rc != I3RC_SUCCESS) return rc;
+  h->readyToCompute = true;
+  h->message.clear();
+  return I3RC_SUCCESS;
+}
+
+i3rc_integrator* make_handle() {
+  i3rc_integrator* h = new i3rc_integrator();
+  cudaGetDevice(&h->device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess) h->numSMs = prop.multiProcessorCount;
+  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  return h;
+}
+
+bool valid_edges(const float* e, int n) {
+  for (int i = 0; i < n; i++)
+    if (!(e[i + 1] - e[i] > 0.0f)) return false;
+  return true;
+}
+
+int upload_table_desc(i3rc_integrator* h) {
+  if (!h->tableDescDirty && h->d_tableDesc) return I3RC_SUCCESS;
+  std::vector<TableDesc> td(h->nc);
+  for (int c = 0; c < h->nc; c++) {
+    td[c].inv = h->inv[c].d;
+    td[c].nInv = h->inv[c].nSteps;
+    td[c].fwd = h->fwd[c].d;
+    td[c].fwdOrig = h->fwdOrig[c].d ? h->fwdOrig[c].d : h->fwd[c].d;
+    td[c].nFwd = h->fwd[c].nSteps;
+    td[c].nEntries = h->inv[c].nEntries;
+    td[c].pad = 0;
+  }
+  CUDA_OK(h, upload(&h->d_tableDesc, td.data(), td.size(), h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  h->tableDescDirty = false;
+  return I3RC_SUCCESS;
+}
+
+// tabulateInversePhaseFunctions / tabulateForwardPhaseFunctions (MCRT:1809-1923)
+int tabulate(i3rc_integrator* h) {
+  for (int c = 0; c < h->nc; c++) {
+    HostTable& t = h->tables[c];
+    PhaseTableDev pd{t.kind,    t.nEntries, t.d_offsets, t.d_coefs, t.nAngles, t.d_angles,
+                     t.d_values, t.maxNodes, t.nodesPerEntry.data()};
+    if (!(h->inv[c].d && h->inv[c].nSteps >= h->minInverseTableSize)) {
+      if (t.kind == 0) return fail(h, "tabulateInversePhaseFunctions: failed on component (no phase function table)");
+      free_matrix(h->inv[c]);
+      int n = h->minInverseTableSize;
+      CUDA_OK(h, cudaMalloc(&h->inv[c].d, sizeof(float) * (size_t)n * t.nEntries));
+      CUDA_OK(h, build_inverse_table(pd, n, h->inv[c].d, h->stream));
+      h->inv[c].nSteps = n;
+      h->inv[c].nEntries = t.nEntries;
+      h->otherLaunches += 4;
+      h->tableDescDirty = true;
+    }
+    if (h->computeIntensity && !(h->fwd[c].d && h->fwd[c].nSteps >= h->minForwardTableSize)) {
+      if (t.kind == 0) return fail(h, "tabulatePhaseFunctions: failed on component (no phase function table)");
+      free_matrix(h->fwd[c]);
+      free_matrix(h->fwdOrig[c]);
+      int n = h->minForwardTableSize;
+      size_t bytes = sizeof(float) * (size_t)n * t.nEntries;
+      CUDA_OK(h, cudaMalloc(&h->fwdOrig[c].d, bytes));
+      CUDA_OK(h, cudaMalloc(&h->fwd[c].d, bytes));
+      CUDA_OK(h, build_forward_table(pd, n, h->fwdOrig[c].d, h->stream));
+      if (h->useHybrid && h->hybridWidth > 0.0f)
+        CUDA_OK(h, build_hybrid_table(h->fwdOrig[c].d, h->fwd[c].d, n, t.nEntries, h->hybridWidth, h->stream));
+      else
+        CUDA_OK(h, cudaMemcpyAsync(h->fwd[c].d, h->fwdOrig[c].d, bytes, cudaMemcpyDeviceToDevice, h->stream));
+      h->fwd[c].nSteps = h->fwdOrig[c].nSteps = n;
+      h->fwd[c].nEntries = h->fwdOrig[c].nEntries = t.nEntries;
+      h->otherLaunches += 3;
+      h->tableDescDirty = true;
+    }
+  }
+  return upload_table_desc(h);
+}
+
+void fill_problem(i3rc_integrator* h, Problem& p) {
+  memset(&p, 0, sizeof(p));
+  p.nx = h->nx;
+  p.ny = h->ny;
+  p.nz = h->nz;
+  p.nc = h->nc;
+  p.xyRegular = h->xyRegular;
+  p.zRegular = h->zRegular;
+  p.x0 = h->xe.front();
+  p.y0 = h->ye.front();
+  p.z0 = h->ze.front();
+  p.xmax = h->xe.back();
+  p.ymax = h->ye.back();
+  p.zmax = h->ze.back();
+  p.dx = h->deltaX;
+  p.dy = h->deltaY;
+  p.dz = h->deltaZ;
+  p.xe = h->d_xe;
+  p.ye = h->d_ye;
+  p.ze = h->d_ze;
+  p.ext = h->d_ext;
+  p.cumExt = h->d_cum;
+  p.ssa = h->d_ssa;
+  p.pfIdx = h->d_pf;
+  p.maxExt = h->maxExt;
+  p.tables = h->d_tableDesc;
+  p.computeIntensity = h->computeIntensity;
+  p.nDir = h->computeIntensity ? h->nDir : 0;
+  p.dirs = h->d_dirs;
+  p.useRayTracing = h->useRayTracing;
+  p.useRussianRoulette = h->useRussianRoulette;
+  p.useRRIntensity = h->useRRIntensity;
+  p.useHybrid = h->useHybrid;
+  p.numOrdersOrig = h->numOrdersOrig;
+  p.limitContrib = h->limitContrib;
+  p.useSurfaceBDRF = h->useSurfaceBDRF;
+  p.trackByComponent = h->trackByComponent || h->limitContrib;
+  p.rouletteW = h->RussianRouletteW;
+  p.surfaceAlbedo = h->surfaceAlbedo;
+  p.zetaMin = h->zetaMin;
+  p.maxContrib = h->maxContrib;
+  p.surf_nx = h->surf_nx;
+  p.surf_ny = h->surf_ny;
+  p.surf_x = h->d_surf_x;
+  p.surf_y = h->d_surf_y;
+  p.surf_albedo = h->d_surf_p;
+  p.fluxUp = h->d_fluxUp;
+  p.fluxDown = h->d_fluxDown;
+  p.fluxAbs = h->d_fluxAbs;
+  p.volAbs = h->d_volAbs;
+  p.intensity = h->d_intensity;
+  p.intByComp = h->d_intByComp;
+  p.excess = h->d_excess;
+  p.counters = h->d_counters;
+  p.nextPhoton = h->d_next;
+}
+
+// validation of a photon source: the checks of the new_PhotonStream constructors
+// (Code/monteCarloIllumination.f95:78-83, 122-125, 163-164, 200-208, 251-268, 353-376)
+int validate_source(i3rc_integrator* h, const i3rc_photon_source* s) {
+  if (!s) return fail(h, "getNextPhoton: photons have not been initialized.");
+  if (s->numberOfPhotons <= 0) return fail(h, "setIllumination: must ask for non-negative number of photons.");
+  switch (s->kind) {
+    case I3RC_SRC_DIRECTIONAL:
+    case I3RC_SRC_SPOTLIGHT:
+      if (s->solarAzimuth < 0.0f || s->solarAzimuth > 360.0f) return fail(h, "setIllumination: solarAzimuth out of bounds");
+      /* fall through */
+    case I3RC_SRC_RANDOM_AZIMUTH:
+      if (fabsf(s->solarMu) > 1.0f || fabsf(s->solarMu) <= F_TINY) return fail(h, "setIllumination: solarMu out of bounds");
+      break;
+    case I3RC_SRC_FLUX:
+      break;
+    case I3RC_SRC_INTERNAL_FLUX:
+    case I3RC_SRC_INTERNAL_INTENSITY:
+      break;
+    case I3RC_SRC_ARRAYS:
+      if (!s->xPosition || !s->yPosition || !s->zPosition || !s->initialMu || !s->initialPhi)
+        return fail(h, "getNextPhoton: photons have not been initialized.");
+      break;
+    default:
+      return fail(h, "new_PhotonStream: unknown source kind");
+  }
+  if (s->kind == I3RC_SRC_SPOTLIGHT && (s->x > 1.0f || s->x <= 0.0f || s->y > 1.0f || s->y <= 0.0f))
+    return fail(h, "setIllumination: x and y positions must be between 0 and 1");
+  if (s->kind == I3RC_SRC_INTERNAL_FLUX || s->kind == I3RC_SRC_INTERNAL_INTENSITY) {
+    if (s->x > 1.0f || s->x <= 0.0f || s->y > 1.0f || s->y <= 0.0f || s->z > 1.0f || s->z <= 0.0f)
+      return fail(h, "setIllumination: x, y, z positions must be between 0 and 1");
+    if ((s->has_deltaX && (s->x + s->deltaX / 2.0f > 1.0f || s->x - s->deltaX / 2.0f <= 0.0f)) ||
+        (s->has_deltaY && (s->y + s->deltaY / 2.0f > 1.0f || s->y - s->deltaY / 2.0f <= 0.0f)))
+      return fail(h, "setIllumination: max, min positions must be between 0 and 1");
+  }
+  if (s->kind == I3RC_SRC_INTERNAL_INTENSITY) {
+    if (s->detectorPhi < 0.0f || s->detectorPhi > 360.0f) return fail(h, "setIllumination: detectorPhi out of bounds");
+    if (fabsf(s->detectorMu) > 1.0f || fabsf(s->detectorMu) <= F_TINY)
+      return fail(h, "setIllumination: detectorMu out of bounds");
+  }
+  return I3RC_SUCCESS;
+}
+
+int fill_source(i3rc_integrator* h, const i3rc_photon_source* s, SourceDev& d) {
+  memset(&d, 0, sizeof(d));
+  const float pi = acosf(-1.0f);
+  d.kind = s->kind;
+  d.n = s->numberOfPhotons;
+  d.mu = -fabsf(s->solarMu);
+  d.phi = s->solarAzimuth * pi / 180.0f;
+  d.x = s->x;
+  d.y = s->y;
+  d.z = s->z;
+  if (s->kind == I3RC_SRC_INTERNAL_FLUX)
+    d.z = s->detectorPointsUp ? fmaxf(s->z, 2.0f * F_TINY) : fminf(s->z, 1.0f - h_spacing(1.0f));
+  if (s->kind == I3RC_SRC_INTERNAL_INTENSITY)
+    d.z = s->detectorMu > F_TINY ? fmaxf(s->z, 2.0f * F_TINY) : fminf(s->z, 1.0f - h_spacing(1.0f));
+  d.detectorMu = s->detectorMu;
+  d.detectorPhi = s->detectorPhi;
+  d.pointsUp = s->detectorPointsUp;
+  d.hasDx = s->has_deltaX;
+  d.hasDy = s->has_deltaY;
+  d.deltaX = s->deltaX;
+  d.deltaY = s->deltaY;
+  if (s->kind == I3RC_SRC_ARRAYS) {
+    size_t n = (size_t)s->numberOfPhotons;
+    if (h->srcArraysN < 5 * n) {
+      dfree(h->d_srcArrays);
+      CUDA_OK(h, cudaMalloc(&h->d_srcArrays, sizeof(float) * 5 * n));
+      h->srcArraysN = 5 * n;
+    }
+    const float* srcs[5] = {s->xPosition, s->yPosition, s->zPosition, s->initialMu, s->initialPhi};
+    for (int k = 0; k < 5; k++)
+      CUDA_OK(h, cudaMemcpyAsync(h->d_srcArrays + k * n, srcs[k], sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    d.ax = h->d_srcArrays;
+    d.ay = h->d_srcArrays + n;
+    d.az = h->d_srcArrays + 2 * n;
+    d.amu = h->d_srcArrays + 3 * n;
+    d.aphi = h->d_srcArrays + 4 * n;
+  }
+  return I3RC_SUCCESS;
+}
+
+template <int BLOCK>
+int launch_transport_t(i3rc_integrator* h, const Problem& p) {
+  int perSM = h->blocksPerSM;
+  if (perSM <= 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_transport<BLOCK>, BLOCK, 0) != cudaSuccess || perSM <= 0)
+      perSM = 1;
+  }
+  long long want = (p.src.n + BLOCK - 1) / BLOCK;
+  long long grid = (long long)h->numSMs * perSM;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  k_transport<BLOCK><<<(unsigned)grid, BLOCK, 0, h->stream>>>(p, h->kSteps);
+  return I3RC_SUCCESS;
+}
+
+// zero tallies, trace one batch, post-process (MCRT:296-395); no host synchronisation
+int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint32_t key1) {
+  size_t ncol = (size_t)h->nx * h->ny, ncell = ncol * h->nz;
+  int nD = h->computeIntensity ? h->nDir : 0;
+  bool byComp = h->trackByComponent || h->limitContrib;
+  CUDA_OK(h, cudaMemsetAsync(h->d_fluxUp, 0, sizeof(float) * ncol, h->stream));
+  CUDA_OK(h, cudaMemsetAsync(h->d_fluxDown, 0, sizeof(float) * ncol, h->stream));
+  CUDA_OK(h, cudaMemsetAsync(h->d_fluxAbs, 0, sizeof(float) * ncol, h->stream));
+  CUDA_OK(h, cudaMemsetAsync(h->d_volAbs, 0, sizeof(float) * ncell, h->stream));
+  if (h->d_intensity) CUDA_OK(h, cudaMemsetAsync(h->d_intensity, 0, sizeof(float) * ncol * h->nDir, h->stream));
+  if (h->d_intByComp && byComp)
+    CUDA_OK(h, cudaMemsetAsync(h->d_intByComp, 0, sizeof(float) * ncol * h->nDir * (h->nc + 1), h->stream));
+  if (h->d_excess) CUDA_OK(h, cudaMemsetAsync(h->d_excess, 0, sizeof(float) * (size_t)(h->nc + 1) * h->nDir, h->stream));
+  CUDA_OK(h, cudaMemsetAsync(h->d_next, 0, sizeof(unsigned long long), h->stream));
+
+  Problem p;
+  fill_problem(h, p);
+  p.src = src;
+  p.key0 = key0;
+  p.key1 = key1;
+  p.firstPhoton = 0;
+  // time the transport kernel with CUDA events on this handle's stream
+  if (h->evUsed + 2 > h->ev.size()) {
+    cudaEvent_t a, b;
+    CUDA_OK(h, cudaEventCreate(&a));
+    CUDA_OK(h, cudaEventCreate(&b));
+    h->ev.push_back(a);
+    h->ev.push_back(b);
+  }
+  CUDA_OK(h, cudaEventRecord(h->ev[h->evUsed], h->stream));
+  int rc;
+  switch (h->blockSize) {
+    case 64:
+      rc = launch_transport_t<64>(h, p);
+      break;
+    case 256:
+      rc = launch_transport_t<256>(h, p);
+      break;
+    default:
+      rc = launch_transport_t<128>(h, p);
+      break;
+  }
+  if (rc != I3RC_SUCCESS) return rc;
+  CUDA_OK(h, cudaGetLastError());
+  CUDA_OK(h, cudaEventRecord(h->ev[h->evUsed + 1], h->stream));
+  h->evUsed += 2;
+  h->traceLaunches++;
+
+  if (nD && h->limitContrib) {  // MCRT:327-347
+    int rows = (h->nc + 1) * nD;
+    if (ensure_scratch(h, rows) != I3RC_SUCCESS) return I3RC_FAILURE;
+    k_slab_sums<<<rows, 256, 0, h->stream>>>(h->d_intByComp, ncol, h->d_scratch);
+    dim3 g((unsigned)((ncol + 255) / 256), nD);
+    k_redistribute_excess<<<g, 256, 0, h->stream>>>(nD, h->nc + 1, ncol, h->d_excess, h->d_scratch, h->d_intensity,
+                                                    h->d_intByComp);
+    h->otherLaunches += 2;
+  }
+  NormArgs a;
+  a.nx = h->nx;
+  a.ny = h->ny;
+  a.nz = h->nz;
+  a.nDir = nD;
+  a.nc = h->nc;
+  a.xyRegular = h->xyRegular;
+  a.trackByComponent = byComp && nD;
+  a.numPhotons = (float)src.n;
+  a.xe = h->d_xe;
+  a.ye = h->d_ye;
+  a.ze = h->d_ze;
+  a.fluxUp = h->d_fluxUp;
+  a.fluxDown = h->d_fluxDown;
+  a.fluxAbs = h->d_fluxAbs;
+  a.volAbs = h->d_volAbs;
+  a.intensity = h->d_intensity;
+  a.intByComp = h->d_intByComp;
+  k_normalize<<<(unsigned)((ncol + 127) / 128), 128, 0, h->stream>>>(a);
+  h->otherLaunches++;
+  CUDA_OK(h, cudaGetLastError());
+  return I3RC_SUCCESS;
+}
+
+int prepare_compute(i3rc_integrator* h, const i3rc_photon_source* src, SourceDev& sd) {
+  if (!h || !h->readyToCompute) {
+    if (h) h->message = "computeRadiativeTransfer: problem not completely specified.";
+    return I3RC_FAILURE;
+  }
+  CUDA_OK(h, cudaSetDevice(h->device));
+  int rc = validate_source(h, src);
+  if (rc != I3RC_SUCCESS) return rc;
+  if (!h->useRayTracing && !(h->maxExt > 0.0f))
+    return fail(h, "computeRadiativeTransfer: maximum cross-section needs a domain with extinction > 0.");
+  rc = tabulate(h);
+  if (rc != I3RC_SUCCESS) return rc;
+  return fill_source(h, src, sd);
+}
+
+int fetch_counters(i3rc_integrator* h) {
+  unsigned long long c[CNT_N];
+  CUDA_OK(h, cudaMemcpyAsync(c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  i3rc_counters& o = h->counters;
+  o.photons = c[CNT_PHOTONS];
+  o.bad = c[CNT_BAD];
+  o.crossings_photon = c[CNT_CROSS_PH];
+  o.crossings_intensity = c[CNT_CROSS_LE];
+  o.collisions = c[CNT_COLL];
+  o.absorptions = c[CNT_ABS];
+  o.contributions = c[CNT_CONTRIB];
+  o.exits_top = c[CNT_TOP];
+  o.surface_hits = c[CNT_SURF];
+  o.rng_draws = c[CNT_RNG];
+  o.roulette_kills = c[CNT_KILL];
+  o.null_collisions = c[CNT_NULL];
+  return I3RC_SUCCESS;
+}
+
+void seed_to_key(const int32_t* seed, int nseed, uint32_t& k0, uint32_t& k1) {
+  k0 = nseed > 0 ? (uint32_t)seed[0] : 0u;
+  k1 = nseed > 1 ? (uint32_t)seed[1] : 0x9E3779B9u;
+  for (int i = 2; i < nseed; i++) {  // longer seed vectors are folded in
+    k0 = k0 * 0x01000193u ^ (uint32_t)seed[i];
+    k1 = (k1 << 5 | k1 >> 27) ^ (uint32_t)seed[i] * 0x85EBCA6Bu;
+  }
+}
+
+// packed layout of the batch-moment buffer (doubles); every block is [sum(x) | sum(x*x)]
+struct StatsLayout {
+  size_t mean[3], flux[3], prof, rad, mrad, vol, total;
+};
+StatsLayout stats_layout(const i3rc_integrator* h, int nD, bool withVolume) {
+  StatsLayout L;
+  size_t ncol = (size_t)h->nx * h->ny, o = 0;
+  for (int i = 0; i < 3; i++) {
+    L.mean[i] = o;
+    o += 2;
+  }
+  for (int i = 0; i < 3; i++) {
+    L.flux[i] = o;
+    o += 2 * ncol;
+  }
+  L.prof = o;
+  o += 2 * (size_t)h->nz;
+  L.rad = o;
+  o += 2 * ncol * nD;
+  L.mrad = o;
+  o += 2 * (size_t)nD;
+  L.vol = o;
+  if (withVolume) o += 2 * ncol * h->nz;
+  L.total = o;
+  return L;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* i3rc_version(void) { return "i3rc_b200 0.1.0 (sm_100a)"; }
+
+int i3rc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+int i3rc_set_device(int device) { return cudaSetDevice(device) == cudaSuccess ? I3RC_SUCCESS : I3RC_FAILURE; }
+
+const char* i3rc_last_message(const i3rc_integrator* h) { return h ? h->message.c_str() : g_message.c_str(); }
+
+int i3rc_new_Integrator(int nx, int ny, int nz, int nc, const float* xPos, const float* yPos, const float* zPos,
+                        const float* totalExt, const float* cumExt, const float* ssa, const int32_t* pfIndex,
+                        i3rc_integrator** out) {
+  if (out) *out = nullptr;
+  if (!have_device()) {
+    g_message = "new_Integrator: no CUDA device (the B200 integrator has no CPU fallback)";
+    return I3RC_FAILURE;
+  }
+  if (!out || nx < 1 || ny < 1 || nz < 1 || nc < 1 || !xPos || !yPos || !zPos || !totalExt || !cumExt || !ssa || !pfIndex ||
+      !valid_edges(xPos, nx) || !valid_edges(yPos, ny) || !valid_edges(zPos, nz)) {
+    g_message = "new_Integrator: Problems reading domain.";
+    return I3RC_FAILURE;
+  }
+  i3rc_integrator* h = make_handle();
+  h->nx = nx;
+  h->ny = ny;
+  h->nz = nz;
+  h->nc = nc;
+  h->xe.assign(xPos, xPos + nx + 1);
+  h->ye.assign(yPos, yPos + ny + 1);
+  h->ze.assign(zPos, zPos + nz + 1);
+  size_t ncell = (size_t)nx * ny * nz;
+  int rc = I3RC_SUCCESS;
+  if (upload(&h->d_ext, totalExt, ncell, h->stream) != cudaSuccess || upload(&h->d_cum, cumExt, ncell * nc, h->stream) != cudaSuccess ||
+      upload(&h->d_ssa, ssa, ncell * nc, h->stream) != cudaSuccess || upload(&h->d_pf, pfIndex, ncell * nc, h->stream) != cudaSuccess)
+    rc = fail(h, "new_Integrator: out of device memory");
+  if (rc == I3RC_SUCCESS) rc = finish_new_integrator(h);
+  if (rc == I3RC_FAILURE) {
+    g_message = h->message;
+    i3rc_finalize_Integrator(h);
+    return rc;
+  }
+  *out = h;
+  return rc;
+}
+
+int i3rc_new_Integrator_components(int nx, int ny, int nz, const float* xPos, const float* yPos, const float* zPos,
+                                   int nc, const i3rc_component* comps, i3rc_integrator** out) {
+  if (out) *out = nullptr;
+  if (!have_device()) {
+    g_message = "new_Integrator: no CUDA device (the B200 integrator has no CPU fallback)";
+    return I3RC_FAILURE;
+  }
+  if (!out || nx < 1 || ny < 1 || nz < 1 || nc < 1 || !comps || !xPos || !yPos || !zPos || !valid_edges(xPos, nx) ||
+      !valid_edges(yPos, ny) || !valid_edges(zPos, nz)) {
+    g_message = "new_Integrator: Problems reading domain.";
+    return I3RC_FAILURE;
+  }
+  for (int c = 0; c < nc; c++)
+    if (comps[c].z_level_base < 1 || comps[c].z_level_base + comps[c].nz - 1 > nz || !comps[c].extinction ||
+        !comps[c].ssa || !comps[c].phase_index) {
+      g_message = "getOpticalPropertiesByComponent: component does not conform to the domain.";
+      return I3RC_FAILURE;
+    }
+  i3rc_integrator* h = make_handle();
+  h->nx = nx;
+  h->ny = ny;
+  h->nz = nz;
+  h->nc = nc;
+  h->xe.assign(xPos, xPos + nx + 1);
+  h->ye.assign(yPos, yPos + ny + 1);
+  h->ze.assign(zPos, zPos + nz + 1);
+  size_t ncell = (size_t)nx * ny * nz, ncol = (size_t)nx * ny;
+  int rc = I3RC_SUCCESS;
+  std::vector<ComponentDev> cd(nc);
+  std::vector<void*> temps;
+  auto body = [&]() -> int {
+    CUDA_OK(h, cudaMalloc(&h->d_ext, sizeof(float) * ncell));
+    CUDA_OK(h, cudaMalloc(&h->d_cum, sizeof(float) * ncell * nc));
+    CUDA_OK(h, cudaMalloc(&h->d_ssa, sizeof(float) * ncell * nc));
+    CUDA_OK(h, cudaMalloc(&h->d_pf, sizeof(int) * ncell * nc));
+    for (int c = 0; c < nc; c++) {
+      size_t n = (comps[c].horizontally_uniform ? 1 : ncol) * (size_t)comps[c].nz;
+      float *e = nullptr, *s = nullptr;
+      int* f = nullptr;
+      CUDA_OK(h, upload(&e, comps[c].extinction, n, h->stream));
+      temps.push_back(e);
+      CUDA_OK(h, upload(&s, comps[c].ssa, n, h->stream));
+      temps.push_back(s);
+      CUDA_OK(h, upload(&f, (const int*)comps[c].phase_index, n, h->stream));
+      temps.push_back(f);
+      cd[c] = ComponentDev{e, s, f, comps[c].horizontally_uniform, comps[c].z_level_base - 1, comps[c].nz};
+    }
+    ComponentDev* d_cd = nullptr;
+    CUDA_OK(h, upload(&d_cd, cd.data(), cd.size(), h->stream));
+    temps.push_back(d_cd);
+    k_expand_components<<<(unsigned)((ncell + 255) / 256), 256, 0, h->stream>>>(nx, ny, nz, nc, d_cd, h->d_ext, h->d_cum,
+                                                                               h->d_ssa, h->d_pf);
+    h->otherLaunches++;
+    CUDA_OK(h, cudaGetLastError());
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return I3RC_SUCCESS;
+  };
+  rc = body();
+  for (void* t : temps) cudaFree(t);
+  if (rc == I3RC_SUCCESS) rc = finish_new_integrator(h);
+  if (rc == I3RC_SUCCESS)
+    for (int c = 0; c < nc && rc != I3RC_FAILURE; c++) rc = i3rc_set_phase_table(h, c, &comps[c].table);
+  if (rc == I3RC_FAILURE) {
+    g_message = h->message;
+    i3rc_finalize_Integrator(h);
+    return rc;
+  }
+  *out = h;
+  return rc;
+}
+
+int i3rc_set_phase_table(i3rc_integrator* h, int comp, const i3rc_phase_table* t) {
+  if (!h) return I3RC_FAILURE;
+  if (comp < 0 || comp >= h->nc || !t) return fail(h, "set_phase_table: no such component");
+  if (t->n_entries < 1) return fail(h, "set_phase_table: phase function table is not ready.");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  HostTable& o = h->tables[comp];
+  free_table(o);
+  o = HostTable();
+  o.kind = t->kind;
+  o.nEntries = t->n_entries;
+  o.nodesPerEntry.resize(t->n_entries);
+  if (t->kind == 1) {
+    if (!t->coef_offsets) return fail(h, "set_phase_table: Legendre table without offsets");
+    o.offsets.assign(t->coef_offsets, t->coef_offsets + t->n_entries + 1);
+    int total = o.offsets.back();
+    if (total > 0 && !t->coefs) return fail(h, "set_phase_table: Legendre table without coefficients");
+    o.coefs.assign(t->coefs, t->coefs + total);
+    if (o.coefs.empty()) o.coefs.push_back(0.0f);
+    for (int e = 0; e < t->n_entries; e++) {
+      int nm = o.offsets[e + 1] - o.offsets[e];
+      if (nm < 0) return fail(h, "set_phase_table: offsets must be increasing");
+      if (nm > 1 && (o.coefs[o.offsets[e]] > 1.0f || o.coefs[o.offsets[e]] < -1.0f))
+        return fail(h, "newPhaseFunction: Asymmetery parameter out of bounds.");
+      o.nodesPerEntry[e] = std::max(nm, 2);
+      o.maxNodes = std::max(o.maxNodes, o.nodesPerEntry[e]);
+    }
+    CUDA_OK(h, upload(&o.d_offsets, o.offsets.data(), o.offsets.size(), h->stream));
+    CUDA_OK(h, upload(&o.d_coefs, o.coefs.data(), o.coefs.size(), h->stream));
+  } else if (t->kind == 2) {
+    int n = t->n_angles;
+    if (n < 2 || !t->angles || !t->values) return fail(h, "newPhaseFunctionTable: Number of scattering angles and phase function values must match.");
+    const float pi = 3.141592654f;
+    for (int i = 0; i < n; i++)
+      if (t->angles[i] < 0.0f || t->angles[i] > pi) return fail(h, "newPhaseFunctionTable: ScatteringAngle out of bounds.");
+    if (fabsf(t->angles[0]) > h_spacing(0.0f)) return fail(h, "newPhaseFunctionTable: First scattering angle must be min value");
+    if (fabsf(t->angles[n - 1] - pi) > h_spacing(pi)) return fail(h, "newPhaseFunctionTable: Last scattering angle must be max value");
+    for (int i = 0; i + 1 < n; i++)
+      if (!(t->angles[i + 1] - t->angles[i] > 0.0f)) return fail(h, "newPhaseFunctionTable: Scattering angle must be increasing, unique.");
+    for (size_t i = 0; i < (size_t)n * t->n_entries; i++)
+      if (t->values[i] < 0.0f) return fail(h, "newPhaseFunctionTable: Negative phase function values supplied.");
+    o.nAngles = n;
+    o.angles.assign(t->angles, t->angles + n);
+    o.values.assign(t->values, t->values + (size_t)n * t->n_entries);
+    for (int e = 0; e < t->n_entries; e++) o.nodesPerEntry[e] = n;
+    o.maxNodes = n;
+    CUDA_OK(h, upload(&o.d_angles, o.angles.data(), o.angles.size(), h->stream));
+    CUDA_OK(h, upload(&o.d_values, o.values.data(), o.values.size(), h->stream));
+    // normalised by the constructor and again by the copy the integrator keeps
+    // (scatteringPhaseFunctions.f95:322-325, 433; opticalProperties.f95:525)
+    CUDA_OK(h, normalize_tabulated(o.d_angles, o.d_values, n, t->n_entries, 2, h->stream));
+    h->otherLaunches += 2;
+  } else {
+    return fail(h, "set_phase_table: unknown table kind");
+  }
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  free_matrix(h->inv[comp]);
+  free_matrix(h->fwd[comp]);
+  free_matrix(h->fwdOrig[comp]);
+  h->tableDescDirty = true;
+  h->message.clear();
+  return I3RC_SUCCESS;
+}
+
+void i3rc_finalize_Integrator(i3rc_integrator* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  i3rc_comm_finalize(h);
+  dfree(h->d_xe);
+  dfree(h->d_ye);
+  dfree(h->d_ze);
+  dfree(h->d_ext);
+  dfree(h->d_cum);
+  dfree(h->d_ssa);
+  dfree(h->d_pf);
+  dfree(h->d_surf_x);
+  dfree(h->d_surf_y);
+  dfree(h->d_surf_p);
+  for (auto& t : h->tables) free_table(t);
+  for (auto& m : h->inv) free_matrix(m);
+  for (auto& m : h->fwd) free_matrix(m);
+  for (auto& m : h->fwdOrig) free_matrix(m);
+  dfree(h->d_tableDesc);
+  dfree(h->d_dirs);
+  dfree(h->d_fluxUp);
+  dfree(h->d_fluxDown);
+  dfree(h->d_fluxAbs);
+  dfree(h->d_volAbs);
+  dfree(h->d_intensity);
+  dfree(h->d_intByComp);
+  dfree(h->d_excess);
+  dfree(h->d_counters);
+  dfree(h->d_next);
+  dfree(h->d_scratch);
+  dfree(h->d_fscratch);
+  dfree(h->d_srcArrays);
+  dfree(h->d_stats);
+  for (auto e : h->ev) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int i3rc_isReady_Integrator(const i3rc_integrator* h) { return h && h->readyToCompute; }
+
+int i3rc_specifyParameters(i3rc_integrator* h, const i3rc_params* p) {
+  if (!h || !p) return I3RC_FAILURE;
+  const uint32_t m = p->present;
+  auto has = [m](uint32_t b) { return (m & b) != 0; };
+  bool warn = false, failed = false;
+  auto W = [&](const char* s) {
+    h->message = s;
+    warn = true;
+  };
+  auto F = [&](const char* s) {
+    h->message = s;
+    failed = true;
+  };
+  // MCRT:872-947
+  if (has(I3RC_P_surfaceBDRF) && has(I3RC_P_surfaceAlbedo)) F("specifyParameters: only one surface specification can be provided");
+  if (has(I3RC_P_surfaceAlbedo) && (p->surfaceAlbedo > 1.0f || p->surfaceAlbedo < 0.0f)) F("specifyParameters: surface albedo out of range.");
+  if (has(I3RC_P_surfaceBDRF) && !(p->surf_x && p->surf_y && p->surf_params && p->surf_nx > 0 && p->surf_ny > 0))
+    F("specifyParameters: surface description isn't valid.");
+  if (has(I3RC_P_minForwardTableSize) && p->minForwardTableSize < 9001)
+    W("specifyParameters: minForwardTableSize less than default. Value ignored.");
+  if (has(I3RC_P_minInverseTableSize) && p->minInverseTableSize < 9001)
+    W("specifyParameters: minInverseTableSize less than default. Value ignored.");
+  if (has(I3RC_P_hybridPhaseFunWidth) && (p->hybridPhaseFunWidth > 30.0f || p->hybridPhaseFunWidth < 0.0f))
+    W("specifyParameters: hybridPhaseFunWidth out of range (0 to 30degrees).Using default (7)");
+  if (has(I3RC_P_numOrdersOrigPhaseFunIntenCalcs) && p->numOrdersOrigPhaseFunIntenCalcs < 0)
+    W("specifyParameters: numOrdersExactPhaseFunIntenCalcs less than 0.Using default (0)");
+  if (has(I3RC_P_maxIntensityContribution) && p->maxIntensityContribution <= 0.0f)
+    W("specifyParameters: maxIntensityContribution <= 0. Value is unchanged.");
+  if (has(I3RC_P_intensityMus) != has(I3RC_P_intensityPhis))
+    F("specifyParameters: Both or neither of intensityMus and intensityPhis must be supplied");
+  if (has(I3RC_P_intensityMus) && !failed) {
+    if (p->numIntensityDirections < 1 || p->numIntensityDirections > MAX_DIRS || !p->intensityMus || !p->intensityPhis) {
+      F("specifyParameters: between 1 and 32 intensity directions are supported");
+    } else {
+      for (int i = 0; i < p->numIntensityDirections; i++) {
+        if (p->intensityMus[i] < -1.0f || p->intensityMus[i] > 1.0f) F("specifyParameters: intensityMus must be between -1 and 1");
+        if (fabsf(p->intensityMus[i]) < F_TINY) F("specifyParameters: intensityMus can't be 0 (directly sideways)");
+        if (p->intensityPhis[i] < 0.0f || p->intensityPhis[i] > 360.0f) F("specifyParameters: intensityPhis must be between 0 and 360");
+      }
+    }
+  }
+  if (has(I3RC_P_computeIntensity)) {
+    if (!p->computeIntensity && has(I3RC_P_intensityMus))
+      W("specifyParameters: intensity directions *and* computeIntensity set to false.Will compute intensity at given angles.");
+    if (p->computeIntensity && !has(I3RC_P_intensityMus) && h->dirs.empty())
+      F("specifyParameters: Can't compute intensity without specifying directions.");
+  }
+  if (failed) return I3RC_FAILURE;
+  CUDA_OK(h, cudaSetDevice(h->device));
+
+  // MCRT:950-1067
+  if (has(I3RC_P_surfaceAlbedo)) {
+    h->surfaceAlbedo = p->surfaceAlbedo;
+    h->useSurfaceBDRF = false;
+  } else if (has(I3RC_P_surfaceBDRF)) {
+    h->surf_nx = p->surf_nx;
+    h->surf_ny = p->surf_ny;
+    h->surf_x.assign(p->surf_x, p->surf_x + p->surf_nx + 1);
+    h->surf_y.assign(p->surf_y, p->surf_y + p->surf_ny + 1);
+    h->surf_p.assign(p->surf_params, p->surf_params + (size_t)p->surf_nx * p->surf_ny);
+    CUDA_OK(h, upload(&h->d_surf_x, h->surf_x.data(), h->surf_x.size(), h->stream));
+    CUDA_OK(h, upload(&h->d_surf_y, h->surf_y.data(), h->surf_y.size(), h->stream));
+    CUDA_OK(h, upload(&h->d_surf_p, h->surf_p.data(), h->surf_p.size(), h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    h->useSurfaceBDRF = true;
+  }
+  if (has(I3RC_P_useRayTracing)) h->useRayTracing = p->useRayTracing != 0;
+  if (has(I3RC_P_minForwardTableSize)) h->minForwardTableSize = std::max(p->minForwardTableSize, 9001);
+  if (has(I3RC_P_minInverseTableSize)) h->minInverseTableSize = std::max(p->minInverseTableSize, 9001);
+  if (has(I3RC_P_useRussianRoulette)) h->useRussianRoulette = p->useRussianRoulette != 0;
+  if (has(I3RC_P_useRussianRouletteForIntensity)) h->useRRIntensity = p->useRussianRouletteForIntensity != 0;
+  if (has(I3RC_P_zetaMin)) {
+    if (p->zetaMin < 0.0f) {
+      W("specifyParameters: zetaMin must be >= 0. Value is unchanged.");
+    } else {
+      h->zetaMin = p->zetaMin;
+      if (p->zetaMin > 1.0f) W("specifyParameters: zetaMin > 1. That's kind of large.");
+    }
+  }
+  if (has(I3RC_P_useHybridPhaseFunsForIntenCalcs)) {
+    bool v = p->useHybridPhaseFunsForIntenCalcs != 0;
+    if (v != h->useHybrid)  // the forward tables depend on it: re-tabulate
+      for (auto& mtx : h->fwd) free_matrix(mtx);
+    h->useHybrid = v;
+  }
+  if (has(I3RC_P_hybridPhaseFunWidth)) {
+    if (p->hybridPhaseFunWidth > 0.0f && p->hybridPhaseFunWidth < 30.0f)
+      h->hybridWidth = p->hybridPhaseFunWidth;
+    else
+      h->hybridWidth = 7.0f;
+    for (auto& mtx : h->fwd) free_matrix(mtx);  // MCRT:996-1004: re-tabulate
+    h->tableDescDirty = true;
+  }
+  if (has(I3RC_P_numOrdersOrigPhaseFunIntenCalcs))
+    h->numOrdersOrig = p->numOrdersOrigPhaseFunIntenCalcs >= 0 ? p->numOrdersOrigPhaseFunIntenCalcs : 0;
+  if (has(I3RC_P_limitIntensityContributions)) h->limitContrib = p->limitIntensityContributions != 0;
+  if (has(I3RC_P_maxIntensityContribution) && p->maxIntensityContribution > 0.0f) h->maxContrib = p->maxIntensityContribution;
+  size_t ncol = (size_t)h->nx * h->ny;
+  if (has(I3RC_P_intensityMus)) {  // MCRT:1026-1045
+    h->nDir = p->numIntensityDirections;
+    h->dirs.assign((size_t)h->nDir * DIR_STRIDE, 0.0f);
+    for (int i = 0; i < h->nDir; i++) {
+      float mu = p->intensityMus[i], phi = p->intensityPhis[i] * F_PI / 180.0f;
+      float st = sqrtf(1.0f - mu * mu);
+      float* d = &h->dirs[(size_t)i * DIR_STRIDE];
+      d[0] = st * cosf(phi);
+      d[1] = st * sinf(phi);
+      d[2] = mu;
+      for (int a = 0; a < 3; a++) d[3 + a] = fabsf(d[a]) >= 2.0f * F_TINY ? 1.0f / fabsf(d[a]) : INFINITY;
+      d[6] = 4.0f * F_PI * fabsf(mu);
+    }
+    CUDA_OK(h, upload(&h->d_dirs, h->dirs.data(), h->dirs.size(), h->stream));
+    dfree(h->d_intensity);
+    dfree(h->d_intByComp);
+    CUDA_OK(h, cudaMalloc(&h->d_intensity, sizeof(float) * ncol * h->nDir));
+    CUDA_OK(h, cudaMalloc(&h->d_intByComp, sizeof(float) * ncol * h->nDir * (h->nc + 1)));
+    CUDA_OK(h, cudaMemsetAsync(h->d_intensity, 0, sizeof(float) * ncol * h->nDir, h->stream));
+    CUDA_OK(h, cudaMemsetAsync(h->d_intByComp, 0, sizeof(float) * ncol * h->nDir * (h->nc + 1), h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    h->computeIntensity = true;
+  }
+  if (has(I3RC_P_computeIntensity) && !p->computeIntensity && !has(I3RC_P_intensityMus)) {  // MCRT:1052-1057
+    h->dirs.clear();
+    h->nDir = 0;
+    dfree(h->d_dirs);
+    dfree(h->d_intensity);
+    dfree(h->d_intByComp);
+    h->computeIntensity = false;
+  }
+  if (h->computeIntensity && h->limitContrib) {  // MCRT:1060-1064
+    dfree(h->d_excess);
+    CUDA_OK(h, cudaMalloc(&h->d_excess, sizeof(float) * (size_t)(h->nc + 1) * h->nDir));
+  }
+  if (!warn) h->message.clear();
+  return warn ? I3RC_WARNING : I3RC_SUCCESS;
+}
+
+int i3rc_tabulate(i3rc_integrator* h) {
+  if (!h) return I3RC_FAILURE;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  return tabulate(h);
+}
+
+int i3rc_get_table(i3rc_integrator* h, int which, int comp, float* out, int* nSteps, int* nEntries) {
+  if (!h || comp < 0 || comp >= h->nc) return I3RC_FAILURE;
+  DevMatrix& m = which == 0 ? h->inv[comp] : which == 1 ? h->fwd[comp] : h->fwdOrig[comp];
+  if (!m.d) return fail(h, "get_table: table has not been tabulated");
+  if (nSteps) *nSteps = m.nSteps;
+  if (nEntries) *nEntries = m.nEntries;
+  if (out) {
+    CUDA_OK(h, cudaMemcpyAsync(out, m.d, sizeof(float) * (size_t)m.nSteps * m.nEntries, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  }
+  return I3RC_SUCCESS;
+}
+
+int i3rc_set_inverse_table(i3rc_integrator* h, int comp, int nSteps, int nEntries, const float* values) {
+  if (!h || comp < 0 || comp >= h->nc || nSteps < 2 || nEntries < 1 || !values) return I3RC_FAILURE;
+  free_matrix(h->inv[comp]);
+  CUDA_OK(h, upload(&h->inv[comp].d, values, (size_t)nSteps * nEntries, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  h->inv[comp].nSteps = nSteps;
+  h->inv[comp].nEntries = nEntries;
+  if (nSteps > h->minInverseTableSize) h->minInverseTableSize = nSteps;
+  h->tableDescDirty = true;
+  return I3RC_SUCCESS;
+}
+int i3rc_set_forward_table(i3rc_integrator* h, int comp, int nSteps, int nEntries, const float* tabulated,
+                           const float* original) {
+  if (!h || comp < 0 || comp >= h->nc || nSteps < 2 || nEntries < 1 || !tabulated) return I3RC_FAILURE;
+  free_matrix(h->fwd[comp]);
+  free_matrix(h->fwdOrig[comp]);
+  CUDA_OK(h, upload(&h->fwd[comp].d, tabulated, (size_t)nSteps * nEntries, h->stream));
+  CUDA_OK(h, upload(&h->fwdOrig[comp].d, original ? original : tabulated, (size_t)nSteps * nEntries, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  h->fwd[comp].nSteps = h->fwdOrig[comp].nSteps = nSteps;
+  h->fwd[comp].nEntries = h->fwdOrig[comp].nEntries = nEntries;
+  if (nSteps > h->minForwardTableSize) h->minForwardTableSize = nSteps;
+  h->tableDescDirty = true;
+  return I3RC_SUCCESS;
+}
+
+int i3rc_computeRadiativeTransfer(i3rc_integrator* h, const i3rc_photon_source* src, const int32_t* seed, int nseed) {
+  SourceDev sd;
+  int rc = prepare_compute(h, src, sd);
+  if (rc != I3RC_SUCCESS) return rc;
+  uint32_t k0, k1;
+  seed_to_key(seed, nseed, k0, k1);
+  CUDA_OK(h, cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * CNT_N, h->stream));
+  rc = run_one_batch(h, sd, k0, k1);
+  if (rc != I3RC_SUCCESS) return rc;
+  rc = fetch_counters(h);
+  if (rc != I3RC_SUCCESS) return rc;
+  if (h->counters.photons <= 0) return fail(h, "computeRadiativeTransfer: Didn't process any photons.");
+  h->message = "computeRadiativeTransfer: finished with photons";
+  return I3RC_SUCCESS;
+}
+
+int i3rc_reportResults(i3rc_integrator* h, float* meanFluxUp, float* meanFluxDown, float* meanFluxAbsorbed,
+                       float* fluxUp, float* fluxDown, float* fluxAbsorbed, float* absorbedProfile,
+                       float* volumeAbsorption, float* meanIntensity, float* intensity) {
+  if (!h || !h->readyToCompute) return I3RC_FAILURE;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  size_t ncol = (size_t)h->nx * h->ny, ncell = ncol * h->nz;
+  if ((meanIntensity || intensity) && !h->d_intensity) return fail(h, "reportResults: intensity information not available");
+  int nD = h->d_intensity ? h->nDir : 0;
+  int rows = 3 + h->nz + nD;
+  if (ensure_scratch(h, rows) != I3RC_SUCCESS || ensure_fscratch(h, rows) != I3RC_SUCCESS) return I3RC_FAILURE;
+  std::vector<float> host(rows, 0.0f);
+  bool needMeans = meanFluxUp || meanFluxDown || meanFluxAbsorbed || absorbedProfile || meanIntensity;
+  if (needMeans) {
+    k_slab_sums<<<1, 256, 0, h->stream>>>(h->d_fluxUp, ncol, h->d_scratch + 0);
+    k_slab_sums<<<1, 256, 0, h->stream>>>(h->d_fluxDown, ncol, h->d_scratch + 1);
+    k_slab_sums<<<1, 256, 0, h->stream>>>(h->d_fluxAbs, ncol, h->d_scratch + 2);
+    k_slab_sums<<<h->nz, 256, 0, h->stream>>>(h->d_volAbs, ncol, h->d_scratch + 3);
+    if (nD) k_slab_sums<<<nD, 256, 0, h->stream>>>(h->d_intensity, ncol, h->d_scratch + 3 + h->nz);
+    k_means_to_float<<<(rows + 127) / 128, 128, 0, h->stream>>>(h->d_scratch, rows, 1.0 / (double)ncol, h->d_fscratch);
+    h->otherLaunches += 6;
+    CUDA_OK(h, cudaMemcpyAsync(host.data(), h->d_fscratch, sizeof(float) * rows, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (fluxUp) CUDA_OK(h, cudaMemcpyAsync(fluxUp, h->d_fluxUp, sizeof(float) * ncol, cudaMemcpyDeviceToHost, h->stream));
+  if (fluxDown) CUDA_OK(h, cudaMemcpyAsync(fluxDown, h->d_fluxDown, sizeof(float) * ncol, cudaMemcpyDeviceToHost, h->stream));
+  if (fluxAbsorbed) CUDA_OK(h, cudaMemcpyAsync(fluxAbsorbed, h->d_fluxAbs, sizeof(float) * ncol, cudaMemcpyDeviceToHost, h->stream));
+  if (volumeAbsorption)
+    CUDA_OK(h, cudaMemcpyAsync(volumeAbsorption, h->d_volAbs, sizeof(float) * ncell, cudaMemcpyDeviceToHost, h->stream));
+  if (intensity)
+    CUDA_OK(h, cudaMemcpyAsync(intensity, h->d_intensity, sizeof(float) * ncol * nD, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  if (meanFluxUp) *meanFluxUp = host[0];
+  if (meanFluxDown) *meanFluxDown = host[1];
+  if (meanFluxAbsorbed) *meanFluxAbsorbed = host[2];
+  if (absorbedProfile) memcpy(absorbedProfile, host.data() + 3, sizeof(float) * h->nz);
+  if (meanIntensity) memcpy(meanIntensity, host.data() + 3 + h->nz, sizeof(float) * nD);
+  h->message.clear();
+  return I3RC_SUCCESS;
+}
+
+int i3rc_get_intensityByComponent(i3rc_integrator* h, float* out) {
+  if (!h || !h->d_intByComp || !(h->trackByComponent || h->limitContrib))
+    return h ? fail(h, "intensityByComponent is only tracked with limitIntensityContributions or tuning track_by_component=1") : I3RC_FAILURE;
+  size_t n = (size_t)h->nx * h->ny * h->nDir * (h->nc + 1);
+  CUDA_OK(h, cudaMemcpyAsync(out, h->d_intByComp, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return I3RC_SUCCESS;
+}
+
+void i3rc_get_counters(const i3rc_integrator* h, i3rc_counters* c) {
+  if (h && c) *c = h->counters;
+}
+
+int i3rc_copy_Integrator(const i3rc_integrator* s, i3rc_integrator** out) {
+  if (!s || !out) return I3RC_FAILURE;
+  *out = nullptr;
+  cudaSetDevice(s->device);
+  // rebuild from the device-resident dense arrays (a full copy, unlike MCRT:1082-1253 which forgets the
+  // intensity-limiting members: quirk Q6)
+  size_t ncell = (size_t)s->nx * s->ny * s->nz;
+  std::vector<float> te(ncell), ce(ncell * s->nc), sa(ncell * s->nc);
+  std::vector<int32_t> pf(ncell * s->nc);
+  cudaMemcpy(te.data(), s->d_ext, sizeof(float) * ncell, cudaMemcpyDeviceToHost);
+  cudaMemcpy(ce.data(), s->d_cum, sizeof(float) * ncell * s->nc, cudaMemcpyDeviceToHost);
+  cudaMemcpy(sa.data(), s->d_ssa, sizeof(float) * ncell * s->nc, cudaMemcpyDeviceToHost);
+  cudaMemcpy(pf.data(), s->d_pf, sizeof(int32_t) * ncell * s->nc, cudaMemcpyDeviceToHost);
+  i3rc_integrator* h = nullptr;
+  int rc = i3rc_new_Integrator(s->nx, s->ny, s->nz, s->nc, s->xe.data(), s->ye.data(), s->ze.data(), te.data(), ce.data(),
+                               sa.data(), pf.data(), &h);
+  if (rc == I3RC_FAILURE) return rc;
+  for (int c = 0; c < s->nc; c++) {
+    const HostTable& t = s->tables[c];
+    if (t.kind == 0) continue;
+    i3rc_phase_table pt{t.kind, t.nEntries, t.offsets.data(), t.coefs.data(), t.nAngles, t.angles.data(), t.values.data()};
+    i3rc_set_phase_table(h, c, &pt);
+  }
+  i3rc_params p;
+  memset(&p, 0, sizeof(p));
+  std::vector<float> mus(s->nDir), phis(s->nDir);
+  p.present = I3RC_P_minForwardTableSize | I3RC_P_minInverseTableSize | I3RC_P_useRayTracing | I3RC_P_useRussianRoulette |
+              I3RC_P_useRussianRouletteForIntensity | I3RC_P_zetaMin | I3RC_P_useHybridPhaseFunsForIntenCalcs |
+              I3RC_P_hybridPhaseFunWidth | I3RC_P_numOrdersOrigPhaseFunIntenCalcs | I3RC_P_limitIntensityContributions |
+              I3RC_P_maxIntensityContribution;
+  p.minForwardTableSize = s->minForwardTableSize;
+  p.minInverseTableSize = s->minInverseTableSize;
+  p.useRayTracing = s->useRayTracing;
+  p.useRussianRoulette = s->useRussianRoulette;
+  p.useRussianRouletteForIntensity = s->useRRIntensity;
+  p.zetaMin = s->zetaMin;
+  p.useHybridPhaseFunsForIntenCalcs = s->useHybrid;
+  p.hybridPhaseFunWidth = s->hybridWidth;
+  p.numOrdersOrigPhaseFunIntenCalcs = s->numOrdersOrig;
+  p.limitIntensityContributions = s->limitContrib;
+  p.maxIntensityContribution = s->maxContrib;
+  if (s->useSurfaceBDRF) {
+    p.present |= I3RC_P_surfaceBDRF;
+    p.surf_nx = s->surf_nx;
+    p.surf_ny = s->surf_ny;
+    p.surf_x = s->surf_x.data();
+    p.surf_y = s->surf_y.data();
+    p.surf_params = s->surf_p.data();
+  } else {
+    p.present |= I3RC_P_surfaceAlbedo;
+    p.surfaceAlbedo = s->surfaceAlbedo;
+  }
+  rc = i3rc_specifyParameters(h, &p);
+  if (rc != I3RC_FAILURE && s->computeIntensity && s->nDir > 0) {
+    // directions are stored as cosines; hand them over directly
+    h->nDir = s->nDir;
+    h->dirs = s->dirs;
+    size_t ncol = (size_t)h->nx * h->ny;
+    upload(&h->d_dirs, h->dirs.data(), h->dirs.size(), h->stream);
+    cudaMalloc(&h->d_intensity, sizeof(float) * ncol * h->nDir);
+    cudaMalloc(&h->d_intByComp, sizeof(float) * ncol * h->nDir * (h->nc + 1));
+    cudaMemsetAsync(h->d_intensity, 0, sizeof(float) * ncol * h->nDir, h->stream);
+    if (h->limitContrib) cudaMalloc(&h->d_excess, sizeof(float) * (size_t)(h->nc + 1) * h->nDir);
+    cudaStreamSynchronize(h->stream);
+    h->computeIntensity = true;
+  }
+  h->trackByComponent = s->trackByComponent;
+  h->blockSize = s->blockSize;
+  h->blocksPerSM = s->blocksPerSM;
+  h->kSteps = s->kSteps;
+  h->message.clear();
+  *out = h;
+  return I3RC_SUCCESS;
+}
+
+// ---- probes --------------------------------------------------------------------------------------------
+int i3rc_trace_rays(i3rc_integrator* h, int n, const float* pos, const float* dir, const float* tauLimit, float* tauOut,
+                    float* posOut, int32_t* idxOut) {
+  if (!h || !h->readyToCompute || n < 1) return I3RC_FAILURE;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  float *d_pos = nullptr, *d_dir = nullptr, *d_lim = nullptr, *d_tau = nullptr, *d_po = nullptr;
+  int* d_idx = nullptr;
+  int rc = [&]() -> int {
+    CUDA_OK(h, upload(&d_pos, pos, (size_t)3 * n, h->stream));
+    CUDA_OK(h, upload(&d_dir, dir, (size_t)3 * n, h->stream));
+    if (tauLimit) CUDA_OK(h, upload(&d_lim, tauLimit, (size_t)n, h->stream));
+    CUDA_OK(h, cudaMalloc(&d_tau, sizeof(float) * n));
+    CUDA_OK(h, cudaMalloc(&d_po, sizeof(float) * 3 * n));
+    CUDA_OK(h, cudaMalloc(&d_idx, sizeof(int) * 3 * n));
+    Problem p;
+    fill_problem(h, p);
+    k_trace_rays<<<(n + 127) / 128, 128, 0, h->stream>>>(p, n, d_pos, d_dir, d_lim, d_tau, d_po, d_idx);
+    h->otherLaunches++;
+    CUDA_OK(h, cudaGetLastError());
+    CUDA_OK(h, cudaMemcpyAsync(tauOut, d_tau, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (posOut) CUDA_OK(h, cudaMemcpyAsync(posOut, d_po, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
+    if (idxOut) CUDA_OK(h, cudaMemcpyAsync(idxOut, d_idx, sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return I3RC_SUCCESS;
+  }();
+  dfree(d_pos);
+  dfree(d_dir);
+  dfree(d_lim);
+  dfree(d_tau);
+  dfree(d_po);
+  dfree(d_idx);
+  return rc;
+}
+
+static int probe_1d(i3rc_integrator* h, const float* table, int nSteps, int n, const float* in, float* out, bool inverse) {
+  float *d_in = nullptr, *d_out = nullptr;
+  int rc = [&]() -> int {
+    CUDA_OK(h, upload(&d_in, in, (size_t)n, h->stream));
+    CUDA_OK(h, cudaMalloc(&d_out, sizeof(float) * n));
+    if (inverse)
+      k_sample_angles<<<(n + 127) / 128, 128, 0, h->stream>>>(table, nSteps, n, d_in, d_out);
+    else
+      k_lookup_phase<<<(n + 127) / 128, 128, 0, h->stream>>>(table, nSteps, n, d_in, d_out);
+    h->otherLaunches++;
+    CUDA_OK(h, cudaGetLastError());
+    CUDA_OK(h, cudaMemcpyAsync(out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return I3RC_SUCCESS;
+  }();
+  dfree(d_in);
+  dfree(d_out);
+  return rc;
+}
+int i3rc_sample_scattering_angles(i3rc_integrator* h, int comp, int entry, int n, const float* xi, float* theta) {
+  if (!h || comp < 0 || comp >= h->nc || !h->inv[comp].d || entry < 0 || entry >= h->inv[comp].nEntries) return I3RC_FAILURE;
+  return probe_1d(h, h->inv[comp].d + (size_t)entry * h->inv[comp].nSteps, h->inv[comp].nSteps, n, xi, theta, true);
+}
+int i3rc_lookup_phase_function(i3rc_integrator* h, int comp, int entry, int which, int n, const float* angles, float* out) {
+  if (!h || comp < 0 || comp >= h->nc) return I3RC_FAILURE;
+  DevMatrix& m = which == 1 ? h->fwd[comp] : h->fwdOrig[comp];
+  if (!m.d || entry < 0 || entry >= m.nEntries) return I3RC_FAILURE;
+  return probe_1d(h, m.d + (size_t)entry * m.nSteps, m.nSteps, n, angles, out, false);
+}
+
+// ---- batch moments -------------------------------------------------------------------------------------
+int i3rc_stats_reset(i3rc_integrator* h, int with_volume) {
+  if (!h || !h->readyToCompute) return I3RC_FAILURE;
+  CUDA_OK(h, cudaSetDevice(h->device));
+  int nD = h->computeIntensity ? h->nDir : 0;
+  StatsLayout L = stats_layout(h, nD, with_volume != 0);
+  if (h->statsN != L.total) {
+    dfree(h->d_stats);
+    CUDA_OK(h, cudaMalloc(&h->d_stats, sizeof(double) * L.total));
+    h->statsN = L.total;
+  }
+  h->statsVolume = with_volume != 0;
+  h->statsNDir = nD;
+  CUDA_OK(h, cudaMemsetAsync(h->d_stats, 0, sizeof(double) * L.total, h->stream));
+  return I3RC_SUCCESS;
+}
+
+int i3rc_stats_accumulate(i3rc_integrator* h) {
+  if (!h || !h->d_stats) return h ? fail(h, "stats_accumulate: call stats_reset first") : I3RC_FAILURE;
+  int nD = h->statsNDir;
+  StatsLayout L = stats_layout(h, nD, h->statsVolume);
+  size_t ncol = (size_t)h->nx * h->ny, ncell = ncol * h->nz;
+  int rows = 3 + h->nz + nD;
+  if (ensure_scratch(h, rows) != I3RC_SUCCESS) return I3RC_FAILURE;
+  double* S = h->d_stats;
+  cudaStream_t st = h->stream;
+  k_slab_sums<<<1, 256, 0, st>>>(h->d_fluxUp, ncol, h->d_scratch + 0);
+  k_slab_sums<<<1, 256, 0, st>>>(h->d_fluxDown, ncol, h->d_scratch + 1);
+  k_slab_sums<<<1, 256, 0, st>>>(h->d_fluxAbs, ncol, h->d_scratch + 2);
+  k_slab_sums<<<h->nz, 256, 0, st>>>(h->d_volAbs, ncol, h->d_scratch + 3);
+  if (nD) k_slab_sums<<<nD, 256, 0, st>>>(h->d_intensity, ncol, h->d_scratch + 3 + h->nz);
+  double inv = 1.0 / (double)ncol;
+  for (int i = 0; i < 3; i++) k_moments_mean<<<1, 32, 0, st>>>(h->d_scratch + i, 1, inv, S + L.mean[i], S + L.mean[i] + 1);
+  k_moments_mean<<<(h->nz + 127) / 128, 128, 0, st>>>(h->d_scratch + 3, h->nz, inv, S + L.prof, S + L.prof + h->nz);
+  if (nD) k_moments_mean<<<1, 32, 0, st>>>(h->d_scratch + 3 + h->nz, nD, inv, S + L.mrad, S + L.mrad + nD);
+  unsigned gcol = (unsigned)((ncol + 255) / 256);
+  k_moments_f<<<gcol, 256, 0, st>>>(h->d_fluxUp, ncol, S + L.flux[0], S + L.flux[0] + ncol);
+  k_moments_f<<<gcol, 256, 0, st>>>(h->d_fluxDown, ncol, S + L.flux[1], S + L.flux[1] + ncol);
+  k_moments_f<<<gcol, 256, 0, st>>>(h->d_fluxAbs, ncol, S + L.flux[2], S + L.flux[2] + ncol);
+  if (nD) k_moments_f<<<(unsigned)((ncol * nD + 255) / 256), 256, 0, st>>>(h->d_intensity, ncol * nD, S + L.rad, S + L.rad + ncol * nD);
+  if (h->statsVolume) k_moments_f<<<(unsigned)((ncell + 255) / 256), 256, 0, st>>>(h->d_volAbs, ncell, S + L.vol, S + L.vol + ncell);
+  h->otherLaunches += 14;
+  CUDA_OK(h, cudaGetLastError());
+  return I3RC_SUCCESS;
+}
+
+int i3rc_stats_device_buffer(i3rc_integrator* h, void** dev_ptr, int64_t* n_doubles) {
+  if (!h || !h->d_stats) return I3RC_FAILURE;
+  if (dev_ptr) *dev_ptr = h->d_stats;
+  if (n_doubles) *n_doubles = (int64_t)h->statsN;
+  return I3RC_SUCCESS;
+}
+
+int i3rc_stats_report(i3rc_integrator* h, double solarFlux, int numBatches, const i3rc_stats_out* out) {
+  if (!h || !h->d_stats || !out) return I3RC_FAILURE;
+  if (numBatches < 2) return fail(h, "stats_report: at least two batches are needed (monteCarloDriver.f95:264)");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  int nD = h->statsNDir;
+  StatsLayout L = stats_layout(h, nD, h->statsVolume);
+  size_t ncol = (size_t)h->nx * h->ny, ncell = ncol * h->nz;
+  double* d_tmp = nullptr;
+  size_t maxBlock = std::max({ncol * (size_t)std::max(nD, 1), (size_t)h->nz, h->statsVolume ? ncell : (size_t)1, (size_t)8});
+  CUDA_OK(h, cudaMalloc(&d_tmp, sizeof(double) * 2 * maxBlock));
+  auto emit = [&](size_t off, size_t n, double* dst) -> int {
+    if (!dst || n == 0) return I3RC_SUCCESS;
+    k_stats_finish<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_stats + off, h->d_stats + off + n, n, solarFlux,
+                                                                      numBatches, d_tmp, d_tmp + n);
+    CUDA_OK(h, cudaMemcpyAsync(dst, d_tmp, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    h->otherLaunches++;
+    return I3RC_SUCCESS;
+  };
+  int rc = I3RC_SUCCESS;
+  double* means[3] = {out->meanFluxUp, out->meanFluxDown, out->meanFluxAbsorbed};
+  double* fluxes[3] = {out->fluxUp, out->fluxDown, out->fluxAbsorbed};
+  for (int i = 0; i < 3 && rc == I3RC_SUCCESS; i++) rc = emit(L.mean[i], 1, means[i]);
+  for (int i = 0; i < 3 && rc == I3RC_SUCCESS; i++) rc = emit(L.flux[i], ncol, fluxes[i]);
+  if (rc == I3RC_SUCCESS) rc = emit(L.prof, h->nz, out->absorbedProfile);
+  if (rc == I3RC_SUCCESS && nD) rc = emit(L.rad, ncol * nD, out->radiance);
+  if (rc == I3RC_SUCCESS && nD) rc = emit(L.mrad, nD, out->meanRadiance);
+  if (rc == I3RC_SUCCESS && h->statsVolume) rc = emit(L.vol, ncell, out->absorbedVolume);
+  cudaFree(d_tmp);
+  return rc;
+}
+
+int i3rc_run_batches(i3rc_integrator* h, const i3rc_photon_source* src, int32_t iseed, int seedOrder, int batchBegin,
+                     int nBatches) {
+  SourceDev sd;
+  int rc = prepare_compute(h, src, sd);
+  if (rc != I3RC_SUCCESS) return rc;
+  if (!h->d_stats) {
+    rc = i3rc_stats_reset(h, 0);
+    if (rc != I3RC_SUCCESS) return rc;
+  }
+  CUDA_OK(h, cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * CNT_N, h->stream));
+  for (int b = 0; b < nBatches; b++) {
+    int32_t seed[2];
+    seed[0] = seedOrder == 0 ? iseed : batchBegin + b;
+    seed[1] = seedOrder == 0 ? batchBegin + b : iseed;
+    uint32_t k0, k1;
+    seed_to_key(seed, 2, k0, k1);
+    rc = run_one_batch(h, sd, k0, k1);
+    if (rc != I3RC_SUCCESS) return rc;
+    rc = i3rc_stats_accumulate(h);
+    if (rc != I3RC_SUCCESS) return rc;
+  }
+  return fetch_counters(h);
+}
+
+// ---- NCCL (dlopen'ed so that the library neither links NCCL nor clashes with the copy torch bundles) -------
+namespace {
+struct NcclId {
+  char internal[128];
+};
+typedef int (*fn_getid)(NcclId*);
+typedef int (*fn_init)(void**, int, NcclId, int);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_destroy)(void*);
+void* nccl_lib() {
+  static void* lib = nullptr;
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  return lib;
+}
+}  // namespace
+
+int i3rc_comm_unique_id(char* id128) {
+  void* lib = nccl_lib();
+  if (!lib || !id128) {
+    g_message = "comm_unique_id: libnccl.so.2 not found";
+    return I3RC_FAILURE;
+  }
+  fn_getid f = (fn_getid)dlsym(lib, "ncclGetUniqueId");
+  NcclId id;
+  if (!f || f(&id) != 0) return I3RC_FAILURE;
+  memcpy(id128, id.internal, 128);
+  return I3RC_SUCCESS;
+}
+int i3rc_comm_init(i3rc_integrator* h, int nRanks, int rank, const char* id128) {
+  if (!h || !id128) return I3RC_FAILURE;
+  void* lib = nccl_lib();
+  if (!lib) return fail(h, "comm_init: libnccl.so.2 not found");
+  fn_init f = (fn_init)dlsym(lib, "ncclCommInitRank");
+  if (!f) return fail(h, "comm_init: ncclCommInitRank not found");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  NcclId id;
+  memcpy(id.internal, id128, 128);
+  void* comm = nullptr;
+  if (f(&comm, nRanks, id, rank) != 0) return fail(h, "comm_init: ncclCommInitRank failed");
+  h->nccl = comm;
+  h->ncclLib = lib;
+  return I3RC_SUCCESS;
+}
+int i3rc_stats_allreduce(i3rc_integrator* h) {
+  if (!h || !h->d_stats) return I3RC_FAILURE;
+  if (!h->nccl) return I3RC_SUCCESS;  // single process: identity, like multipleProcesses_nompi.f95
+  fn_allreduce f = (fn_allreduce)dlsym(h->ncclLib, "ncclAllReduce");
+  if (!f) return fail(h, "stats_allreduce: ncclAllReduce not found");
+  // ncclFloat64 = 8, ncclSum = 0
+  if (f(h->d_stats, h->d_stats, h->statsN, 8, 0, h->nccl, h->stream) != 0) return fail(h, "stats_allreduce: ncclAllReduce failed");
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return I3RC_SUCCESS;
+}
+int i3rc_comm_finalize(i3rc_integrator* h) {
+  if (!h || !h->nccl) return I3RC_SUCCESS;
+  fn_destroy f = (fn_destroy)dlsym(h->ncclLib, "ncclCommDestroy");
+  if (f) f(h->nccl);
+  h->nccl = nullptr;
+  return I3RC_SUCCESS;
+}
+
+// ---- streams, timing, tuning ---------------------------------------------------------------------------
+int i3rc_synchronize(i3rc_integrator* h) {
+  if (!h) return I3RC_FAILURE;
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  return I3RC_SUCCESS;
+}
+void* i3rc_stream(i3rc_integrator* h) { return h ? (void*)h->stream : nullptr; }
+
+int i3rc_get_timing(i3rc_integrator* h, double* trace_ms, int64_t* trace_launches, int64_t* other_launches) {
+  if (!h) return I3RC_FAILURE;
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i + 1 < h->evUsed; i += 2) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) h->traceMs += ms;
+  }
+  h->evUsed = 0;
+  if (trace_ms) *trace_ms = h->traceMs;
+  if (trace_launches) *trace_launches = h->traceLaunches;
+  if (other_launches) *other_launches = h->otherLaunches;
+  return I3RC_SUCCESS;
+}
+int i3rc_reset_timing(i3rc_integrator* h) {
+  if (!h) return I3RC_FAILURE;
+  CUDA_OK(h, cudaStreamSynchronize(h->stream));
+  h->evUsed = 0;
+  h->traceMs = 0.0;
+  h->traceLaunches = h->otherLaunches = 0;
+  return I3RC_SUCCESS;
+}
+int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
+  if (!h || !key) return I3RC_FAILURE;
+  std::string k(key);
+  if (k == "block_size" && (value == 64 || value == 128 || value == 256))
+    h->blockSize = value;
+  else if (k == "blocks_per_sm" && value >= 0)
+    h->blocksPerSM = value;
+  else if (k == "steps_per_event_phase" && value >= 1)
+    h->kSteps = value;
+  else if (k == "track_by_component")
+    h->trackByComponent = value != 0;
+  else
+    return fail(h, "set_tuning: unknown key or bad value");
+  return I3RC_SUCCESS;
+}
+
+}  // extern "C"

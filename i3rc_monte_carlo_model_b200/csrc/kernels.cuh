@@ -1,0 +1,254 @@
+// __global__ kernels of the integrator (sm_100a).  The photon transport kernel is the hot path; the rest are
+// the small setup / normalisation / reporting kernels around it.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "transport.cuh"
+
+namespace i3rc {
+
+// ---- K1: persistent photon transport ------------------------------------------------------------------
+// grid = (#SMs x resident blocks), every thread owns one photon slot and refills it from the device photon
+// counter (one warp-aggregated atomicAdd per refill round).  Between events all lanes of a warp execute the
+// same DDA cell-crossing step; `kSteps` crossings are taken between two event phases.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_transport(const Problem p, const int kSteps) {
+  Lane L;
+#pragma unroll
+  for (int i = 0; i < CNT_N; i++) L.cnt[i] = 0;
+  L.active = 0;
+  L.done = DONE_RUN;
+  L.mode = MODE_PHOTON;
+  bool exhausted = false;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    // refill finished slots
+    bool need = !L.active && !exhausted;
+    unsigned m = __ballot_sync(full, need);
+    if (m) {
+      unsigned long long base = 0;
+      int leader = __ffs(m) - 1;
+      if (lane == leader) base = atomicAdd(p.nextPhoton, (unsigned long long)__popc(m));
+      base = __shfl_sync(full, base, leader);
+      if (need) {
+        long long id = (long long)base + __popc(m & ((1u << lane) - 1u));
+        if (id < p.src.n)
+          init_photon(p, L, id);
+        else
+          exhausted = true;
+      }
+    }
+    if (!__any_sync(full, L.active)) break;
+    // cell crossings
+    for (int k = 0; k < kSteps; k++) {
+      bool stepping = L.active && L.done == DONE_RUN;
+      if (stepping) dda_step(p, L);
+      if (!__any_sync(full, L.active && L.done == DONE_RUN)) break;
+    }
+    // events
+    if (L.active && L.done != DONE_RUN) handle_event(p, L);
+  }
+  // flush the per-thread counters: warp reduce, one atomic per warp and counter
+#pragma unroll
+  for (int i = 0; i < CNT_N; i++) {
+    unsigned long long v = L.cnt[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(full, v, o);
+    if (lane == 0 && v) atomicAdd(p.counters + i, v);
+  }
+}
+
+// ---- probes: accumulateExtinctionAlongPath for explicit rays (deterministic sub-path parity) ---------------
+__global__ void k_trace_rays(const Problem p, int n, const float* __restrict__ pos, const float* __restrict__ dir,
+                             const float* __restrict__ tauLimit, float* __restrict__ tauOut,
+                             float* __restrict__ posOut, int* __restrict__ idxOut) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  Lane L;
+  for (int i = 0; i < CNT_N; i++) L.cnt[i] = 0;
+  locate_abs(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, p.dx, pos[3 * r], 1, &L.cx, &L.fx);
+  locate_abs(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, p.dy, pos[3 * r + 1], 1, &L.cy, &L.fy);
+  locate_abs(p.ze, p.zRegular, p.nz, p.z0, p.zmax, p.dz, pos[3 * r + 2], 0, &L.cz, &L.fz);
+  float dx = dir[3 * r], dy = dir[3 * r + 1], dz = dir[3 * r + 2];
+  start_ray(p, L, dx, dy, dz, inv_abs(dx), inv_abs(dy), inv_abs(dz), tauLimit ? tauLimit[r] : INFINITY);
+  while (L.done == DONE_RUN) dda_step(p, L);
+  tauOut[r] = L.done == DONE_BAD ? -2.0f : L.tau;
+  ray_local(p, L, &L.fx, &L.fy, &L.fz);
+  if (posOut) {
+    posOut[3 * r] = abs_x(p, L.ix, L.fx);
+    posOut[3 * r + 1] = abs_y(p, L.iy, L.fy);
+    posOut[3 * r + 2] = L.done == DONE_TOP ? p.zmax : (L.done == DONE_BOTTOM ? p.z0 : abs_z(p, L.iz, L.fz));
+  }
+  if (idxOut) {
+    idxOut[3 * r] = L.ix + 1;
+    idxOut[3 * r + 1] = L.iy + 1;
+    idxOut[3 * r + 2] = L.iz + 1;
+  }
+}
+__global__ void k_sample_angles(const float* __restrict__ T, int nSteps, int n, const float* __restrict__ xi,
+                                float* __restrict__ theta) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) theta[i] = scattering_angle(T, nSteps, xi[i]);
+}
+__global__ void k_lookup_phase(const float* __restrict__ T, int nSteps, int n, const float* __restrict__ ang,
+                               float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = phase_lookup(T, nSteps, ang[i]);
+}
+
+// ---- setup: getOpticalPropertiesByComponent on the device (Code/opticalProperties.f95:429-539) -------------
+struct ComponentDev {
+  const float* ext;
+  const float* ssa;
+  const int* pfi;
+  int uniform, zBase, nz;  // zBase 0-based
+};
+__global__ void k_expand_components(int nx, int ny, int nz, int nc, const ComponentDev* __restrict__ comps,
+                                    float* __restrict__ totalExt, float* __restrict__ cumExt,
+                                    float* __restrict__ ssa, int* __restrict__ pfIdx) {
+  size_t ncell = (size_t)nx * ny * nz;
+  size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ncell) return;
+  int iz = (int)(cell / ((size_t)nx * ny));
+  size_t col = cell - (size_t)iz * nx * ny;
+  float run = 0.0f;
+  for (int c = 0; c < nc; c++) {
+    ComponentDev k = comps[c];
+    float e = 0.0f, s = 0.0f;
+    int f = 0;
+    int kz = iz - k.zBase;
+    if (kz >= 0 && kz < k.nz) {
+      size_t src = k.uniform ? (size_t)kz : (size_t)kz * nx * ny + col;
+      e = k.ext[src];
+      s = k.ssa[src];
+      f = k.pfi[src];
+    }
+    run = (c == 0) ? e : e + run;  // cumulativeExt(:,:,:,i) + cumulativeExt(:,:,:,i-1)
+    cumExt[(size_t)c * ncell + cell] = run;
+    ssa[(size_t)c * ncell + cell] = s;
+    pfIdx[(size_t)c * ncell + cell] = f;
+  }
+  totalExt[cell] = run;
+  if (run > F_TINY)
+    for (int c = 0; c < nc; c++) cumExt[(size_t)c * ncell + cell] = cumExt[(size_t)c * ncell + cell] / run;
+}
+// MCRT:233-234: nudge the last cumulative fraction to 1 + epsilon; also the domain maximum of totalExt
+__global__ void k_bump_and_max(size_t ncell, float* __restrict__ lastCum, const float* __restrict__ totalExt,
+                               unsigned int* __restrict__ maxBits) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float m = 0.0f;
+  if (i < ncell) {
+    const float eps = 1.1920929e-7f;
+    float c = lastCum[i];
+    if (fabsf(c - 1.0f) <= eps) lastCum[i] = 1.0f + eps;
+    m = fmaxf(totalExt[i], 0.0f);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(maxBits, __float_as_uint(m));
+}
+
+// ---- post-processing of one batch (MCRT:327-395) -------------------------------------------------------------
+// sum over the columns of `rows` consecutive (nx*ny)-slabs: out[r] = sum(in[r*ncol : (r+1)*ncol]) in double
+__global__ void k_slab_sums(const float* __restrict__ in, size_t ncol, double* __restrict__ out) {
+  __shared__ double sh[256];
+  const float* row = in + (size_t)blockIdx.x * ncol;
+  double s = 0.0;
+  for (size_t i = threadIdx.x; i < ncol; i += blockDim.x) s += (double)row[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+// redistribute the clipped local-estimate excess in proportion to intensityByComponent (MCRT:327-347)
+__global__ void k_redistribute_excess(int nDir, int ncomp1, size_t ncol, const float* __restrict__ excess,
+                                      const double* __restrict__ slabSum, float* __restrict__ intensity,
+                                      float* __restrict__ intByComp) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int d = blockIdx.y;
+  if (i >= ncol) return;
+  for (int j = 0; j < ncomp1; j++) {
+    float ex = excess[j * nDir + d];
+    if (ex > 0.0f) {
+      size_t o = ((size_t)j * nDir + d) * ncol + i;
+      float share = (intByComp[o] / (float)slabSum[j * nDir + d]) * ex;
+      intensity[(size_t)d * ncol + i] += share;
+      intByComp[o] += share;
+    }
+  }
+}
+struct NormArgs {
+  int nx, ny, nz, nDir, nc, xyRegular, trackByComponent;
+  float numPhotons;
+  const float *xe, *ye, *ze;
+  float *fluxUp, *fluxDown, *fluxAbs, *volAbs, *intensity, *intByComp;
+};
+// divide by the mean number of photons per column, absorption also by the layer depth (MCRT:353-395)
+__global__ void k_normalize(const NormArgs a) {
+  size_t ncol = (size_t)a.nx * a.ny;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncol) return;
+  float nppc;
+  if (a.xyRegular) {
+    nppc = a.numPhotons / (float)(a.nx * a.ny);
+  } else {
+    int ix = (int)(i % a.nx), iy = (int)(i / a.nx);
+    nppc = ((a.ye[iy + 1] - a.ye[iy]) * (a.xe[ix + 1] - a.xe[ix])) /
+           ((a.xe[a.nx] - a.xe[0]) * (a.ye[a.ny] - a.ye[0]));
+    nppc = nppc * a.numPhotons;
+  }
+  a.fluxUp[i] = a.fluxUp[i] / nppc;
+  a.fluxDown[i] = a.fluxDown[i] / nppc;
+  a.fluxAbs[i] = a.fluxAbs[i] / nppc;
+  for (int k = 0; k < a.nz; k++) {
+    float dz = a.ze[k + 1] - a.ze[k];
+    a.volAbs[(size_t)k * ncol + i] = a.volAbs[(size_t)k * ncol + i] / (nppc * dz);
+  }
+  for (int d = 0; d < a.nDir; d++) a.intensity[(size_t)d * ncol + i] = a.intensity[(size_t)d * ncol + i] / nppc;
+  if (a.trackByComponent)  // components 1..nc only, like the reference's forall (MCRT:390-394)
+    for (int j = 1; j <= a.nc; j++)
+      for (int d = 0; d < a.nDir; d++) {
+        size_t o = ((size_t)j * a.nDir + d) * ncol + i;
+        a.intByComp[o] = a.intByComp[o] / nppc;
+      }
+}
+
+// ---- batch moments (monteCarloDriver.f95:300-321): s1 += x, s2 += x*x ------------------------------------------
+__global__ void k_moments_f(const float* __restrict__ x, size_t n, double* __restrict__ s1, double* __restrict__ s2) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    double v = (double)x[i];
+    s1[i] += v;
+    s2[i] += v * v;
+  }
+}
+// the same for domain means: x = float(sum / ncol) like reportResults (MCRT:739-742, 780, 803-805)
+__global__ void k_moments_mean(const double* __restrict__ sums, int n, double invCols, double* __restrict__ s1,
+                               double* __restrict__ s2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    double v = (double)(float)(sums[i] * invCols);
+    s1[i] += v;
+    s2[i] += v * v;
+  }
+}
+__global__ void k_means_to_float(const double* __restrict__ sums, int n, double invCols, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)(sums[i] * invCols);
+}
+// mean and standard error from the two moments (monteCarloDriver.f95:358-378)
+__global__ void k_stats_finish(const double* __restrict__ s1, const double* __restrict__ s2, size_t n, double solarFlux,
+                               int numBatches, double* __restrict__ mean, double* __restrict__ err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    double m = solarFlux * s1[i] / numBatches;
+    double q = solarFlux * s2[i] / numBatches;
+    mean[i] = m;
+    double v = q - m * m;
+    err[i] = sqrt((v > 0.0 ? v : 0.0) / (double)(numBatches - 1));
+  }
+}
+
+}  // namespace i3rc

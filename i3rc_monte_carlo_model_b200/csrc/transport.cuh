@@ -1,0 +1,722 @@
+// Photon transport core of the B200 integrator: the device-side restatement of
+//   computeRT                      Integrators/monteCarloRadiativeTransfer.f95:400-707   (MCRT)
+//   accumulateExtinctionAlongPath  MCRT:1654-1807
+//   computeIntensityContribution   MCRT:1419-1611
+//   computeScatteringAngle / lookUpPhaseFuncValsFromTable / next_direct   MCRT:1390, 1613, 2086
+//   new_PhotonStream_* sampling    Code/monteCarloIllumination.f95:62-424
+//   computeSurfaceReflectance      Code/surfaceProperties.f95:121-162
+//
+// Design (not a translation):
+//  * one persistent thread per photon slot; a finished slot refills from a device photon counter;
+//  * every lane is a small state machine whose only inner operation is ONE cell crossing of a 3-D DDA,
+//    shared by photon path segments and local-estimate rays, so a warp's lanes run the same code even
+//    when they are in different phases of a photon's life;
+//  * positions are (cell index, fractional offset inside the cell); the ray is advanced in its own
+//    parametric distance t (Amanatides-Woo), so periodic wrap-around touches indices only and no
+//    spacing()-style nudges are needed;
+//  * random numbers come from a per-photon Philox4x32-10 stream (philox.cuh).
+//
+// Everything here is __host__ __device__ so that tests/hostsim can run the very same code on the CPU
+// (one lane at a time) against the oracle before any GPU time is spent.  The product never runs it on
+// the CPU: the only entry point the library exposes launches the __global__ wrappers in api.cu.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "philox.cuh"
+
+#ifdef __CUDA_ARCH__
+#define I3RC_LDG(p) __ldg(p)
+#define I3RC_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define I3RC_LOG(x) __logf(x)
+#define I3RC_EXP(x) __expf(x)
+#define I3RC_COS(x) __cosf(x)
+#define I3RC_SINCOS(x, s, c) __sincosf((x), (s), (c))
+#define I3RC_FDIV(a, b) __fdividef((a), (b))
+#else
+#define I3RC_LDG(p) (*(p))
+#define I3RC_ATOMIC_ADD(p, v) (*(p) += (v))
+#define I3RC_LOG(x) logf(x)
+#define I3RC_EXP(x) expf(x)
+#define I3RC_COS(x) cosf(x)
+#define I3RC_SINCOS(x, s, c) (*(s) = sinf(x), *(c) = cosf(x))
+#define I3RC_FDIV(a, b) ((a) / (b))
+#endif
+
+namespace i3rc {
+
+constexpr int MAX_DIRS = 32;
+constexpr float F_TINY = 1.17549435e-38f;
+constexpr float F_PI = 3.14159265358979312f;
+constexpr int DIR_STRIDE = 8;
+constexpr int MAX_RAY_STEPS = 1 << 26;  // hang protection: a ray that long is dropped as "bad"
+
+enum { CNT_PHOTONS = 0, CNT_BAD, CNT_CROSS_PH, CNT_CROSS_LE, CNT_COLL, CNT_ABS, CNT_CONTRIB, CNT_TOP, CNT_SURF,
+       CNT_RNG, CNT_KILL, CNT_NULL, CNT_N };
+
+enum { DONE_RUN = 0, DONE_INSIDE = 1, DONE_TOP = 2, DONE_BOTTOM = 3, DONE_BAD = 4 };
+enum { MODE_PHOTON = 0, MODE_LE_PLAIN = 1, MODE_LE_SMALL = 2, MODE_LE_BIG1 = 3, MODE_LE_BIG2 = 4 };
+
+struct TableDesc {
+  const float* inv;      // [nEntries][nInv]   scattering angle vs CDF (radians)
+  const float* fwd;      // [nEntries][nFwd]   phase function on equal angle steps (hybrid if enabled)
+  const float* fwdOrig;  // [nEntries][nFwd]
+  int nInv, nFwd, nEntries, pad;
+};
+
+struct SourceDev {
+  int kind;
+  long long n;
+  float mu, phi;  // directional: -|solarMu|, azimuth in radians
+  float x, y, z;
+  float detectorMu, detectorPhi;
+  int pointsUp, hasDx, hasDy;
+  float deltaX, deltaY;
+  const float *ax, *ay, *az, *amu, *aphi;  // I3RC_SRC_ARRAYS (device copies)
+};
+
+struct Problem {
+  int nx, ny, nz, nc;
+  int xyRegular, zRegular;
+  float x0, y0, z0, xmax, ymax, zmax;
+  float dx, dy, dz;
+  const float *xe, *ye, *ze;
+  const float* ext;
+  const float* cumExt;
+  const float* ssa;
+  const int* pfIdx;
+  float maxExt;
+  const TableDesc* tables;
+  int computeIntensity, nDir;
+  const float* dirs;  // [nDir][DIR_STRIDE]: d.x d.y d.z 1/|d.x| 1/|d.y| 1/|d.z| 4*pi*|mu| pad
+  int useRayTracing, useRussianRoulette, useRRIntensity, useHybrid, numOrdersOrig, limitContrib, useSurfaceBDRF;
+  int trackByComponent;
+  float rouletteW, surfaceAlbedo, zetaMin, maxContrib;
+  int surf_nx, surf_ny;
+  const float *surf_x, *surf_y, *surf_albedo;
+  SourceDev src;
+  uint32_t key0, key1;
+  float *fluxUp, *fluxDown, *fluxAbs, *volAbs, *intensity, *intByComp, *excess;
+  unsigned long long* counters;
+  unsigned long long* nextPhoton;
+  long long firstPhoton;  // photon ids of this launch are firstPhoton + [0, src.n)
+};
+
+struct Lane {
+  // current ray
+  int ix, iy, iz, idx;
+  float tx, ty, tz, t, tau, tauLimit;
+  float iax, iay, iaz;
+  int sgn;
+  int done;
+  int nsteps;
+  // photon
+  float fx, fy, fz;
+  int cx, cy, cz;
+  float ux, uy, uz;
+  float w;
+  int order;
+  int mode, d, comp, pfi;
+  float phat, tauFree;
+  Rng rng;
+  int active;
+  uint32_t cnt[CNT_N];
+};
+
+// ---- small helpers ------------------------------------------------------------------------------
+I3RC_HD float cell_w(const float* edges, int regular, float d, int i) {
+  return regular ? d : (I3RC_LDG(edges + i + 1) - I3RC_LDG(edges + i));
+}
+I3RC_HD float inv_abs(float d) { return fabsf(d) >= 2.0f * F_TINY ? 1.0f / fabsf(d) : INFINITY; }
+
+// largest i in [0, n-1] with edges[i] <= v (edges has n+1 entries); clamps
+I3RC_HD int search_edges(const float* edges, int n, float v) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (v >= I3RC_LDG(edges + mid))
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+// fractional domain coordinate q in [0,1] -> (cell, offset) along one axis
+I3RC_HD void locate_frac(const float* edges, int regular, int n, float e0, float emax, float q, int* i, float* f) {
+  q = q - floorf(q);  // periodic (q == 1 maps to 0, as findXYIndicies does, MCRT:1368-1369)
+  if (regular) {
+    float g = q * (float)n;
+    int k = (int)g;
+    if (k > n - 1) k = n - 1;
+    *i = k;
+    *f = fminf(fmaxf(g - (float)k, 0.0f), 1.0f);
+  } else {
+    float pos = e0 + q * (emax - e0);
+    int k = search_edges(edges, n, pos);
+    float a = I3RC_LDG(edges + k), b = I3RC_LDG(edges + k + 1);
+    *i = k;
+    *f = fminf(fmaxf((pos - a) / (b - a), 0.0f), 1.0f);
+  }
+}
+// absolute coordinate -> (cell, offset); pos is wrapped periodically when `periodic`
+I3RC_HD void locate_abs(const float* edges, int regular, int n, float e0, float emax, float d, float pos, int periodic,
+                        int* i, float* f) {
+  if (periodic) {
+    float L = emax - e0;
+    pos = pos - floorf((pos - e0) / L) * L;
+  }
+  if (regular) {
+    float g = (pos - e0) / d;
+    int k = (int)g;
+    if (k > n - 1) k = n - 1;
+    if (k < 0) k = 0;
+    *i = k;
+    *f = fminf(fmaxf(g - (float)k, 0.0f), 1.0f);
+  } else {
+    int k = search_edges(edges, n, pos);
+    float a = I3RC_LDG(edges + k), b = I3RC_LDG(edges + k + 1);
+    *i = k;
+    *f = fminf(fmaxf((pos - a) / (b - a), 0.0f), 1.0f);
+  }
+}
+
+I3RC_HD void make_direction(float mu, float phi, float* ux, float* uy, float* uz) {  // MCRT:2041-2059
+  float st = sqrtf(fmaxf(1.0f - mu * mu, 0.0f));
+  float s, c;
+  I3RC_SINCOS(phi, &s, &c);
+  *ux = st * c;
+  *uy = st * s;
+  *uz = mu;
+}
+
+// computeScatteringAngle, MCRT:1390-1417 (quirk Q1 kept: the interpolation weight is not scaled)
+I3RC_HD float scattering_angle(const float* T, int n, float xi) {
+  int k = (int)(xi * (float)n);  // angleIndex - 1
+  if (k + 1 < n) {
+    float leftOver = xi - (float)k / (float)n;
+    return (1.0f - leftOver) * I3RC_LDG(T + k) + leftOver * I3RC_LDG(T + k + 1);
+  }
+  return I3RC_LDG(T + n - 1);
+}
+
+// lookUpPhaseFuncValsFromTable, MCRT:1613-1652
+I3RC_HD float phase_lookup(const float* T, int n, float angle) {
+  float deltaTheta = F_PI / (float)(n - 1);
+  int k = (int)(angle / deltaTheta);  // angleIndex - 1
+  if (k + 1 < n) {
+    float wgt = 1.0f - (angle - (float)k * deltaTheta) / deltaTheta;
+    return wgt * I3RC_LDG(T + k) + (1.0f - wgt) * I3RC_LDG(T + k + 1);
+  }
+  return I3RC_LDG(T + n - 1);
+}
+
+// next_direct, MCRT:2086-2113 (Marchuk rotation, rejection sampling in the unit disc)
+I3RC_HD void next_direct(Lane& L, float cs) {
+  float D = 2.0f, AX = 0.0f, AY = 0.0f;
+  while (D > 1.0f) {
+    AX = 1.0f - 2.0f * L.rng.next();
+    AY = 1.0f - 2.0f * L.rng.next();
+    L.cnt[CNT_RNG] += 2;
+    D = AX * AX + AY * AY;
+  }
+  float B = sqrtf(fmaxf(1.0f - cs * cs, 0.0f) / D);
+  AX *= B;
+  AY *= B;
+  B = L.ux * AX - L.uy * AY;
+  D = cs - B / (1.0f + fabsf(L.uz));
+  L.ux = L.ux * D + AX;
+  L.uy = L.uy * D - AY;
+  float sb = (L.uz * B >= 0.0f) ? fabsf(B) : -fabsf(B);
+  L.uz = L.uz * cs - sb;
+}
+
+// ---- the ray ------------------------------------------------------------------------------------
+// Start a ray at the event point (cx,cy,cz ; fx,fy,fz) of the lane along direction (dx,dy,dz).
+I3RC_HD void start_ray(const Problem& p, Lane& L, float dx, float dy, float dz, float iax, float iay, float iaz,
+                       float tauLimit) {
+  L.ix = L.cx;
+  L.iy = L.cy;
+  L.iz = L.cz;
+  L.idx = (L.cz * p.ny + L.cy) * p.nx + L.cx;
+  L.iax = iax;
+  L.iay = iay;
+  L.iaz = iaz;
+  L.sgn = (dx >= 0.0f ? 1 : 0) | (dy >= 0.0f ? 2 : 0) | (dz >= 0.0f ? 4 : 0);
+  float wx = cell_w(p.xe, p.xyRegular, p.dx, L.cx);
+  float wy = cell_w(p.ye, p.xyRegular, p.dy, L.cy);
+  float wz = cell_w(p.ze, p.zRegular, p.dz, L.cz);
+  L.tx = isinf(iax) ? INFINITY : ((L.sgn & 1) ? (1.0f - L.fx) : L.fx) * wx * iax;
+  L.ty = isinf(iay) ? INFINITY : ((L.sgn & 2) ? (1.0f - L.fy) : L.fy) * wy * iay;
+  L.tz = isinf(iaz) ? INFINITY : ((L.sgn & 4) ? (1.0f - L.fz) : L.fz) * wz * iaz;
+  L.t = 0.0f;
+  L.tau = 0.0f;
+  L.tauLimit = tauLimit;
+  L.nsteps = 0;
+  L.done = DONE_RUN;
+}
+
+// ONE cell crossing (the body of accumulateExtinctionAlongPath's loop, MCRT:1690-1806).
+I3RC_HD void dda_step(const Problem& p, Lane& L) {
+  float e = I3RC_LDG(p.ext + L.idx);
+  float tn = fminf(L.tx, fminf(L.ty, L.tz));
+  float dtau = (tn - L.t) * e;
+  L.nsteps++;
+  if (L.tau + dtau > L.tauLimit) {  // MCRT:1721-1731: the target optical path is reached inside this cell
+    L.t = L.t + (L.tauLimit - L.tau) / e;
+    L.tau = L.tauLimit;
+    L.done = DONE_INSIDE;
+    return;
+  }
+  L.tau += dtau;
+  L.t = tn;
+  if (L.tx <= tn) {
+    if (L.sgn & 1) {
+      L.ix++;
+      L.idx++;
+      if (L.ix >= p.nx) {
+        L.ix = 0;
+        L.idx -= p.nx;
+      }
+    } else {
+      L.ix--;
+      L.idx--;
+      if (L.ix < 0) {
+        L.ix = p.nx - 1;
+        L.idx += p.nx;
+      }
+    }
+    L.tx += cell_w(p.xe, p.xyRegular, p.dx, L.ix) * L.iax;
+  }
+  if (L.ty <= tn) {
+    if (L.sgn & 2) {
+      L.iy++;
+      L.idx += p.nx;
+      if (L.iy >= p.ny) {
+        L.iy = 0;
+        L.idx -= p.nx * p.ny;
+      }
+    } else {
+      L.iy--;
+      L.idx -= p.nx;
+      if (L.iy < 0) {
+        L.iy = p.ny - 1;
+        L.idx += p.nx * p.ny;
+      }
+    }
+    L.ty += cell_w(p.ye, p.xyRegular, p.dy, L.iy) * L.iay;
+  }
+  if (L.tz <= tn) {
+    if (L.sgn & 4) {
+      L.iz++;
+      if (L.iz >= p.nz) {
+        L.done = DONE_TOP;
+        return;
+      }
+      L.idx += p.nx * p.ny;
+    } else {
+      L.iz--;
+      if (L.iz < 0) {
+        L.done = DONE_BOTTOM;
+        return;
+      }
+      L.idx -= p.nx * p.ny;
+    }
+    L.tz += cell_w(p.ze, p.zRegular, p.dz, L.iz) * L.iaz;
+  }
+  if (L.nsteps > MAX_RAY_STEPS) L.done = DONE_BAD;
+}
+
+// offset inside the current cell of the ray's current point, per axis (keeps f where the ray does not move)
+I3RC_HD void ray_local(const Problem& p, const Lane& L, float* fx, float* fy, float* fz) {
+  if (!isinf(L.iax)) {
+    float rem = (L.tx - L.t) / (cell_w(p.xe, p.xyRegular, p.dx, L.ix) * L.iax);
+    rem = fminf(fmaxf(rem, 0.0f), 1.0f);
+    *fx = (L.sgn & 1) ? 1.0f - rem : rem;
+  }
+  if (!isinf(L.iay)) {
+    float rem = (L.ty - L.t) / (cell_w(p.ye, p.xyRegular, p.dy, L.iy) * L.iay);
+    rem = fminf(fmaxf(rem, 0.0f), 1.0f);
+    *fy = (L.sgn & 2) ? 1.0f - rem : rem;
+  }
+  if (L.iz >= 0 && L.iz < p.nz && !isinf(L.iaz)) {
+    float rem = (L.tz - L.t) / (cell_w(p.ze, p.zRegular, p.dz, L.iz) * L.iaz);
+    rem = fminf(fmaxf(rem, 0.0f), 1.0f);
+    *fz = (L.sgn & 4) ? 1.0f - rem : rem;
+  }
+}
+
+// ---- photon life ----------------------------------------------------------------------------------
+I3RC_HD float draw(Lane& L) {
+  L.cnt[CNT_RNG]++;
+  return L.rng.next();
+}
+I3RC_HD float draw_tau(Lane& L) { return -I3RC_LOG(fmaxf(F_TINY, draw(L))); }  // MCRT:480
+
+I3RC_HD float abs_x(const Problem& p, int ix, float fx) {
+  float a = p.xyRegular ? p.x0 + (float)ix * p.dx : I3RC_LDG(p.xe + ix);
+  return a + fx * cell_w(p.xe, p.xyRegular, p.dx, ix);
+}
+I3RC_HD float abs_y(const Problem& p, int iy, float fy) {
+  float a = p.xyRegular ? p.y0 + (float)iy * p.dy : I3RC_LDG(p.ye + iy);
+  return a + fy * cell_w(p.ye, p.xyRegular, p.dy, iy);
+}
+I3RC_HD float abs_z(const Problem& p, int iz, float fz) {
+  float a = p.zRegular ? p.z0 + (float)iz * p.dz : I3RC_LDG(p.ze + iz);
+  return a + fz * cell_w(p.ze, p.zRegular, p.dz, iz);
+}
+
+// Maximum cross-section flight (MCRT:491-497, 504-511, 521-528, 586-588) from the event point to the
+// next boundary or PHYSICAL collision.  Cell indices are looked up after every move (deviation Q11).
+I3RC_HD void max_cross_section_flight(const Problem& p, Lane& L) {
+  float x = abs_x(p, L.cx, L.fx), y = abs_y(p, L.cy, L.fy), z = abs_z(p, L.cz, L.fz);
+  float Lx = p.xmax - p.x0, Ly = p.ymax - p.y0;
+  for (;;) {
+    float dist = draw_tau(L) / p.maxExt;
+    x += L.ux * dist;
+    y += L.uy * dist;
+    z += L.uz * dist;
+    if (z >= p.zmax) {
+      float back = fabsf((z - p.zmax) / L.uz);
+      x -= L.ux * back;
+      y -= L.uy * back;
+      locate_abs(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, p.dx, x, 1, &L.ix, &L.fx);
+      locate_abs(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, p.dy, y, 1, &L.iy, &L.fy);
+      L.iz = p.nz;
+      L.done = DONE_TOP;
+      return;
+    }
+    if (z <= p.z0) {
+      float back = fabsf((z - p.z0) / L.uz);
+      x -= L.ux * back;
+      y -= L.uy * back;
+      locate_abs(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, p.dx, x, 1, &L.ix, &L.fx);
+      locate_abs(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, p.dy, y, 1, &L.iy, &L.fy);
+      L.iz = -1;
+      L.done = DONE_BOTTOM;
+      return;
+    }
+    x = x - floorf((x - p.x0) / Lx) * Lx;
+    y = y - floorf((y - p.y0) / Ly) * Ly;
+    locate_abs(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, p.dx, x, 0, &L.ix, &L.fx);
+    locate_abs(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, p.dy, y, 0, &L.iy, &L.fy);
+    locate_abs(p.ze, p.zRegular, p.nz, p.z0, p.zmax, p.dz, z, 0, &L.iz, &L.fz);
+    L.idx = (L.iz * p.ny + L.iy) * p.nx + L.ix;
+    float e = I3RC_LDG(p.ext + L.idx);
+    if (draw(L) < e / p.maxExt) {
+      L.done = DONE_INSIDE;
+      return;
+    }
+    L.cnt[CNT_NULL]++;
+  }
+}
+
+// Begin the next path segment of the photon from its event point (MCRT:474-497).
+I3RC_HD void start_segment(const Problem& p, Lane& L) {
+  L.mode = MODE_PHOTON;
+  if (p.useRayTracing) {
+    start_ray(p, L, L.ux, L.uy, L.uz, inv_abs(L.ux), inv_abs(L.uy), inv_abs(L.uz), draw_tau(L));
+  } else {
+    L.nsteps = 0;
+    L.iax = L.iay = L.iaz = INFINITY;  // ray_local keeps the offsets set by the flight
+    L.t = 0.0f;
+    L.tx = L.ty = L.tz = INFINITY;
+    L.sgn = 0;
+    max_cross_section_flight(p, L);
+  }
+}
+
+// Draw a photon from the source descriptor (Code/monteCarloIllumination.f95:62-424) and start it (MCRT:453-470).
+I3RC_HD void init_photon(const Problem& p, Lane& L, long long id) {
+  const SourceDev& s = p.src;
+  L.rng.init(p.key0, p.key1, (uint64_t)(p.firstPhoton + id));
+  float qx, qy, qz = 1.0f, mu, phi;
+  const float twoPi = 2.0f * F_PI;
+  switch (s.kind) {
+    case 1:
+      qx = draw(L);
+      qy = draw(L);
+      mu = s.mu;
+      phi = s.phi;
+      break;
+    case 2:
+      qx = draw(L);
+      qy = draw(L);
+      phi = draw(L) * twoPi;
+      mu = s.mu;
+      break;
+    case 3:
+      qx = draw(L);
+      qy = draw(L);
+      mu = -sqrtf(draw(L));
+      phi = draw(L) * twoPi;
+      break;
+    case 4:
+      qx = s.x;
+      qy = s.y;
+      mu = s.mu;
+      phi = s.phi;
+      break;
+    case 5: {
+      qx = s.x;
+      qy = s.y;
+      qz = s.z;
+      mu = sqrtf(draw(L));
+      phi = draw(L) * twoPi;
+      while (fabsf(mu) < 2.0f * F_TINY) mu = sqrtf(draw(L));
+      if (!s.pointsUp) mu = -mu;
+      if (s.hasDx) qx += s.deltaX * (1.0f - 0.5f * draw(L));
+      if (s.hasDy) qy += s.deltaY * (1.0f - 0.5f * draw(L));
+      break;
+    }
+    case 6:
+      qx = s.x;
+      qy = s.y;
+      qz = s.z;
+      mu = s.detectorMu;
+      phi = s.detectorPhi;  // stored as given, like the reference (monteCarloIllumination.f95:392)
+      if (s.hasDx) qx += s.deltaX * (1.0f - 0.5f * draw(L));
+      if (s.hasDy) qy += s.deltaY * (1.0f - 0.5f * draw(L));
+      break;
+    default:
+      qx = I3RC_LDG(s.ax + id);
+      qy = I3RC_LDG(s.ay + id);
+      qz = I3RC_LDG(s.az + id);
+      mu = I3RC_LDG(s.amu + id);
+      phi = I3RC_LDG(s.aphi + id);
+      break;
+  }
+  locate_frac(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, qx, &L.cx, &L.fx);
+  locate_frac(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, qy, &L.cy, &L.fy);
+  if (qz >= 1.0f - 1.2e-7f) {  // 1 - spacing(1.): the top face of the top layer
+    L.cz = p.nz - 1;
+    L.fz = 1.0f;
+  } else {
+    float zz = fmaxf(qz, 0.0f);
+    if (p.zRegular) {
+      float g = zz * (float)p.nz;
+      int k = (int)g;
+      if (k > p.nz - 1) k = p.nz - 1;
+      L.cz = k;
+      L.fz = fminf(fmaxf(g - (float)k, 0.0f), 1.0f);
+    } else {
+      locate_abs(p.ze, 0, p.nz, p.z0, p.zmax, p.dz, p.z0 + zz * (p.zmax - p.z0), 0, &L.cz, &L.fz);
+    }
+  }
+  make_direction(mu, phi, &L.ux, &L.uy, &L.uz);
+  L.w = 1.0f;
+  L.order = 0;
+  L.active = 1;
+  L.cnt[CNT_PHOTONS]++;
+  start_segment(p, L);
+}
+
+// Lambertian albedo map lookup (Code/surfaceProperties.f95:121-162)
+I3RC_HD float surface_reflectance(const Problem& p, float x, float y) {
+  float x0 = I3RC_LDG(p.surf_x), xm = I3RC_LDG(p.surf_x + p.surf_nx);
+  float y0 = I3RC_LDG(p.surf_y), ym = I3RC_LDG(p.surf_y + p.surf_ny);
+  int i, j;
+  float f;
+  if (p.surf_nx == 1) {
+    i = 0;
+  } else {
+    locate_abs(p.surf_x, 0, p.surf_nx, x0, xm, 0.0f, x, 1, &i, &f);
+  }
+  if (p.surf_ny == 1) {
+    j = 0;
+  } else {
+    locate_abs(p.surf_y, 0, p.surf_ny, y0, ym, 0.0f, y, 1, &j, &f);
+  }
+  return I3RC_LDG(p.surf_albedo + j * p.surf_nx + i);
+}
+
+// Set up the local-estimate ray towards direction L.d from the event point (MCRT:1473-1510, 1517-1521,
+// 1540-1569).  Returns 0 when the contribution is known to be zero without tracing.
+I3RC_HD int start_le_ray(const Problem& p, Lane& L) {
+  const float* dv = p.dirs + L.d * DIR_STRIDE;
+  float ddx = I3RC_LDG(dv + 0), ddy = I3RC_LDG(dv + 1), ddz = I3RC_LDG(dv + 2);
+  if (L.comp < 1) {
+    L.phat = 1.0f / F_PI;  // quirk Q10 (MCRT:1479)
+  } else {
+    float proj = L.ux * ddx + L.uy * ddy + L.uz * ddz;
+    proj = fminf(fmaxf(proj, -1.0f), 1.0f);
+    float ang = acosf(proj);
+    const TableDesc& T = p.tables[L.comp - 1];
+    const float* tab = (p.useHybrid && L.order <= p.numOrdersOrig) ? T.fwdOrig : T.fwd;
+    float val = phase_lookup(tab + (size_t)L.pfi * T.nFwd, T.nFwd, ang);
+    L.phat = val / I3RC_LDG(dv + 6);
+  }
+  float lim = INFINITY;
+  if (!p.useRRIntensity) {
+    L.mode = MODE_LE_PLAIN;
+  } else {
+    L.tauFree = draw_tau(L);  // MCRT:1542
+    if (F_PI * L.phat <= p.zetaMin) {
+      // Iwabuchi Eq 13 (MCRT:1546-1559).  The acceptance draw does not depend on the ray, so it is taken
+      // first and rejected rays are never traced (the reference traces them and then discards them).
+      float xi = draw(L);
+      if (!(xi <= F_PI * L.phat / p.zetaMin)) return 0;
+      L.mode = MODE_LE_SMALL;
+      lim = L.tauFree;
+    } else {
+      L.mode = MODE_LE_BIG1;  // MCRT:1566-1569
+      lim = -I3RC_LOG(p.zetaMin / fmaxf(F_TINY, F_PI * L.phat));
+    }
+  }
+  start_ray(p, L, ddx, ddy, ddz, I3RC_LDG(dv + 3), I3RC_LDG(dv + 4), I3RC_LDG(dv + 5), lim);
+  return 1;
+}
+
+I3RC_HD void tally_intensity(const Problem& p, Lane& L, float c) {
+  if (p.limitContrib && c > p.maxContrib) {  // MCRT:1598-1609
+    I3RC_ATOMIC_ADD(p.excess + L.comp * p.nDir + L.d, c - p.maxContrib);
+    c = p.maxContrib;
+  }
+  if (c != 0.0f) {
+    int col = L.iy * p.nx + L.ix;
+    size_t ncol = (size_t)p.nx * p.ny;
+    I3RC_ATOMIC_ADD(p.intensity + (size_t)L.d * ncol + col, c);
+    if (p.trackByComponent) I3RC_ATOMIC_ADD(p.intByComp + ((size_t)L.comp * p.nDir + L.d) * ncol + col, c);
+    L.cnt[CNT_CONTRIB]++;
+  }
+}
+
+// After the local estimate (or directly, when no intensity is wanted): roulette, scattering, next segment
+// (MCRT:670-688); for a surface event just continue with the reflected direction.
+I3RC_HD void continue_photon(const Problem& p, Lane& L) {
+  if (L.comp >= 1) {
+    if (p.useRussianRoulette && L.w < p.rouletteW * 0.5f) {  // MCRT:673-679
+      if (draw(L) >= L.w / p.rouletteW) {
+        L.w = 0.0f;
+        L.cnt[CNT_KILL]++;
+      } else {
+        L.w = p.rouletteW;
+      }
+    }
+    if (L.w <= F_TINY) {
+      L.active = 0;
+      return;
+    }
+    const TableDesc& T = p.tables[L.comp - 1];
+    float theta = scattering_angle(T.inv + (size_t)L.pfi * T.nInv, T.nInv, draw(L));
+    next_direct(L, I3RC_COS(theta));
+  }
+  start_segment(p, L);
+}
+
+// Walk the local-estimate directions from L.d on; returns when a ray is in flight or all are done.
+I3RC_HD void advance_le(const Problem& p, Lane& L) {
+  while (L.d < p.nDir) {
+    if (start_le_ray(p, L)) return;
+    L.d++;
+  }
+  continue_photon(p, L);
+}
+
+// A ray has finished (L.done != 0): do what computeRT / computeIntensityContribution do next.
+I3RC_HD void handle_event(const Problem& p, Lane& L) {
+  int done = L.done;
+  L.done = DONE_RUN;
+  if (L.mode == MODE_PHOTON) {
+    L.cnt[CNT_CROSS_PH] += L.nsteps;
+    if (done == DONE_BAD) {
+      L.cnt[CNT_BAD]++;
+      L.active = 0;
+      return;
+    }
+    if (done == DONE_TOP) {  // MCRT:499-514
+      I3RC_ATOMIC_ADD(p.fluxUp + L.iy * p.nx + L.ix, L.w);
+      L.cnt[CNT_TOP]++;
+      L.active = 0;
+      return;
+    }
+    ray_local(p, L, &L.fx, &L.fy, &L.fz);
+    L.cx = L.ix;
+    L.cy = L.iy;
+    if (done == DONE_BOTTOM) {  // MCRT:515-580
+      L.order++;
+      L.cz = 0;
+      L.fz = 0.0f;
+      I3RC_ATOMIC_ADD(p.fluxDown + L.cy * p.nx + L.cx, L.w);
+      L.cnt[CNT_SURF]++;
+      float mu;
+      do {
+        mu = sqrtf(draw(L));
+      } while (!(fabsf(mu) > 2.0f * F_TINY));
+      float phi = 2.0f * F_PI * draw(L);
+      if (p.useSurfaceBDRF)
+        L.w *= surface_reflectance(p, abs_x(p, L.cx, L.fx), abs_y(p, L.cy, L.fy));
+      else
+        L.w *= p.surfaceAlbedo;
+      if (L.w <= F_TINY) {
+        L.active = 0;
+        return;
+      }
+      make_direction(mu, phi, &L.ux, &L.uy, &L.uz);
+      L.comp = 0;
+      L.pfi = 0;
+    } else {  // collision, MCRT:581-668
+      L.cz = L.iz;
+      L.order++;
+      L.cnt[CNT_COLL]++;
+      size_t ncell = (size_t)p.nx * p.ny * p.nz;
+      int comp = 1;
+      if (p.nc > 1) {  // findIndex(xi, (/0, cumulativeExt(:)/)), MCRT:637-638
+        float xi = draw(L);
+        while (comp < p.nc && xi >= I3RC_LDG(p.cumExt + (size_t)(comp - 1) * ncell + L.idx)) comp++;
+      }
+      L.comp = comp;
+      float ssa = I3RC_LDG(p.ssa + (size_t)(comp - 1) * ncell + L.idx);
+      L.pfi = I3RC_LDG(p.pfIdx + (size_t)(comp - 1) * ncell + L.idx) - 1;
+      if (L.pfi < 0) L.pfi = 0;
+      if (ssa < 1.0f) {  // MCRT:642-649
+        float a = L.w * (1.0f - ssa);
+        I3RC_ATOMIC_ADD(p.fluxAbs + L.cy * p.nx + L.cx, a);
+        I3RC_ATOMIC_ADD(p.volAbs + L.idx, a);
+        L.w *= ssa;
+        L.cnt[CNT_ABS]++;
+      }
+    }
+    if (p.computeIntensity) {
+      L.d = 0;
+      advance_le(p, L);
+    } else {
+      continue_photon(p, L);
+    }
+    return;
+  }
+  // ---- a local-estimate ray has finished ----
+  L.cnt[CNT_CROSS_LE] += L.nsteps;
+  float c = 0.0f;
+  if (done != DONE_BAD) {
+    switch (L.mode) {
+      case MODE_LE_PLAIN:  // MCRT:1529-1535
+        c = L.w * L.phat * I3RC_EXP(-L.tau);
+        break;
+      case MODE_LE_SMALL:  // MCRT:1554-1559 (escape is detected at the TOP only: quirk Q4)
+        if (done == DONE_TOP) c = L.w * p.zetaMin / F_PI;
+        break;
+      case MODE_LE_BIG1:  // MCRT:1570-1593
+        if (done == DONE_TOP) {
+          c = L.w * L.phat * I3RC_EXP(-L.tau);
+        } else if (done == DONE_INSIDE) {
+          // tau reached tauMax inside the domain: chain a second trace of tauFree from here (MCRT:1576-1578)
+          L.cnt[CNT_CROSS_LE] -= 0;
+          L.mode = MODE_LE_BIG2;
+          L.tau = 0.0f;
+          L.tauLimit = L.tauFree;
+          L.nsteps = 0;
+          return;
+        }
+        break;
+      default:  // MODE_LE_BIG2, MCRT:1583-1587
+        if (done == DONE_TOP) c = L.w * p.zetaMin / F_PI;
+        break;
+    }
+  }
+  tally_intensity(p, L, c);
+  L.d++;
+  advance_le(p, L);
+}
+
+}  // namespace i3rc

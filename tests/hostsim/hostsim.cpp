@@ -1,0 +1,156 @@
+// tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE.
+// Compiles the product's __host__ __device__ transport core (csrc/transport.cuh, csrc/philox.cuh) for the
+// CPU and runs it one lane at a time, so that the kernel's logic and its Philox streams can be checked
+// against the oracle in this GPU-less container before GPU time is spent.  It is not part of the product
+// and is never loaded by the package: the shipped library only launches the __global__ kernels.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../i3rc_monte_carlo_model_b200/csrc/transport.cuh"
+
+using namespace i3rc;
+
+extern "C" {
+
+struct HostSimArgs {
+  int nx, ny, nz, nc;
+  const float *xe, *ye, *ze;
+  const float *ext, *cum, *ssa;
+  const int* pf;
+  int xyRegular, zRegular;
+  // tables, per component
+  const float* const* inv;
+  const float* const* fwd;
+  const float* const* fwdOrig;
+  const int* nInv;
+  const int* nFwd;
+  const int* nEntries;
+  // parameters
+  int nDir;
+  const float* mus;
+  const float* phisDeg;
+  int useRayTracing, useRussianRoulette, useRRIntensity, useHybrid, numOrdersOrig, limitContrib, trackByComponent;
+  float surfaceAlbedo, zetaMin, maxContrib;
+  int surf_nx, surf_ny;
+  const float *surf_x, *surf_y, *surf_p;
+  // source
+  int kind;
+  long long n;
+  float solarMu, solarAzimuthDeg, sx, sy, sz, detectorMu, detectorPhi;
+  int pointsUp, hasDx, hasDy;
+  float deltaX, deltaY;
+  const float *ax, *ay, *az, *amu, *aphi;
+  uint32_t key0, key1;
+  // outputs (raw, un-normalised tallies)
+  float *fluxUp, *fluxDown, *fluxAbs, *volAbs, *intensity, *intByComp, *excess;
+  unsigned long long* counters;  // [CNT_N]
+};
+
+void hostsim_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+  u32x4 c = {c0, c1, c2, c3};
+  u32x4 r = philox4x32_10(c, k0, k1);
+  out[0] = r.x;
+  out[1] = r.y;
+  out[2] = r.z;
+  out[3] = r.w;
+}
+
+int hostsim_trace_rays(const HostSimArgs* a, int n, const float* pos, const float* dir, const float* tauLimit,
+                       float* tauOut, float* posOut, int* idxOut);
+
+static void fill(const HostSimArgs* a, Problem& p, std::vector<TableDesc>& td, std::vector<float>& dirs) {
+  memset(&p, 0, sizeof(p));
+  p.nx = a->nx; p.ny = a->ny; p.nz = a->nz; p.nc = a->nc;
+  p.xyRegular = a->xyRegular; p.zRegular = a->zRegular;
+  p.xe = a->xe; p.ye = a->ye; p.ze = a->ze;
+  p.x0 = a->xe[0]; p.y0 = a->ye[0]; p.z0 = a->ze[0];
+  p.xmax = a->xe[a->nx]; p.ymax = a->ye[a->ny]; p.zmax = a->ze[a->nz];
+  p.dx = a->xe[1] - a->xe[0]; p.dy = a->ye[1] - a->ye[0]; p.dz = a->ze[1] - a->ze[0];
+  p.ext = a->ext; p.cumExt = a->cum; p.ssa = a->ssa; p.pfIdx = a->pf;
+  size_t ncell = (size_t)a->nx * a->ny * a->nz;
+  float mx = 0.0f;
+  for (size_t i = 0; i < ncell; i++) mx = a->ext[i] > mx ? a->ext[i] : mx;
+  p.maxExt = mx;
+  td.resize(a->nc);
+  for (int c = 0; c < a->nc; c++) {
+    td[c].inv = a->inv[c]; td[c].fwd = a->fwd ? a->fwd[c] : nullptr;
+    td[c].fwdOrig = a->fwdOrig ? a->fwdOrig[c] : td[c].fwd;
+    td[c].nInv = a->nInv[c]; td[c].nFwd = a->nFwd ? a->nFwd[c] : 0; td[c].nEntries = a->nEntries[c]; td[c].pad = 0;
+  }
+  p.tables = td.data();
+  p.computeIntensity = a->nDir > 0; p.nDir = a->nDir;
+  dirs.assign((size_t)a->nDir * DIR_STRIDE + 1, 0.0f);
+  for (int i = 0; i < a->nDir; i++) {
+    float mu = a->mus[i], phi = a->phisDeg[i] * F_PI / 180.0f;
+    float st = sqrtf(1.0f - mu * mu);
+    float* d = &dirs[(size_t)i * DIR_STRIDE];
+    d[0] = st * cosf(phi); d[1] = st * sinf(phi); d[2] = mu;
+    for (int k = 0; k < 3; k++) d[3 + k] = fabsf(d[k]) >= 2.0f * F_TINY ? 1.0f / fabsf(d[k]) : INFINITY;
+    d[6] = 4.0f * F_PI * fabsf(mu);
+  }
+  p.dirs = dirs.data();
+  p.useRayTracing = a->useRayTracing; p.useRussianRoulette = a->useRussianRoulette; p.useRRIntensity = a->useRRIntensity;
+  p.useHybrid = a->useHybrid; p.numOrdersOrig = a->numOrdersOrig; p.limitContrib = a->limitContrib;
+  p.trackByComponent = a->trackByComponent || a->limitContrib;
+  p.useSurfaceBDRF = a->surf_nx > 0;
+  p.rouletteW = 1.0f; p.surfaceAlbedo = a->surfaceAlbedo; p.zetaMin = a->zetaMin; p.maxContrib = a->maxContrib;
+  p.surf_nx = a->surf_nx; p.surf_ny = a->surf_ny; p.surf_x = a->surf_x; p.surf_y = a->surf_y; p.surf_albedo = a->surf_p;
+  SourceDev& s = p.src;
+  s.kind = a->kind; s.n = a->n; s.mu = -fabsf(a->solarMu); s.phi = a->solarAzimuthDeg * acosf(-1.0f) / 180.0f;
+  s.x = a->sx; s.y = a->sy; s.z = a->sz; s.detectorMu = a->detectorMu; s.detectorPhi = a->detectorPhi;
+  s.pointsUp = a->pointsUp; s.hasDx = a->hasDx; s.hasDy = a->hasDy; s.deltaX = a->deltaX; s.deltaY = a->deltaY;
+  s.ax = a->ax; s.ay = a->ay; s.az = a->az; s.amu = a->amu; s.aphi = a->aphi;
+  p.key0 = a->key0; p.key1 = a->key1;
+  p.fluxUp = a->fluxUp; p.fluxDown = a->fluxDown; p.fluxAbs = a->fluxAbs; p.volAbs = a->volAbs;
+  p.intensity = a->intensity; p.intByComp = a->intByComp; p.excess = a->excess;
+  p.counters = a->counters; p.nextPhoton = nullptr; p.firstPhoton = 0;
+}
+
+int hostsim_run(const HostSimArgs* a) {
+  Problem p;
+  std::vector<TableDesc> td;
+  std::vector<float> dirs;
+  fill(a, p, td, dirs);
+  Lane L;
+  memset(&L, 0, sizeof(L));
+  for (long long id = 0; id < a->n; id++) {
+    L.active = 0; L.done = DONE_RUN; L.mode = MODE_PHOTON;
+    init_photon(p, L, id);
+    while (L.active) {
+      if (L.done == DONE_RUN) dda_step(p, L);
+      else handle_event(p, L);
+    }
+  }
+  for (int i = 0; i < CNT_N; i++) a->counters[i] += L.cnt[i];
+  return 0;
+}
+
+int hostsim_trace_rays(const HostSimArgs* a, int n, const float* pos, const float* dir, const float* tauLimit,
+                       float* tauOut, float* posOut, int* idxOut) {
+  Problem p;
+  std::vector<TableDesc> td;
+  std::vector<float> dirs;
+  fill(a, p, td, dirs);
+  for (int r = 0; r < n; r++) {
+    Lane L;
+    memset(&L, 0, sizeof(L));
+    locate_abs(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, p.dx, pos[3 * r], 1, &L.cx, &L.fx);
+    locate_abs(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, p.dy, pos[3 * r + 1], 1, &L.cy, &L.fy);
+    locate_abs(p.ze, p.zRegular, p.nz, p.z0, p.zmax, p.dz, pos[3 * r + 2], 0, &L.cz, &L.fz);
+    float dx = dir[3 * r], dy = dir[3 * r + 1], dz = dir[3 * r + 2];
+    start_ray(p, L, dx, dy, dz, inv_abs(dx), inv_abs(dy), inv_abs(dz), tauLimit ? tauLimit[r] : INFINITY);
+    while (L.done == DONE_RUN) dda_step(p, L);
+    tauOut[r] = L.done == DONE_BAD ? -2.0f : L.tau;
+    ray_local(p, L, &L.fx, &L.fy, &L.fz);
+    if (posOut) {
+      posOut[3 * r] = abs_x(p, L.ix, L.fx);
+      posOut[3 * r + 1] = abs_y(p, L.iy, L.fy);
+      posOut[3 * r + 2] = L.done == DONE_TOP ? p.zmax : (L.done == DONE_BOTTOM ? p.z0 : abs_z(p, L.iz, L.fz));
+    }
+    if (idxOut) { idxOut[3 * r] = L.ix + 1; idxOut[3 * r + 1] = L.iy + 1; idxOut[3 * r + 2] = L.iz + 1; }
+  }
+  return 0;
+}
+}
