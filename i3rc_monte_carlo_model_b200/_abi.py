@@ -1,9 +1,8 @@
 """ctypes view of include/i3rc_b200.h.
 
-The struct layouts here are the ones declared in ``include/i3rc_b200.h``; the CPU oracle
-(``oracle/i3rc_oracle.h``, test infrastructure) deliberately uses the same layouts, so one set of
-definitions drives both shared libraries.  ``Backend`` binds the entry points of one library by prefix
-(``i3rc_`` for the product).
+The struct layouts here are the ones declared in ``include/i3rc_b200.h``.  ``Backend`` binds the entry
+points of one shared library by prefix (``i3rc_`` for the product); the test suite reuses it for the CPU
+checker, which deliberately exports the same layouts under another prefix.
 """
 from __future__ import annotations
 

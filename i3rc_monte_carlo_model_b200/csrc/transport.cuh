@@ -12,8 +12,8 @@
 //    shared by photon path segments and local-estimate rays, so a warp's lanes run the same code even
 //    when they are in different phases of a photon's life;
 //  * positions are (cell index, fractional offset inside the cell); the ray is advanced in its own
-//    parametric distance t (Amanatides-Woo), so periodic wrap-around touches indices only and no
-//    spacing()-style nudges are needed;
+//    remaining path length to the next cell face on each axis (Amanatides-Woo in cell-local form), so periodic
+//    wrap-around touches indices only and no spacing()-style nudges are needed;
 //  * random numbers come from a per-photon Philox4x32-10 stream (philox.cuh).
 //
 // Everything here is __host__ __device__ so that tests/hostsim can run the very same code on the CPU
@@ -105,7 +105,7 @@ struct Problem {
 struct Lane {
   // current ray
   int ix, iy, iz, idx;
-  float tx, ty, tz, t, tau, tauLimit;
+  float rx, ry, rz, tau, tauLimit;  // path length left to the next x/y/z cell face; optical path so far / target
   float iax, iay, iaz;
   int sgn;
   int done;
@@ -246,10 +246,9 @@ I3RC_HD void start_ray(const Problem& p, Lane& L, float dx, float dy, float dz, 
   float wx = cell_w(p.xe, p.xyRegular, p.dx, L.cx);
   float wy = cell_w(p.ye, p.xyRegular, p.dy, L.cy);
   float wz = cell_w(p.ze, p.zRegular, p.dz, L.cz);
-  L.tx = isinf(iax) ? INFINITY : ((L.sgn & 1) ? (1.0f - L.fx) : L.fx) * wx * iax;
-  L.ty = isinf(iay) ? INFINITY : ((L.sgn & 2) ? (1.0f - L.fy) : L.fy) * wy * iay;
-  L.tz = isinf(iaz) ? INFINITY : ((L.sgn & 4) ? (1.0f - L.fz) : L.fz) * wz * iaz;
-  L.t = 0.0f;
+  L.rx = isinf(iax) ? INFINITY : ((L.sgn & 1) ? (1.0f - L.fx) : L.fx) * wx * iax;
+  L.ry = isinf(iay) ? INFINITY : ((L.sgn & 2) ? (1.0f - L.fy) : L.fy) * wy * iay;
+  L.rz = isinf(iaz) ? INFINITY : ((L.sgn & 4) ? (1.0f - L.fz) : L.fz) * wz * iaz;
   L.tau = 0.0f;
   L.tauLimit = tauLimit;
   L.nsteps = 0;
@@ -257,20 +256,28 @@ I3RC_HD void start_ray(const Problem& p, Lane& L, float dx, float dy, float dz, 
 }
 
 // ONE cell crossing (the body of accumulateExtinctionAlongPath's loop, MCRT:1690-1806).
+// The ray carries the path length left to the next face on each axis (rx, ry, rz): all quantities stay of the
+// order of one cell, so the accumulated optical path does not lose precision with the distance travelled.
 I3RC_HD void dda_step(const Problem& p, Lane& L) {
   float e = I3RC_LDG(p.ext + L.idx);
-  float tn = fminf(L.tx, fminf(L.ty, L.tz));
-  float dtau = (tn - L.t) * e;
+  float s = fminf(L.rx, fminf(L.ry, L.rz));
+  float dtau = s * e;
   L.nsteps++;
   if (L.tau + dtau > L.tauLimit) {  // MCRT:1721-1731: the target optical path is reached inside this cell
-    L.t = L.t + (L.tauLimit - L.tau) / e;
+    float sp = (L.tauLimit - L.tau) / e;
+    L.rx -= sp;
+    L.ry -= sp;
+    L.rz -= sp;
     L.tau = L.tauLimit;
     L.done = DONE_INSIDE;
     return;
   }
   L.tau += dtau;
-  L.t = tn;
-  if (L.tx <= tn) {
+  const bool cx = L.rx <= s, cy = L.ry <= s, cz = L.rz <= s;
+  L.rx -= s;
+  L.ry -= s;
+  L.rz -= s;
+  if (cx) {
     if (L.sgn & 1) {
       L.ix++;
       L.idx++;
@@ -286,9 +293,9 @@ I3RC_HD void dda_step(const Problem& p, Lane& L) {
         L.idx += p.nx;
       }
     }
-    L.tx += cell_w(p.xe, p.xyRegular, p.dx, L.ix) * L.iax;
+    L.rx = cell_w(p.xe, p.xyRegular, p.dx, L.ix) * L.iax;
   }
-  if (L.ty <= tn) {
+  if (cy) {
     if (L.sgn & 2) {
       L.iy++;
       L.idx += p.nx;
@@ -304,9 +311,9 @@ I3RC_HD void dda_step(const Problem& p, Lane& L) {
         L.idx += p.nx * p.ny;
       }
     }
-    L.ty += cell_w(p.ye, p.xyRegular, p.dy, L.iy) * L.iay;
+    L.ry = cell_w(p.ye, p.xyRegular, p.dy, L.iy) * L.iay;
   }
-  if (L.tz <= tn) {
+  if (cz) {
     if (L.sgn & 4) {
       L.iz++;
       if (L.iz >= p.nz) {
@@ -322,7 +329,7 @@ I3RC_HD void dda_step(const Problem& p, Lane& L) {
       }
       L.idx -= p.nx * p.ny;
     }
-    L.tz += cell_w(p.ze, p.zRegular, p.dz, L.iz) * L.iaz;
+    L.rz = cell_w(p.ze, p.zRegular, p.dz, L.iz) * L.iaz;
   }
   if (L.nsteps > MAX_RAY_STEPS) L.done = DONE_BAD;
 }
@@ -330,17 +337,17 @@ I3RC_HD void dda_step(const Problem& p, Lane& L) {
 // offset inside the current cell of the ray's current point, per axis (keeps f where the ray does not move)
 I3RC_HD void ray_local(const Problem& p, const Lane& L, float* fx, float* fy, float* fz) {
   if (!isinf(L.iax)) {
-    float rem = (L.tx - L.t) / (cell_w(p.xe, p.xyRegular, p.dx, L.ix) * L.iax);
+    float rem = L.rx / (cell_w(p.xe, p.xyRegular, p.dx, L.ix) * L.iax);
     rem = fminf(fmaxf(rem, 0.0f), 1.0f);
     *fx = (L.sgn & 1) ? 1.0f - rem : rem;
   }
   if (!isinf(L.iay)) {
-    float rem = (L.ty - L.t) / (cell_w(p.ye, p.xyRegular, p.dy, L.iy) * L.iay);
+    float rem = L.ry / (cell_w(p.ye, p.xyRegular, p.dy, L.iy) * L.iay);
     rem = fminf(fmaxf(rem, 0.0f), 1.0f);
     *fy = (L.sgn & 2) ? 1.0f - rem : rem;
   }
   if (L.iz >= 0 && L.iz < p.nz && !isinf(L.iaz)) {
-    float rem = (L.tz - L.t) / (cell_w(p.ze, p.zRegular, p.dz, L.iz) * L.iaz);
+    float rem = L.rz / (cell_w(p.ze, p.zRegular, p.dz, L.iz) * L.iaz);
     rem = fminf(fmaxf(rem, 0.0f), 1.0f);
     *fz = (L.sgn & 4) ? 1.0f - rem : rem;
   }
@@ -419,8 +426,7 @@ I3RC_HD void start_segment(const Problem& p, Lane& L) {
   } else {
     L.nsteps = 0;
     L.iax = L.iay = L.iaz = INFINITY;  // ray_local keeps the offsets set by the flight
-    L.t = 0.0f;
-    L.tx = L.ty = L.tz = INFINITY;
+    L.rx = L.ry = L.rz = INFINITY;
     L.sgn = 0;
     max_cross_section_flight(p, L);
   }
@@ -701,7 +707,6 @@ I3RC_HD void handle_event(const Problem& p, Lane& L) {
           c = L.w * L.phat * I3RC_EXP(-L.tau);
         } else if (done == DONE_INSIDE) {
           // tau reached tauMax inside the domain: chain a second trace of tauFree from here (MCRT:1576-1578)
-          L.cnt[CNT_CROSS_LE] -= 0;
           L.mode = MODE_LE_BIG2;
           L.tau = 0.0f;
           L.tauLimit = L.tauFree;

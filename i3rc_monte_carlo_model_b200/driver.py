@@ -1,0 +1,216 @@
+"""The caller of the hot path: the batch loop, batch partitioning and moment statistics of
+Example-Drivers/monteCarloDriver.f95 (:264-378), and its namelist reader (:90-103, 143-150).
+
+Two ways through the loop:
+  * ``run_batches_host``  -- the reference's own call sequence per batch (new_PhotonStream,
+    computeRadiativeTransfer, reportResults into HOST arrays, moments on the host).  Works with any backend.
+  * ``run_batches_device`` -- the same loop through ``i3rc_run_batches``: photons are generated, traced,
+    normalised and folded into the sum(x) / sum(x*x) buffers on the device; nothing crosses PCIe per batch.
+Ranks (one process per GPU) take contiguous blocks of batches exactly like monteCarloDriver.f95:264-274 and the
+moment buffers are summed with ONE all-reduce (replacing the nine MPI_REDUCE calls of :333-348).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+
+import numpy as np
+
+from . import _abi
+from .monteCarloIllumination import new_PhotonStream
+from .monteCarloRadiativeTransfer import computeRadiativeTransfer, reportResults
+from .RandomNumbers import new_RandomNumberSequence
+
+
+def partition_batches(numBatches, numProcs=1, thisProc=0):
+    """monteCarloDriver.f95:264-274: at least two batches, rounded up to a multiple of the number of processes;
+    process p takes batches p*bpp+1 .. (p+1)*bpp.  Returns (numBatches, range of this process)."""
+    numBatches = max(int(numBatches), 2)
+    bpp = numBatches // numProcs
+    if numBatches % numProcs != 0:
+        bpp += 1
+        numBatches = bpp * numProcs
+    return numBatches, range(thisProc * bpp + 1, thisProc * bpp + bpp + 1)
+
+
+class BatchStatistics:
+    """First and second moments of every output over batches (monteCarloDriver.f95:300-321), in float64."""
+
+    def __init__(self):
+        self.sums: dict[str, np.ndarray] = {}
+        self.nLocal = 0
+
+    def add(self, results: dict):
+        for k, v in results.items():
+            v = np.asarray(v, dtype=np.float64)
+            if k not in self.sums:
+                self.sums[k] = np.zeros((2,) + v.shape)
+            self.sums[k][0] += v
+            self.sums[k][1] += v * v
+        self.nLocal += 1
+
+    def pack(self):
+        keys = sorted(self.sums)
+        return keys, np.concatenate([self.sums[k].ravel() for k in keys]) if keys else np.zeros(0)
+
+    def unpack(self, keys, flat):
+        o = 0
+        for k in keys:
+            n = self.sums[k].size
+            self.sums[k] = flat[o:o + n].reshape(self.sums[k].shape).copy()
+            o += n
+
+    def allreduce(self, dist=None):
+        """sumAcrossProcesses (Code/multipleProcesses_mpi.f95:57-131) as one all-reduce of one packed buffer."""
+        if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+            return
+        import torch
+        keys, flat = self.pack()
+        t = torch.from_numpy(flat)
+        dist.all_reduce(t)
+        self.unpack(keys, t.numpy())
+
+    def finish(self, solarFlux, numBatches):
+        """mean = solarFlux*sum/nB ; stderr = sqrt(max(0, solarFlux*sum2/nB - mean^2)/(nB-1))  (:358-378)"""
+        out = {}
+        for k, s in self.sums.items():
+            mean = solarFlux * s[0] / numBatches
+            second = solarFlux * s[1] / numBatches
+            out[k] = (mean, np.sqrt(np.maximum(0.0, second - mean**2) / (numBatches - 1)))
+        return out
+
+
+def run_batches_host(integ, source, numPhotonsPerBatch, batches, iseed=10, seedOrder=0, want=None, stats=None):
+    """monteCarloDriver.f95:274-326, one call per reference call; ``source`` holds new_PhotonStream's arguments."""
+    stats = stats or BatchStatistics()
+    want = want or (["meanFluxUp", "meanFluxDown", "meanFluxAbsorbed", "fluxUp", "fluxDown", "fluxAbsorbed",
+                     "absorbedProfile"] + (["intensity", "meanIntensity"] if integ.nDir else []))
+    for batch in batches:
+        seed = [iseed, batch] if seedOrder == 0 else [batch, iseed]
+        randoms = new_RandomNumberSequence(seed)
+        photons = new_PhotonStream(numberOfPhotons=numPhotonsPerBatch, randomNumbers=randoms, **source)
+        computeRadiativeTransfer(integ, randoms, photons)
+        stats.add(reportResults(integ, *want))
+    return stats
+
+
+class _DeviceArray:
+    """__cuda_array_interface__ view of the library's packed moment buffer (for torch.distributed)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def run_batches_device(integ, source, numPhotonsPerBatch, batches, iseed=10, seedOrder=0, with_volume=False, reset=True):
+    """The same loop without host round trips (i3rc_run_batches).  Returns the counters of the run."""
+    be = integ.backend
+    if be.run_batches is None:
+        raise RuntimeError("this backend has no device batch loop")
+    src = new_PhotonStream(numberOfPhotons=numPhotonsPerBatch, **source).as_c()
+    if reset:
+        rc = be.stats_reset(integ.handle, int(with_volume))
+        if rc == _abi.FAILURE:
+            raise RuntimeError(integ._msg())
+    batches = list(batches)
+    assert batches == list(range(batches[0], batches[0] + len(batches)))
+    rc = be.run_batches(integ.handle, C.byref(src), int(iseed), int(seedOrder), batches[0], len(batches))
+    if rc == _abi.FAILURE:
+        raise RuntimeError(integ._msg())
+    c = _abi.Counters()
+    be.get_counters(integ.handle, C.byref(c))
+    return c.as_dict()
+
+
+def allreduce_device_stats(integ, dist=None, device=None):
+    """ONE all-reduce (NCCL over NVLink) of the packed device moment buffer."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    import torch
+    be = integ.backend
+    ptr, n = C.c_void_p(), C.c_int64()
+    if be.stats_device_buffer(integ.handle, C.byref(ptr), C.byref(n)) == _abi.FAILURE:
+        raise RuntimeError("no batch statistics to reduce")
+    be.synchronize(integ.handle)
+    t = torch.as_tensor(_DeviceArray(ptr.value, n.value), device=device or torch.device("cuda", torch.cuda.current_device()))
+    dist.all_reduce(t)
+    torch.cuda.synchronize()
+
+
+def device_stats_report(integ, solarFlux, numBatches, with_volume=False):
+    """monteCarloDriver.f95:358-378 on the device; returns name -> (mean, stderr) arrays indexed [x, y(, ..)]."""
+    be = integ.backend
+    nx, ny, nz, nd = integ.nx, integ.ny, integ.nz, integ.nDir
+    out = _abi.StatsOut()
+    bufs = {
+        "meanFluxUp": np.zeros(2), "meanFluxDown": np.zeros(2), "meanFluxAbsorbed": np.zeros(2),
+        "fluxUp": np.zeros((2, ny, nx)), "fluxDown": np.zeros((2, ny, nx)), "fluxAbsorbed": np.zeros((2, ny, nx)),
+        "absorbedProfile": np.zeros((2, nz)),
+    }
+    if nd:
+        bufs["radiance"] = np.zeros((2, nd, ny, nx))
+        bufs["meanRadiance"] = np.zeros((2, nd))
+    if with_volume:
+        bufs["absorbedVolume"] = np.zeros((2, nz, ny, nx))
+    for k, a in bufs.items():
+        setattr(out, k, _abi.dptr(a))
+    rc = be.stats_report(integ.handle, float(solarFlux), int(numBatches), C.byref(out))
+    if rc == _abi.FAILURE:
+        raise RuntimeError(integ._msg())
+    res = {}
+    for k, a in bufs.items():
+        mean, err = a[0], a[1]
+        if mean.ndim >= 2:  # [.., y, x] -> Fortran-like [x, y, ..]
+            mean, err = mean.T, err.T
+        res[k] = (mean, err)
+    return res
+
+
+# ---- namelists (monteCarloDriver.f95:90-103) ------------------------------------------------------------------
+_DEFAULTS = {
+    "radiativetransfer": dict(solarFlux=1.0, solarMu=1.0, solarAzimuth=0.0, surfaceAlbedo=0.0, intensityMus=[], intensityPhis=[]),
+    "montecarlo": dict(numPhotonsPerBatch=0, numBatches=100, iseed=10, nPhaseIntervals=10001),
+    "algorithms": dict(useRayTracing=True, useRussianRoulette=True, useHybridPhaseFunsForIntenCalcs=False,
+                       hybridPhaseFunWidth=7.0, numOrdersOrigPhaseFunIntenCalcs=0, useRussianRouletteForIntensity=True,
+                       zetaMin=0.3, limitIntensityContributions=False, maxIntensityContribution=77.0),
+    "output": dict(reportVolumeAbsorption=False, reportAbsorptionProfile=False),
+    "filenames": dict(domainFileName="", outputFluxFile="", outputRadFile="", outputAbsProfFile="",
+                      outputAbsVolumeFile="", outputNetcdfFile=""),
+}
+
+
+def _parse_value(tok):
+    t = tok.strip()
+    if re.fullmatch(r"\.?(t|true)\.?", t, flags=re.I):
+        return True
+    if re.fullmatch(r"\.?(f|false)\.?", t, flags=re.I):
+        return False
+    if (t.startswith('"') and t.endswith('"')) or (t.startswith("'") and t.endswith("'")):
+        return t[1:-1]
+    try:
+        return int(t)
+    except ValueError:
+        return float(t.replace("d", "e").replace("D", "e"))
+
+
+def read_namelists(path):
+    """A Fortran-namelist reader sufficient for the driver's five groups; returns {group: {name: value}} with the
+    reference's defaults (monteCarloDriver.f95:61-88) filled in and names in the reference's spelling."""
+    text = "\n".join(line.split("!", 1)[0] for line in open(path).read().splitlines())
+    out = {g: dict(v) for g, v in _DEFAULTS.items()}
+    for m in re.finditer(r"&(\w+)(.*?)(?:^|\s)/", text, flags=re.S | re.M):
+        group = m.group(1).lower()
+        if group not in out:
+            continue
+        canon = {k.lower(): k for k in out[group]}
+        body = m.group(2)
+        for am in re.finditer(r"(\w+)\s*=\s*(.*?)(?=(?:\w+\s*=)|\Z)", body, flags=re.S):
+            name, raw = am.group(1).lower(), am.group(2).strip().rstrip(",")
+            if name not in canon:
+                continue
+            toks = [t for t in re.split(r"[,\s]+(?=(?:[^\"']*[\"'][^\"']*[\"'])*[^\"']*$)", raw) if t.strip()]
+            vals = [_parse_value(t) for t in toks]
+            out[group][canon[name]] = vals if isinstance(out[group][canon[name]], list) else vals[0]
+    rt = out["radiativetransfer"]
+    n = sum(1 for v in rt["intensityMus"] if abs(v) > 0)  # numRadDir = count(abs(intensityMus) > 0), :151
+    rt["intensityMus"], rt["intensityPhis"] = rt["intensityMus"][:n], (rt["intensityPhis"] + [0.0] * n)[:n]
+    return out

@@ -1,0 +1,376 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (include/i3rc_b200.h), against the CPU oracle on
+the same inputs and namelists-equivalents.
+
+Criteria (BASELINE.json north_star): because the RNG differs (per-photon Philox streams instead of the shared
+MT19937 stream), domain-mean and per-column fluxes, absorption and intensities agree within 3 sigma of the
+combined Monte Carlo batch standard error; the deterministic sub-paths (phase-table inversion, optical-path
+integration along a fixed ray) agree to 1e-5 relative.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from i3rc_monte_carlo_model_b200 import _abi, fields
+from i3rc_monte_carlo_model_b200.driver import (allreduce_device_stats, device_stats_report, partition_batches,
+                                               run_batches_device, run_batches_host)
+from i3rc_monte_carlo_model_b200.ErrorMessages import ErrorMessage, getCurrentMessage, stateIsFailure
+from i3rc_monte_carlo_model_b200.monteCarloIllumination import new_PhotonStream
+from i3rc_monte_carlo_model_b200.monteCarloRadiativeTransfer import (computeRadiativeTransfer, copy_Integrator, getCounters,
+                                                                    getTable, new_Integrator, new_Integrator_dense,
+                                                                    reportResults, specifyParameters, traceRays)
+from i3rc_monte_carlo_model_b200.RandomNumbers import new_RandomNumberSequence
+from i3rc_monte_carlo_model_b200.surfaceProperties import new_SurfaceDescription
+from tests.cases import assert_statistical_parity, make_integrator, mean_se, run_batches
+from tests.golden.make_golden import CASES as GOLDEN_CASES
+from tests.test_host_mirror import SPECIFY_CASES, check_specify
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# ---- deterministic sub-paths ------------------------------------------------------------------------------------
+def _rel(a, b, floor):
+    return np.max(np.abs(a.astype(np.float64) - b) / np.maximum(np.abs(b), floor))
+
+
+@pytest.mark.parametrize("name,make,params", [
+    ("HG-64", lambda: fields.plane_parallel(), {}),
+    ("HG-299", lambda: fields.landsat_cloud(1.0), dict(minInverseTableSize=10001, minForwardTableSize=10001)),
+    ("HG-tabulated", lambda: fields.plane_parallel(useMoments=False, nAngles=5000), {}),
+    ("C1-tabulated", lambda: fields.radar_cloud(1.0, "C1"), {}),
+    ("multi-entry", lambda: fields.synthetic_les(nx=8, ny=8, nz=16, n_entries=5, seed=3), {}),
+])
+def test_phase_tables_match_oracle(cuda, oracle, name, make, params):
+    """tabulateInverse/ForwardPhaseFunctions on the device vs the oracle: 1e-5 relative."""
+    d = make()
+    kw = dict(surfaceAlbedo=0.0, intensityMus=[1.0], intensityPhis=[0.0], **params)
+    G, O = make_integrator(cuda, d, **kw), make_integrator(oracle, d, **kw)
+    assert cuda.tabulate(G.handle) == 0, G._msg()
+    oracle.tabulate(O.handle)
+    for c in range(G.nc):
+        inv_g, inv_o = getTable(G, 0, c), getTable(O, 0, c).astype(np.float64)
+        assert inv_g.shape == inv_o.shape
+        # angles: 1e-5 relative to pi-scale (entries near 0 are acos() of numbers next to 1: absolute floor 1e-4 rad,
+        # the float32 resolution of acos there)
+        assert np.max(np.abs(inv_g - inv_o) / np.maximum(inv_o, 10.0)) < 1e-5, name
+        assert _rel(np.cos(inv_g), np.cos(inv_o), 1.0) < 1e-5, name
+        fwd_g, fwd_o = getTable(G, 2, c), getTable(O, 2, c).astype(np.float64)
+        assert _rel(fwd_g, fwd_o, np.abs(fwd_o).max() * 1e-3 + 1e-3) < 1e-5 * 5, name
+        assert np.median(np.abs(fwd_g - fwd_o) / np.maximum(np.abs(fwd_o), 1e-3)) < 1e-5, name
+
+
+def test_hybrid_tables_match_oracle(cuda, oracle):
+    d = fields.radar_cloud(1.0, "C1")
+    kw = dict(surfaceAlbedo=0.0, intensityMus=[1.0], intensityPhis=[0.0], useHybridPhaseFunsForIntenCalcs=True,
+              hybridPhaseFunWidth=7.0)
+    G, O = make_integrator(cuda, d, **kw), make_integrator(oracle, d, **kw)
+    assert cuda.tabulate(G.handle) == 0
+    oracle.tabulate(O.handle)
+    hg, ho = getTable(G, 1), getTable(O, 1).astype(np.float64)
+    og = getTable(G, 2)
+    kg, ko = np.nonzero(hg[0] != og[0])[0].max(), np.nonzero(ho[0] != getTable(O, 2)[0])[0].max()
+    assert abs(int(kg) - int(ko)) <= 1  # same transition index (float32 sums may shift it by one)
+    assert _rel(hg, ho, 1e-2) < 2e-4
+
+
+def test_scattering_angle_and_phase_lookup_probes(cuda, oracle):
+    """computeScatteringAngle / lookUpPhaseFuncValsFromTable with IDENTICAL (injected) tables: float32 round-off only."""
+    d = fields.plane_parallel()
+    kw = dict(surfaceAlbedo=0.0, intensityMus=[1.0], intensityPhis=[0.0])
+    G, O = make_integrator(cuda, d, **kw), make_integrator(oracle, d, **kw)
+    oracle.tabulate(O.handle)
+    inv, fwd = getTable(O, 0), getTable(O, 1)
+    assert cuda.set_inverse_table(G.handle, 0, inv.shape[1], 1, _abi.fptr(inv)) == 0
+    assert cuda.set_forward_table(G.handle, 0, fwd.shape[1], 1, _abi.fptr(fwd), None) == 0
+    rng = np.random.default_rng(0)
+    xi = np.concatenate([rng.random(5000), [0.0, 1.0, 0.5]]).astype(np.float32)
+    tg, to = np.zeros_like(xi), np.zeros_like(xi)
+    assert cuda.sample_scattering_angles(G.handle, 0, 0, xi.size, _abi.fptr(xi), _abi.fptr(tg)) == 0
+    oracle.sample_scattering_angles(O.handle, 0, 0, xi.size, _abi.fptr(xi), _abi.fptr(to))
+    assert np.max(np.abs(tg - to)) < 1e-6
+    ang = np.concatenate([rng.random(5000) * np.pi, [0.0, np.pi]]).astype(np.float32)
+    pg, po = np.zeros_like(ang), np.zeros_like(ang)
+    assert cuda.lookup_phase_function(G.handle, 0, 0, 1, ang.size, _abi.fptr(ang), _abi.fptr(pg)) == 0
+    oracle.lookup_phase_function(O.handle, 0, 0, 1, ang.size, _abi.fptr(ang), _abi.fptr(po))
+    assert np.max(np.abs(pg - po) / np.abs(po)) < 1e-5
+
+
+@pytest.mark.parametrize("field", ["stepCloud", "landsat", "irregular"])
+def test_optical_path_along_fixed_rays(cuda, oracle, field):
+    """accumulateExtinctionAlongPath on the device vs exact float64 integration (1e-5) and vs the oracle."""
+    from tests.hostsim.binding import dense_from_domain
+    from tests.test_oracle_pins import _f64_optical_path
+    if field == "stepCloud":
+        d = fields.step_cloud(1.0)
+    elif field == "landsat":
+        d = fields.landsat_cloud(1.0, nLegendreCoefficients=8)
+    else:
+        d = _irregular_domain()
+    tot = dense_from_domain(d)[0].astype(np.float64)
+    G, O = make_integrator(cuda, d, surfaceAlbedo=0.0), make_integrator(oracle, d, surfaceAlbedo=0.0)
+    rng = np.random.default_rng(11)
+    n = 300
+    lo = np.array([d.xPosition[0], d.yPosition[0], d.zPosition[0]], np.float64)
+    hi = np.array([d.xPosition[-1], d.yPosition[-1], d.zPosition[-1]], np.float64)
+    pos = (lo + (0.02 + 0.96 * rng.random((n, 3))) * (hi - lo)).astype(np.float32)
+    mu = rng.uniform(0.15, 1.0, n) * rng.choice([-1, 1], n)
+    phi = rng.uniform(0, 2 * np.pi, n)
+    u = np.column_stack([np.sqrt(1 - mu**2) * np.cos(phi), np.sqrt(1 - mu**2) * np.sin(phi), mu]).astype(np.float32)
+    tau, _, idx = traceRays(G, pos, u)
+    exact = np.array([_f64_optical_path(d, tot, pos[i], u[i]) for i in range(n)])
+    big = exact > 1e-2
+    assert np.max(np.abs(tau[big] - exact[big]) / exact[big]) < 1e-5
+    tau_o, _, idx_o = traceRays(O, pos, u)
+    tol_oracle = 5e-5 if field == "stepCloud" else 2e-3  # the reference's absolute float32 positions (see CPU test)
+    assert np.max(np.abs(tau[big] - tau_o[big]) / exact[big]) < tol_oracle
+    assert np.array_equal(idx[:, 2], idx_o[:, 2])
+    # with an optical-path limit: same end cell, same end point
+    lim = (exact * rng.uniform(0.05, 0.9, n)).astype(np.float32)
+    tg, pg, ig = traceRays(G, pos, u, lim)
+    to, po, io = traceRays(O, pos, u, lim)
+    assert np.allclose(tg, lim, rtol=1e-6) and np.allclose(to, lim, rtol=1e-6)
+    same = np.all(ig == io, axis=1)
+    assert same.mean() > 0.97  # end points within an ulp of a cell face may be attributed to either cell
+    L = hi - lo
+    dpos = np.abs(pg[same] - po[same])
+    dpos[:, :2] = np.minimum(dpos[:, :2], L[:2] - dpos[:, :2])
+    assert dpos.max() < 2e-3 * max(1.0, L.max() / 500.0)
+
+
+def _irregular_domain():
+    """Irregular x, y and z spacing exercises findIndex-style location and per-cell widths (MCRT:1371-1372, 1386)."""
+    from i3rc_monte_carlo_model_b200.opticalProperties import addOpticalComponent, new_Domain
+    rng = np.random.default_rng(4)
+    x = np.concatenate([[0.0], np.cumsum(rng.uniform(20, 80, 12))]).astype(np.float32)
+    y = np.concatenate([[0.0], np.cumsum(rng.uniform(30, 60, 9))]).astype(np.float32)
+    z = np.concatenate([[0.0], np.cumsum(rng.uniform(10, 50, 14))]).astype(np.float32)
+    d = new_Domain(x, y, z)
+    assert not d.xyRegularlySpaced and not d.zRegularlySpaced
+    ext = (rng.random((12, 9, 14)) ** 3 * 0.02).astype(np.float32)
+    ext[rng.random(ext.shape) < 0.3] = 0
+    pfi = np.where(ext > 0, 1, 0).astype(np.int32)
+    addOpticalComponent(d, "cloud", ext, np.where(ext > 0, 0.95, 0).astype(np.float32), pfi, fields._hg_table(0.8, 32))
+    return d
+
+
+# ---- statistical parity against the oracle ------------------------------------------------------------------------
+STAT_CASES = {
+    "C1-planeParallel-flux": (lambda: fields.plane_parallel(), dict(surfaceAlbedo=0.0), dict(solarMu=0.5, solarAzimuth=0.0), 8000),
+    "C1-planeParallel-radiance-nml": (lambda: fields.plane_parallel(), dict(
+        surfaceAlbedo=0.0, intensityMus=[1.0, 0.5, 0.5], intensityPhis=[0.0, 0.0, 180.0],
+        useRussianRouletteForIntensity=False), dict(solarMu=0.5, solarAzimuth=0.0), 4000),
+    "C2-stepCloud-conservative-radiance": (lambda: fields.step_cloud(1.0), dict(
+        surfaceAlbedo=0.0, intensityMus=[1.0, 0.5, 0.5], intensityPhis=[0.0, 0.0, 180.0],
+        useRussianRouletteForIntensity=True, zetaMin=0.3), dict(solarMu=0.5, solarAzimuth=0.0), 3000),
+    "C2-stepCloud-absorbing-overhead-sun": (lambda: fields.step_cloud(0.99), dict(
+        surfaceAlbedo=0.2, intensityMus=[1.0, -0.5], intensityPhis=[0.0, 90.0], useRussianRouletteForIntensity=False),
+        dict(solarMu=1.0, solarAzimuth=0.0), 1500),
+    "max-cross-section": (lambda: fields.step_cloud(0.99), dict(surfaceAlbedo=0.3, useRayTracing=False),
+                          dict(solarMu=0.5, solarAzimuth=0.0), 3000),
+    "irregular-grid-radiance": (_irregular_domain, dict(
+        surfaceAlbedo=0.4, intensityMus=[0.8], intensityPhis=[45.0], useRussianRouletteForIntensity=True, zetaMin=0.2),
+        dict(solarMu=0.7, solarAzimuth=200.0), 3000),
+    "two-components-hybrid-limited": (lambda: fields.synthetic_les(nx=16, ny=16, nz=24, n_entries=4, seed=5), dict(
+        surfaceAlbedo=0.1, intensityMus=[1.0], intensityPhis=[0.0], useHybridPhaseFunsForIntenCalcs=True,
+        hybridPhaseFunWidth=7.0, numOrdersOrigPhaseFunIntenCalcs=1, limitIntensityContributions=True,
+        maxIntensityContribution=0.5, useRussianRouletteForIntensity=False), dict(solarMu=0.6, solarAzimuth=20.0), 2000),
+    "no-roulette-tabulated": (lambda: fields.plane_parallel(useMoments=False, SSA=0.9, nX=3, nY=2, nLayers=4), dict(
+        surfaceAlbedo=0.5, useRussianRoulette=False), dict(solarMu=0.5, solarAzimuth=0.0), 4000),
+    "source-random-azimuth": (lambda: fields.step_cloud(0.99), dict(surfaceAlbedo=0.0), dict(solarMu=0.6), 3000),
+    "source-flux": (lambda: fields.step_cloud(0.99), dict(surfaceAlbedo=0.0), dict(), 3000),
+    "source-spotlight": (lambda: fields.step_cloud(0.99), dict(surfaceAlbedo=0.0),
+                         dict(solarMu=0.5, solarAzimuth=30.0, solarX=0.7, solarY=0.5), 3000),
+    "source-internal-flux": (lambda: fields.step_cloud(0.99), dict(surfaceAlbedo=0.3),
+                             dict(detectorX=0.3, detectorY=0.5, detectorZ=0.5, detectorPointsUp=False), 3000),
+    "source-internal-intensity": (lambda: fields.step_cloud(0.99), dict(surfaceAlbedo=0.3),
+                                  dict(detectorX=0.3, detectorY=0.5, detectorZ=0.6, detectorMu=0.7, detectorPhi=1.0), 3000),
+}
+
+
+@pytest.mark.parametrize("name", list(STAT_CASES))
+def test_statistical_parity_with_oracle(cuda, oracle, name):
+    make, params, source, nph = STAT_CASES[name]
+    d = make()
+    nb = 32
+    got = run_batches(make_integrator(cuda, d, **params), nph, nb, source=source)
+    ref = run_batches(make_integrator(oracle, d, **params), nph, nb, source=source)
+    assert_statistical_parity(got, ref, label=name + ": ")
+    gc, rc = got["counters"], ref["counters"]
+    assert gc["photons"] == nph and gc["bad"] == 0
+    for c in ("collisions", "surface_hits", "exits_top"):
+        a, b = gc[c] / gc["photons"], rc[c] / rc["photons"]
+        assert abs(a - b) <= 0.08 * max(b, 0.05) + 0.03, (c, a, b)
+
+
+def test_surface_brdf_map(cuda, oracle):
+    """specifyParameters(surfaceBDRF = ...) with a Lambertian albedo map (surfaceProperties.f95:60-162)."""
+    d = fields.plane_parallel(nX=4, nY=2, opticalDepth=0.3)
+    xs, ys = np.array([0.0, 250.0, 500.0], np.float32), np.array([0.0, 500.0], np.float32)
+    res = {}
+    for name, be in (("g", cuda), ("o", oracle)):
+        surf = new_SurfaceDescription(np.array([[[0.8], [0.1]]], np.float32), xs, ys)
+        I = make_integrator(be, d, surfaceBDRF=surf, intensityMus=[1.0], intensityPhis=[0.0], useRussianRouletteForIntensity=False)
+        res[name] = run_batches(I, 4000, 32, source=dict(solarMu=0.8, solarAzimuth=0.0))
+    assert_statistical_parity(res["g"], res["o"], label="brdf: ")
+    up = res["g"]["fluxUp"].mean(0)
+    assert up[:2].mean() > 2.5 * up[2:].mean()  # bright half reflects more
+
+
+def test_photon_arrays_source(cuda, oracle):
+    """The public array components of type(photonStream) (monteCarloIllumination.f95:34-41) filled by hand."""
+    d = fields.step_cloud(0.99)
+    rng = np.random.default_rng(1)
+    n = 5000
+    res = {}
+    for name, be in (("g", cuda), ("o", oracle)):
+        I = make_integrator(be, d, surfaceAlbedo=0.0)
+        vals = []
+        for b in range(16):
+            r2 = np.random.default_rng(100 + b)
+            ph = new_PhotonStream(0.5, 0.0, numberOfPhotons=n)
+            ph.xPosition, ph.yPosition = r2.random(n, dtype=np.float32), r2.random(n, dtype=np.float32)
+            ph.zPosition = np.full(n, 1.0 - np.finfo(np.float32).eps, np.float32)
+            ph.initialMu, ph.initialPhi = np.full(n, -0.5, np.float32), np.zeros(n, np.float32)
+            computeRadiativeTransfer(I, new_RandomNumberSequence([10, b + 1]), ph)
+            r = reportResults(I, "meanFluxUp", "meanFluxDown", "meanFluxAbsorbed", "fluxUp")
+            vals.append(r)
+        res[name] = {k: np.stack([np.asarray(v[k], np.float64) for v in vals]) for k in vals[0]}
+    assert_statistical_parity(res["g"], res["o"], label="arrays: ")
+
+
+# ---- golden fixtures (oracle outputs at larger sizes) ------------------------------------------------------------
+def _coarsen(a, f=8):
+    nx, ny = a.shape[0], a.shape[1]
+    if nx % f or ny % f:
+        return a
+    return a.reshape(nx // f, f, ny // f, f, *a.shape[2:]).mean(axis=(1, 3))
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_against_golden_fixture(cuda, name):
+    make, params, source, nph, nb = GOLDEN_CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    I = make_integrator(cuda, make(), **params)
+    nbg = 16
+    got = run_batches(I, nph * 2, nbg, source=source)
+    for k in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed"):
+        m, s = mean_se(got[k])
+        z = (m - g[k + "_mean"]) / np.hypot(s, g[k + "_se"])
+        assert abs(z) < 3.0 + 0.5, (name, k, z)
+    m, s = mean_se(got["absorbedProfile"])
+    z = (m - g["absorbedProfile_mean"]) / np.sqrt(s**2 + g["absorbedProfile_se"] ** 2 + 1e-20)
+    assert np.abs(z).max() < 4.5, (name, "absorbedProfile", np.abs(z).max())
+    if "meanRadiance_mean" in g.files:
+        m, s = mean_se(got["meanIntensity"])
+        z = (m - g["meanRadiance_mean"]) / np.hypot(s, g["meanRadiance_se"])
+        assert np.all(np.abs(z) < 3.0 + 0.5), (name, "meanRadiance", z)
+        # per-column radiance, coarsened to blocks of 8x8 columns
+        gm, gs = g["radiance_mean"].transpose(2, 1, 0), g["radiance_se"].transpose(2, 1, 0)  # [x, y, d]
+        m, s = mean_se(np.stack([_coarsen(b) for b in got["intensity"]]))
+        gm_c = _coarsen(gm)
+        gs_c = np.sqrt(_coarsen(gs**2) / (gm.size / gm_c.size)) if gm_c.shape != gm.shape else gs
+        z = (m - gm_c) / np.sqrt(s**2 + gs_c**2 + 1e-20)
+        assert np.abs(z).max() < 5.0 and np.mean(z**2) < 1.6, (name, "radiance", np.abs(z).max(), np.mean(z**2))
+    # per-column upward flux, coarsened
+    gm, gs = g["fluxUp_mean"].T, g["fluxUp_se"].T
+    m, s = mean_se(np.stack([_coarsen(b) for b in got["fluxUp"]]))
+    gm_c = _coarsen(gm)
+    gs_c = np.sqrt(_coarsen(gs**2) / (gm.size / gm_c.size)) if gm_c.shape != gm.shape else gs
+    z = (m - gm_c) / np.sqrt(s**2 + gs_c**2 + 1e-20)
+    assert np.abs(z).max() < 5.0 and np.mean(z**2) < 1.6, (name, "fluxUp", np.abs(z).max(), np.mean(z**2))
+    cnt = got["counters"]
+    for c in ("collisions", "crossings_photon"):
+        a, b = cnt[c] / cnt["photons"], float(g["cnt_" + c]) / float(g["cnt_photons"])
+        assert abs(a - b) < 0.03 * b + 0.02, (c, a, b)
+
+
+# ---- size-independent properties at benchmark size ---------------------------------------------------------------
+def test_properties_at_landsat_benchmark_size(cuda):
+    """Energy closure, column absorption = integral of the volume absorption, reproducibility per (seed, batch),
+    independence of the launch shape, and agreement of the device batch loop with the host loop."""
+    d = fields.landsat_cloud(0.99)
+    params = dict(surfaceAlbedo=0.3, intensityMus=[1.0, 0.5], intensityPhis=[0.0, 180.0], useRussianRouletteForIntensity=True,
+                  zetaMin=0.3)
+    I = make_integrator(cuda, d, **params)
+    nph = 2_000_000
+    r = run_batches(I, nph, 4, want=["meanFluxUp", "meanFluxDown", "meanFluxAbsorbed", "fluxAbsorbed", "volumeAbsorption",
+                                       "fluxUp", "intensity", "meanIntensity"])
+    closure = r["meanFluxUp"] + r["meanFluxAbsorbed"] + 0.7 * r["meanFluxDown"]
+    assert np.all(np.abs(closure - 1.0) < 2e-3)
+    dz = np.diff(d.zPosition)
+    col = (r["volumeAbsorption"][0] * dz[None, None, :]).sum(-1)
+    assert np.allclose(col, r["fluxAbsorbed"][0], rtol=5e-4, atol=1e-5)
+    assert r["counters"]["photons"] == nph and r["counters"]["bad"] == 0
+    # same (iseed, batch) -> same photons: results agree to float32 atomic-summation order
+    again = run_batches(I, nph, 1, want=["meanFluxUp", "fluxUp", "intensity"])
+    assert abs(again["meanFluxUp"][0] - r["meanFluxUp"][0]) < 2e-6
+    assert np.allclose(again["fluxUp"][0], r["fluxUp"][0], rtol=2e-4, atol=1e-5)
+    # ... independently of the launch shape (per-photon counter-based streams)
+    I2 = copy_Integrator(I)
+    assert cuda.set_tuning(I2.handle, b"block_size", 256) == 0 and cuda.set_tuning(I2.handle, b"steps_per_event_phase", 3) == 0
+    other = run_batches(I2, nph, 1, want=["meanFluxUp", "fluxUp", "meanIntensity"])
+    assert abs(other["meanFluxUp"][0] - r["meanFluxUp"][0]) < 2e-6
+    assert np.allclose(other["meanIntensity"][0], r["meanIntensity"][0], rtol=1e-4)
+    assert other["counters"]["collisions"] == again["counters"]["collisions"]
+
+
+def test_device_batch_loop_equals_host_loop(cuda):
+    """i3rc_run_batches + device moments (monteCarloDriver.f95:300-378) == the same loop through reportResults."""
+    d = fields.step_cloud(0.99)
+    params = dict(surfaceAlbedo=0.2, intensityMus=[1.0, 0.5], intensityPhis=[0.0, 180.0], useRussianRouletteForIntensity=True)
+    src = dict(solarMu=0.5, solarAzimuth=0.0)
+    nB, mine = partition_batches(6, 1, 0)
+    I = make_integrator(cuda, d, **params)
+    host = run_batches_host(I, src, 20000, mine, iseed=10).finish(2.0, nB)
+    run_batches_device(I, src, 20000, mine, iseed=10, with_volume=True)
+    allreduce_device_stats(I, None)
+    dev = device_stats_report(I, 2.0, nB, with_volume=True)
+    pairs = [("meanFluxUp", "meanFluxUp"), ("fluxUp", "fluxUp"), ("fluxAbsorbed", "fluxAbsorbed"),
+             ("absorbedProfile", "absorbedProfile"), ("intensity", "radiance"), ("meanIntensity", "meanRadiance")]
+    for hk, dk in pairs:
+        hm, he = host[hk]
+        dm, de = dev[dk]
+        assert np.allclose(np.squeeze(dm), np.squeeze(hm), rtol=3e-4, atol=1e-6), hk
+        assert np.allclose(np.squeeze(de), np.squeeze(he), rtol=2e-2, atol=1e-5), hk
+
+
+def test_dense_and_component_constructors_agree(cuda):
+    """new_Integrator from dense arrays == new_Integrator(domain) with the expansion done on the device."""
+    from tests.hostsim.binding import dense_from_domain
+    d = fields.synthetic_les(nx=16, ny=16, nz=24, n_entries=4, seed=5)
+    tot, cum, ssa, pfi = dense_from_domain(d)
+    A = make_integrator(cuda, d, surfaceAlbedo=0.1)
+    B = new_Integrator_dense(d.xPosition, d.yPosition, d.zPosition, tot, cum, ssa, pfi, [c.table for c in d.components], backend=cuda)
+    specifyParameters(B, surfaceAlbedo=0.1)
+    ra = run_batches(A, 20000, 2)
+    rb = run_batches(B, 20000, 2)
+    assert np.allclose(ra["fluxUp"], rb["fluxUp"], rtol=2e-4, atol=1e-5)
+    assert ra["counters"]["collisions"] == rb["counters"]["collisions"]
+
+
+# ---- edge cases and status behaviour on the CUDA library ------------------------------------------------------
+@pytest.mark.parametrize("nph", [1, 31, 33, 1000])
+def test_ragged_photon_counts(cuda, nph):
+    I = make_integrator(cuda, fields.plane_parallel(), surfaceAlbedo=0.0)
+    r = run_batches(I, nph, 2)
+    assert r["counters"]["photons"] == nph
+    assert np.allclose(r["meanFluxUp"] + r["meanFluxDown"], 1.0, atol=1e-6)
+
+
+@pytest.mark.parametrize("kw,state,text", SPECIFY_CASES)
+def test_specifyParameters_status_cuda(cuda, kw, state, text):
+    check_specify(cuda, kw, state, text)
+
+
+def test_compute_status_cuda(cuda):
+    status = ErrorMessage()
+    I = new_Integrator(fields.plane_parallel(), status=status, backend=cuda)
+    ph = new_PhotonStream(0.5, 0.0, numberOfPhotons=10)
+    ph.source.solarMu = 2.0
+    computeRadiativeTransfer(I, new_RandomNumberSequence([1, 2]), ph, status=status)
+    assert stateIsFailure(status) and "solarMu out of bounds" in getCurrentMessage(status)
+    status = ErrorMessage()
+    r = reportResults(I, "intensity", status=status)
+    assert stateIsFailure(status) and "intensity information not available" in getCurrentMessage(status)
