@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- photons/s of the photon-tracing hot path (computeRadiativeTransfer incl. local-estimate radiances).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                     (the CPU arm: the oracle port on all host threads)
+
+A "step" is one batch: one pass of the hot path over `--photons` photons of synthetic illumination on the named
+workload (default: the I3RC Landsat cloud, BASELINE.json configs[2], the configuration the north-star target is
+quoted on), including normalisation and the batch-moment update.  Ranks are independent (batches are sharded like
+Example-Drivers/monteCarloDriver.f95:264-274, weak scaling); the only collective is ONE all-reduce of the packed
+moment buffer after the last step.
+
+Timing: every step is bracketed by CUDA events on the stream the kernels are launched on; L2 is flushed (256 MiB
+memset) between steps outside the brackets; a barrier + synchronize surrounds the K steps; the slowest rank counts.
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "photons/sec (incl. local-estimate radiances)"
+UNIT = "photons/s"
+
+
+# ---- workloads ------------------------------------------------------------------------------
+def make_workload(name):
+    from i3rc_monte_carlo_model_b200 import fields
+    rr = dict(useRayTracing=True, useRussianRoulette=True, useRussianRouletteForIntensity=True, zetaMin=0.3,
+              minInverseTableSize=10001, minForwardTableSize=10001)
+    dirs3 = dict(intensityMus=[1.0, 0.5, 0.5], intensityPhis=[0.0, 0.0, 180.0])  # monteCarloDriver.nml
+    src = dict(solarMu=0.5, solarAzimuth=0.0)
+    if name == "landsat":
+        return dict(workload="i3rcLandsatCloud 128x128x119, HG g=0.85 (299 moments), ssa=1, mu0=0.5, 3 radiance directions, "
+                             "Russian roulette for intensity (zetaMin 0.3)",
+                    domain=lambda: fields.landsat_cloud(1.0), params=dict(surfaceAlbedo=0.0, **dirs3, **rr), source=src,
+                    photons=4_000_000, cpu_photons=60_000)
+    if name == "step":
+        return dict(workload="i3rcStepCloud 32x1x32, HG g=0.85 (64 moments), ssa=0.99, mu0=0.5, 3 radiance directions, RR",
+                    domain=lambda: fields.step_cloud(0.99), params=dict(surfaceAlbedo=0.0, **dirs3, **rr), source=src,
+                    photons=4_000_000, cpu_photons=200_000)
+    if name == "planeparallel":
+        return dict(workload="planeParallel.nml 1x1x1 tau=1 HG g=0.85, 3 radiance directions, plain local estimate",
+                    domain=lambda: fields.plane_parallel(),
+                    params=dict(surfaceAlbedo=0.0, useRussianRouletteForIntensity=False, **dirs3), source=src,
+                    photons=8_000_000, cpu_photons=1_000_000)
+    if name == "radar":
+        return dict(workload="i3rcRadarCloud 640x1x54, Deirmendjian C1 (tabulated), ssa=0.99, mu0=0.5, 3 radiance directions, RR",
+                    domain=lambda: fields.radar_cloud(0.99, "C1"), params=dict(surfaceAlbedo=0.0, **dirs3, **rr), source=src,
+                    photons=2_000_000, cpu_photons=40_000)
+    if name in ("les", "les-small"):
+        n = (512, 512, 256) if name == "les" else (128, 128, 64)
+        mus = [1.0, 0.8, 0.6, 0.4]
+        return dict(workload=f"synthetic LES {n[0]}x{n[1]}x{n[2]}, 2 components (27-entry cloud table + absorbing gas), "
+                             "16 radiance directions, RR",
+                    domain=lambda: fields.synthetic_les(nx=n[0], ny=n[1], nz=n[2]),
+                    params=dict(surfaceAlbedo=0.05, intensityMus=[m for m in mus for _ in range(4)],
+                                intensityPhis=[p for _ in mus for p in (0.0, 90.0, 180.0, 270.0)], **rr),
+                    source=dict(solarMu=0.5, solarAzimuth=30.0), photons=2_000_000, cpu_photons=20_000)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def algorithmic_bytes(c, nc):
+    """4 B per cell crossing (totalExt) + (4 nC + 16) B per collision (cumExt, ssa, pfIdx, 2 inverse-table
+    entries) + 32 B per absorption (two read-modify-writes) + 24 B per local-estimate contribution (2 forward-table
+    entries + one read-modify-write) + 8 B per photon exit (one read-modify-write)."""
+    return (4 * (c["crossings_photon"] + c["crossings_intensity"]) + (4 * nc + 16) * c["collisions"] + 32 * c["absorptions"]
+            + 24 * c["contributions"] + 8 * (c["exits_top"] + c["surface_hits"]))
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        try:
+            for line in open(self.path):
+                p = [t.strip() for t in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                    power.append(float(p[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return None
+        busy = [s for s, w in zip(sm, power) if w > 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": float(max(power))}
+
+
+def timing_of(be, I):
+    ms, nl, no = C.c_double(), C.c_int64(), C.c_int64()
+    be.get_timing(I.handle, C.byref(ms), C.byref(nl), C.byref(no))
+    return ms.value, nl.value, no.value
+
+
+# ---- the CPU arm ------------------------------------------------------------------------------------------------
+def cpu_port_rate(wl, seconds, threads=0, nbatches=None):
+    """Photons/s of the oracle port (OpenMP threads stand in for MPI ranks, one batch per thread at a time) on a
+    bounded sample of the workload; returns (rate, cores, description, elapsed)."""
+    from oracle.binding import oracle_backend, run_batches
+    from i3rc_monte_carlo_model_b200.monteCarloIllumination import new_PhotonStream
+    from i3rc_monte_carlo_model_b200.monteCarloRadiativeTransfer import (computeRadiativeTransfer, new_Integrator,
+                                                                        specifyParameters)
+    from i3rc_monte_carlo_model_b200.RandomNumbers import new_RandomNumberSequence
+    be = oracle_backend()
+    cores = threads or os.cpu_count() or 1
+    I = new_Integrator(wl["domain"](), backend=be)
+    specifyParameters(I, **wl["params"])
+    # 1-photon warm-up builds the tables outside the timed region (monteCarloDriver.f95:240-253)
+    computeRadiativeTransfer(I, new_RandomNumberSequence([10, 0]), new_PhotonStream(numberOfPhotons=1, **wl["source"]))
+    nph = wl["cpu_photons"]
+    t0 = time.perf_counter()
+    run_batches(I, new_PhotonStream(numberOfPhotons=max(nph // 8, 100), **wl["source"]), 10, cores, nThreads=cores)
+    probe = time.perf_counter() - t0
+    rate0 = max(nph // 8, 100) * cores / probe
+    if nbatches is None:
+        nph = int(max(1000, min(nph * 8, rate0 * seconds / cores)))
+        nbatches = cores
+    t0 = time.perf_counter()
+    run_batches(I, new_PhotonStream(numberOfPhotons=nph, **wl["source"]), 10, nbatches, batchBegin=1, nThreads=cores)
+    el = time.perf_counter() - t0
+    return nph * nbatches / el, cores, f"{nbatches} batches x {nph} photons of the same workload", el
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    rates, els = [], []
+    per_step = max(2.0, min(20.0, 150.0 / max(args.steps + args.warmup, 1)))
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        r, cores, sample, el = cpu_port_rate(wl, per_step)
+        if i >= args.warmup:
+            rates.append(r)
+            els.append(el)
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean(els) * 1e3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic illumination on the workload's field",
+        "config": {"workload": wl["workload"], "note": "the reference is Fortran 95 and cannot be compiled in this image (no "
+                   "Fortran compiler, MPI or netCDF): this arm times the C restatement of its algorithm (oracle/, OpenMP "
+                   "threads standing in for MPI ranks) on all host threads"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + " per step"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---- the CUDA arm -------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="landsat")
+    ap.add_argument("--photons", type=int, default=0, help="photons per step (batch) and GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tune", default="", help="key=value,... passed to i3rc_set_tuning")
+    args = ap.parse_args()
+    wl = make_workload(args.workload)
+    if args.impl == "reference":
+        return run_reference(args, wl)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    from i3rc_monte_carlo_model_b200 import _abi
+    from i3rc_monte_carlo_model_b200._lib import backend
+    from i3rc_monte_carlo_model_b200.driver import allreduce_device_stats, device_stats_report, partition_batches
+    from i3rc_monte_carlo_model_b200.monteCarloIllumination import new_PhotonStream
+    from i3rc_monte_carlo_model_b200.monteCarloRadiativeTransfer import (computeRadiativeTransfer, getCounters, new_Integrator,
+                                                                        reportResults, specifyParameters)
+    from i3rc_monte_carlo_model_b200.RandomNumbers import new_RandomNumberSequence
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    be = backend()
+    assert be.set_device(local) == 0
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nph = args.photons or wl["photons"]
+    K, W = args.steps, args.warmup
+    I = new_Integrator(wl["domain"](), backend=be)
+    assert I.handle, "new_Integrator failed"
+    specifyParameters(I, **wl["params"])
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        assert be.set_tuning(I.handle, k.encode(), int(v)) == 0, kv
+    src = new_PhotonStream(numberOfPhotons=nph, **wl["source"]).as_c()
+    stream = torch.cuda.ExternalStream(be.stream(I.handle), device=torch.device("cuda", local))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    nB_total, mine = partition_batches(K * world, world, rank)  # rank r: batches r*K+1 .. (r+1)*K
+    mine = list(mine)
+
+    # ---- device-resident arm: photons generated, traced, normalised and folded into the moments on the GPU ----
+    assert be.stats_reset(I.handle, 0) == 0
+    for w in range(W):
+        assert be.run_batches(I.handle, C.byref(src), 10, 0, 1_000_000 + w, 1) == 0, I._msg()
+    assert be.stats_reset(I.handle, 0) == 0
+    be.reset_timing(I.handle)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    counters = dict.fromkeys(_abi.COUNTER_FIELDS, 0)
+    step_ms = []
+    wall0 = time.perf_counter()
+    for b in mine:
+        flush.zero_()  # L2 flush between timed steps, outside the event brackets
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        rc = be.run_batches(I.handle, C.byref(src), 10, 0, b, 1)
+        e1.record(stream)
+        assert rc == 0, I._msg()
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        for k, v in getCounters(I).items():
+            counters[k] += v
+    t_ar0 = time.perf_counter()
+    allreduce_device_stats(I, dist if world > 1 else None)  # the ONE collective of the job
+    be.synchronize(I.handle)
+    allreduce_ms = (time.perf_counter() - t_ar0) * 1e3
+    barrier()
+    wall_ms = (time.perf_counter() - wall0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    trace_ms, trace_launches, other_launches = timing_of(be, I)
+    dev_ms = float(sum(step_ms)) + allreduce_ms
+    if world > 1:
+        t = torch.tensor([dev_ms, wall_ms, trace_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms, trace_ms_max = t.tolist()
+        cs = torch.tensor([counters[k] for k in _abi.COUNTER_FIELDS], device="cuda", dtype=torch.int64)
+        dist.all_reduce(cs)
+        counters_all = dict(zip(_abi.COUNTER_FIELDS, cs.tolist()))
+    else:
+        counters_all = counters
+    total_photons = nph * K * world
+    value = total_photons / (dev_ms * 1e-3)
+    stats = device_stats_report(I, 1.0, nB_total)
+
+    # ---- end-to-end arm: the reference's own call sequence per batch with HOST buffers ----
+    e2e = None
+    if not args.no_e2e:
+        rng = np.random.default_rng(1234 + rank)
+
+        def pinned(n):
+            return torch.empty(n, dtype=torch.float32).pin_memory().numpy()
+
+        ph = new_PhotonStream(numberOfPhotons=nph, **wl["source"])
+        ph.xPosition, ph.yPosition, ph.zPosition, ph.initialMu, ph.initialPhi = (pinned(nph) for _ in range(5))
+        ph.xPosition[:] = rng.random(nph, dtype=np.float32)
+        ph.yPosition[:] = rng.random(nph, dtype=np.float32)
+        ph.zPosition[:] = np.float32(1.0) - np.finfo(np.float32).eps
+        ph.initialMu[:] = -abs(wl["source"].get("solarMu", 0.5))
+        ph.initialPhi[:] = np.float32(wl["source"].get("solarAzimuth", 0.0) * np.pi / 180.0)
+        want = ["meanFluxUp", "meanFluxDown", "meanFluxAbsorbed", "fluxUp", "fluxDown", "fluxAbsorbed", "absorbedProfile",
+                "meanIntensity", "intensity"]
+        out = {"fluxUp": pinned(I.nx * I.ny).reshape((I.nx, I.ny), order="F"),
+               "fluxDown": pinned(I.nx * I.ny).reshape((I.nx, I.ny), order="F"),
+               "fluxAbsorbed": pinned(I.nx * I.ny).reshape((I.nx, I.ny), order="F"),
+               "intensity": pinned(I.nx * I.ny * I.nDir).reshape((I.nx, I.ny, I.nDir), order="F")}
+        d2h = 4 * (3 * I.nx * I.ny + I.nz + I.nx * I.ny * I.nDir + 3 + I.nDir) + C.sizeof(_abi.Counters)
+        h2d = 5 * 4 * nph + C.sizeof(_abi.PhotonSource)
+        for w in range(2):
+            computeRadiativeTransfer(I, new_RandomNumberSequence([11, 2_000_000 + w]), ph)
+        barrier()
+        t0 = time.perf_counter()
+        for b in mine:
+            computeRadiativeTransfer(I, new_RandomNumberSequence([11, b]), ph)  # H2D of the photon arrays + kernel
+            r = reportResults(I, *want, out=out)                                # D2H into host arrays
+        be.synchronize(I.handle)
+        el = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([el], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = t.item()
+        e2e = {"value": total_photons / el, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": el * 1e3 / K, "path": "new_PhotonStream arrays (host, pinned) -> i3rc_computeRadiativeTransfer -> "
+               "i3rc_reportResults into host arrays, per batch", "meanFluxUp_last": float(r["meanFluxUp"])}
+    barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (k_transport) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    nc = I.nc
+    abytes = algorithmic_bytes(counters, nc)  # this rank's launches
+    launches = max(trace_launches, 1)
+    achieved = abytes / launches / (trace_ms / launches * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "transport_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    crossings = counters["crossings_photon"] + counters["crossings_intensity"]
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+                "kernel": "k_transport", "kernel_ms_per_launch": trace_ms / launches, "kernel_share_of_step": trace_ms / max(sum(step_ms), 1e-9),
+                "algorithmic_bytes_per_launch": abytes / launches, "cell_crossings_per_s": crossings / (trace_ms * 1e-3),
+                "bytes_per_crossing_model": "4 B/crossing + (4nC+16) B/collision + 32 B/absorption + 24 B/contribution + 8 B/exit",
+                "note": "fields are L2-resident on this workload (7.8 MB per field): the kernel is latency/issue bound, not HBM bound"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, cores, sample, el = cpu_port_rate(wl, 15.0)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "note": "C restatement of the reference (oracle/), OpenMP threads standing in for MPI ranks; the Fortran reference "
+                       "cannot be built in this image"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic illumination (photons drawn on the device from Philox streams) on the I3RC field shipped as a fixture"
+                if args.workload in ("landsat", "radar") else "synthetic",
+        "config": {"workload": wl["workload"], "photons_per_step_per_gpu": nph, "parallelism": f"batches sharded over {world} GPU(s), "
+                   "replicated domain, one all-reduce of the moment buffer", "l2": "flushed between steps (256 MiB memset), "
+                   "flush outside the CUDA-event brackets", "timing": "sum of per-step CUDA-event times on the launching stream + final "
+                   "all-reduce, max over ranks", "tuning": args.tune or "default"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(trace_launches + other_launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "wall_ms_timed_region": wall_ms, "allreduce_ms": allreduce_ms,
+        "counters_per_photon": {k: v / (nph * K * world) for k, v in counters_all.items() if v},
+        "results": {"meanFluxUp": [float(stats["meanFluxUp"][0]), float(stats["meanFluxUp"][1])],
+                    "meanFluxDown": [float(stats["meanFluxDown"][0]), float(stats["meanFluxDown"][1])],
+                    "meanRadiance": [[float(m), float(e)] for m, e in zip(np.ravel(stats["meanRadiance"][0]), np.ravel(stats["meanRadiance"][1]))]
+                    if "meanRadiance" in stats else None},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

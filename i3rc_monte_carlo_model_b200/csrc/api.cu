@@ -1272,7 +1272,7 @@ int i3rc_stats_accumulate(i3rc_integrator* h) {
   k_moments_f<<<gcol, 256, 0, st>>>(h->d_fluxAbs, ncol, S + L.flux[2], S + L.flux[2] + ncol);
   if (nD) k_moments_f<<<(unsigned)((ncol * nD + 255) / 256), 256, 0, st>>>(h->d_intensity, ncol * nD, S + L.rad, S + L.rad + ncol * nD);
   if (h->statsVolume) k_moments_f<<<(unsigned)((ncell + 255) / 256), 256, 0, st>>>(h->d_volAbs, ncell, S + L.vol, S + L.vol + ncell);
-  h->otherLaunches += 14;
+  h->otherLaunches += 11 + (nD ? 3 : 0) + (h->statsVolume ? 1 : 0);
   CUDA_OK(h, cudaGetLastError());
   return I3RC_SUCCESS;
 }

@@ -39,8 +39,29 @@ def run_batches(I, nph, nb, source=None, iseed=10, first_batch=1, want=None):
 
 
 def mean_se(x):
+    """(mean, standard error) over batches; passes an already summarised (mean, se) pair through."""
+    if isinstance(x, tuple):
+        return x
     nb = x.shape[0]
     return x.mean(0), x.std(0, ddof=1) / np.sqrt(nb)
+
+
+def oracle_summary(I, nph, nb, source=None, iseed=10):
+    """The oracle side of a parity test through its OpenMP batch driver (threads stand in for MPI ranks):
+    name -> (mean, standard error), arrays indexed like reportResults ([x, y(, direction)])."""
+    from oracle.binding import run_batches as oracle_run_batches
+    source = source or dict(solarMu=0.5, solarAzimuth=0.0)
+    sums, cnt = oracle_run_batches(I, new_PhotonStream(numberOfPhotons=nph, **source), iseed, nb, seedOrder=0, nThreads=0)
+    out = {}
+    names = {"radiance": "intensity", "meanRadiance": "meanIntensity"}
+    for k, s in sums.items():
+        mean = s[0] / nb
+        se = np.sqrt(np.maximum(s[1] / nb - mean**2, 0.0) / (nb - 1))
+        if mean.ndim >= 2:
+            mean, se = mean.T, se.T
+        out[names.get(k, k)] = (mean, se)
+    out["counters"] = cnt
+    return out
 
 
 def zscores(a, b, floor=0.0):
@@ -57,7 +78,7 @@ def zscores(a, b, floor=0.0):
 def assert_statistical_parity(a, b, keys=None, sigma=SIGMA, per_column_sigma=4.5, label=""):
     """Domain means within `sigma`; per-column fields: no column beyond per_column_sigma (the expected maximum of
     thousands of unit normals) and a chi-square consistent with unit variance."""
-    keys = keys or [k for k in a if k != "counters"]
+    keys = keys or [k for k in a if k != "counters" and k in b]
     for k in keys:
         z = np.atleast_1d(zscores(a[k], b[k], floor=1e-7))
         if z.size <= 32:
