@@ -104,7 +104,7 @@ struct i3rc_integrator {
   double traceMs = 0.0;
   long long traceLaunches = 0, otherLaunches = 0;
   // tuning
-  int blockSize = 128, blocksPerSM = 0, kSteps = 8;
+  int blockSize = 128, blocksPerSM = 0, kSteps = 4, eventThreshold = 16;
   // nccl
   void* nccl = nullptr;
   void* ncclLib = nullptr;
@@ -459,7 +459,7 @@ int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   long long grid = (long long)h->numSMs * perSM;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  k_transport<BLOCK><<<(unsigned)grid, BLOCK, 0, h->stream>>>(p, h->kSteps);
+  k_transport<BLOCK><<<(unsigned)grid, BLOCK, 0, h->stream>>>(p, h->kSteps, h->eventThreshold);
   return I3RC_SUCCESS;
 }
 
@@ -1162,6 +1162,7 @@ int i3rc_copy_Integrator(const i3rc_integrator* s, i3rc_integrator** out) {
   h->blockSize = s->blockSize;
   h->blocksPerSM = s->blocksPerSM;
   h->kSteps = s->kSteps;
+  h->eventThreshold = s->eventThreshold;
   h->message.clear();
   *out = h;
   return I3RC_SUCCESS;
@@ -1440,6 +1441,8 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->blocksPerSM = value;
   else if (k == "steps_per_event_phase" && value >= 1)
     h->kSteps = value;
+  else if (k == "event_threshold" && value >= 1 && value <= 32)
+    h->eventThreshold = value;
   else if (k == "track_by_component")
     h->trackByComponent = value != 0;
   else

@@ -7,47 +7,154 @@
 
 namespace i3rc {
 
-// ---- K1: persistent photon transport ------------------------------------------------------------------
-// grid = (#SMs x resident blocks), every thread owns one photon slot and refills it from the device photon
-// counter (one warp-aggregated atomicAdd per refill round).  Between events all lanes of a warp execute the
-// same DDA cell-crossing step; `kSteps` crossings are taken between two event phases.
+// ---- K1: persistent, warp-cooperative photon transport ---------------------------------------------------------
+// grid = (#SMs x resident blocks).  Every lane owns one photon slot and refills it from the device photon counter
+// (one warp-aggregated atomicAdd per refill round).  A warp alternates between two phases:
+//
+//   EVENT phase  (uniform code over the lanes whose path segment has ended): boundary / collision handling, then a
+//                warp-uniform loop over the radiance directions in which every such lane builds its local-estimate
+//                ray as a 36-byte TASK and pushes it into the warp's shared-memory ring, then roulette + scattering
+//                and the start of the next path segment;
+//   TRACE phase  (one DDA cell crossing per iteration for every lane): a lane traces its own path segment; when that
+//                ends it pops local-estimate tasks -- of ANY photon of the warp -- from the ring and traces those,
+//                so lanes stay busy while the longest segment of the warp is still running.  The phase ends when the
+//                ring is empty and at least `eventThreshold` lanes wait for their event.
+//
+// The physics functions are the ones of transport.cuh; the per-photon Philox streams make the result independent of
+// which lane traces which ray (up to float summation order in the tallies).
+constexpr int QCAP = 128;  // local-estimate tasks per warp (ring, power of two): 4.5 KB of shared memory per warp
+
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_transport(const Problem p, const int kSteps) {
+__global__ void __launch_bounds__(BLOCK) k_transport(const Problem p, const int checkEvery, const int eventThreshold) {
+  __shared__ LeTask s_task[BLOCK / 32][QCAP];
+  __shared__ int s_head[BLOCK / 32];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  LeTask* q = s_task[warp];
+  int* headp = &s_head[warp];
+  int tail = 0;  // warp-uniform; the ring holds positions [head, tail)
+  if (lane == 0) *headp = 0;
+  __syncwarp();
+
   Lane L;
 #pragma unroll
   for (int i = 0; i < CNT_N; i++) L.cnt[i] = 0;
   L.active = 0;
   L.done = DONE_RUN;
   L.mode = MODE_PHOTON;
+  L.nsteps = 0;
+  bool hasRay = false;    // the ray registers hold a ray in flight (own segment if L.mode == MODE_PHOTON)
+  bool pending = false;   // own segment ended, event not processed yet
   bool exhausted = false;
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  for (;;) {
-    // refill finished slots
-    bool need = !L.active && !exhausted;
-    unsigned m = __ballot_sync(full, need);
-    if (m) {
-      unsigned long long base = 0;
-      int leader = __ffs(m) - 1;
-      if (lane == leader) base = atomicAdd(p.nextPhoton, (unsigned long long)__popc(m));
-      base = __shfl_sync(full, base, leader);
-      if (need) {
-        long long id = (long long)base + __popc(m & ((1u << lane) - 1u));
-        if (id < p.src.n)
-          init_photon(p, L, id);
-        else
-          exhausted = true;
+
+  // one DDA crossing for every lane + bookkeeping of finished rays + popping of tasks
+  auto trace_iteration = [&]() {
+    if (hasRay) {
+      if (L.done == DONE_RUN) dda_step(p, L);
+      if (L.done != DONE_RUN) {
+        if (L.mode == MODE_PHOTON) {
+          segment_finished(p, L);
+          pending = true;
+          hasRay = false;
+        } else if (!finish_le_ray(p, L)) {
+          hasRay = false;
+        }
       }
     }
-    if (!__any_sync(full, L.active)) break;
-    // cell crossings
-    for (int k = 0; k < kSteps; k++) {
-      bool stepping = L.active && L.done == DONE_RUN;
-      if (stepping) dda_step(p, L);
-      if (!__any_sync(full, L.active && L.done == DONE_RUN)) break;
+    if (!hasRay && *(volatile int*)headp < tail) {
+      int h = atomicAdd(headp, 1);
+      if (h < tail) {
+        start_le_task(p, L, q[h & (QCAP - 1)]);
+        hasRay = true;
+      }
     }
-    // events
-    if (L.active && L.done != DONE_RUN) handle_event(p, L);
+  };
+  auto fix_head = [&]() {  // pops may overshoot the tail
+    __syncwarp();
+    if (lane == 0 && *headp > tail) *headp = tail;
+    __syncwarp();
+  };
+
+  for (;;) {
+    // ================= EVENT phase =================
+    const bool ev = pending && !hasRay;
+    bool alive = false;
+    if (ev) {
+      pending = false;
+      alive = photon_event(p, L) != 0;
+    }
+    if (p.computeIntensity) {
+      if (__any_sync(full, alive)) {
+        for (int d = 0; d < p.nDir; d++) {
+          LeTask t;
+          const bool push = alive && make_le_task(p, L, d, t);
+          const unsigned m = __ballot_sync(full, push);
+          const int n = __popc(m);
+          if (n == 0) continue;
+          int head = __shfl_sync(full, *(volatile int*)headp, 0);
+          if (tail - head + n > QCAP) {
+            // ring full: every lane (also the ones in the middle of their event) helps to drain it; lanes of this
+            // event phase must be free again before they start their next segment
+            for (;;) {
+              trace_iteration();
+              const bool stillQueued = __shfl_sync(full, *(volatile int*)headp, 0) < tail;
+              if (!stillQueued && !__any_sync(full, ev && hasRay)) break;
+            }
+            fix_head();
+          }
+          if (push) q[(tail + __popc(m & lt)) & (QCAP - 1)] = t;
+          tail += n;
+          __syncwarp();
+        }
+      }
+    }
+    if (alive) {
+      continue_photon(p, L);  // roulette, scattering, start of the next own segment
+      if (L.active) hasRay = true;
+    }
+    // refill finished slots
+    {
+      const bool need = !L.active && !exhausted && !hasRay && !pending;
+      const unsigned m = __ballot_sync(full, need);
+      if (m) {
+        unsigned long long base = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) base = atomicAdd(p.nextPhoton, (unsigned long long)__popc(m));
+        base = __shfl_sync(full, base, leader);
+        if (need) {
+          const long long id = (long long)base + __popc(m & lt);
+          if (id < p.src.n) {
+            init_photon(p, L, id);
+            hasRay = true;
+          } else {
+            exhausted = true;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // ================= TRACE phase =================
+    bool anything = false;
+    // towards the end of a batch fewer lanes hold photons: do not wait for more events than can come
+    const int nActive = __popc(__ballot_sync(full, L.active != 0));
+    const int threshold = min(eventThreshold, max(1, nActive >> 1));
+    for (;;) {
+      for (int k = 0; k < checkEvery; k++) trace_iteration();
+      const unsigned busy = __ballot_sync(full, hasRay);
+      const int ready = __popc(__ballot_sync(full, pending && !hasRay));
+      if (busy == 0) {
+        anything = ready > 0;
+        break;
+      }
+      const bool queued = __shfl_sync(full, *(volatile int*)headp, 0) < tail;
+      if (!queued && ready >= threshold) {
+        anything = true;
+        break;
+      }
+    }
+    fix_head();
+    if (!anything && !__any_sync(full, L.active || !exhausted)) break;
   }
   // flush the per-thread counters: warp reduce, one atomic per warp and counter
 #pragma unroll

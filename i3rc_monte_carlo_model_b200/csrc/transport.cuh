@@ -110,14 +110,19 @@ struct Lane {
   int sgn;
   int done;
   int nsteps;
+  int segDone;  // how the photon's last own segment ended (DONE_*), kept until its event is processed
   // photon
   float fx, fy, fz;
   int cx, cy, cz;
   float ux, uy, uz;
   float w;
   int order;
-  int mode, d, comp, pfi;
-  float phat, tauFree;
+  int mode;        // what the current ray is: MODE_PHOTON (own path segment) or a local-estimate stage
+  int comp, pfi;   // photon: component (0 = surface) and phase-function entry of the last event
+  int d;           // photon: next local-estimate direction to generate (per-lane scheduler only)
+  // local-estimate ray being traced (may belong to ANOTHER lane's photon in the warp-cooperative kernel)
+  int td, tcomp;
+  float tcw, tcfix, ttauFree;
   Rng rng;
   int active;
   uint32_t cnt[CNT_N];
@@ -536,55 +541,214 @@ I3RC_HD float surface_reflectance(const Problem& p, float x, float y) {
   return I3RC_LDG(p.surf_albedo + j * p.surf_nx + i);
 }
 
-// Set up the local-estimate ray towards direction L.d from the event point (MCRT:1473-1510, 1517-1521,
-// 1540-1569).  Returns 0 when the contribution is known to be zero without tracing.
-I3RC_HD int start_le_ray(const Problem& p, Lane& L) {
-  const float* dv = p.dirs + L.d * DIR_STRIDE;
-  float ddx = I3RC_LDG(dv + 0), ddy = I3RC_LDG(dv + 1), ddz = I3RC_LDG(dv + 2);
+// One local-estimate ray as a self-contained task (36 bytes): origin, direction index, stage, and the two possible
+// contribution values, so that ANY lane of the warp can trace it (warp-cooperative kernel) .
+struct LeTask {
+  uint32_t xy;    // ix | iy << 16
+  uint32_t zdmc;  // iz | d << 16 | mode << 21 | comp << 24
+  float fx, fy, fz;
+  float tauLimit;
+  float cw;       // weight * normalised phase function      (contribution = cw * exp(-tau), MCRT:1530,1574)
+  float cfix;     // weight * zetaMin / pi                    (Iwabuchi roulette survivors, MCRT:1556,1584)
+  float tauFree;  // second-stage optical path (MCRT:1576-1578)
+};
+
+// Build the local-estimate task towards direction d from the lane's event point (MCRT:1473-1510, 1540-1569).
+// Returns 0 when the contribution is known to be zero without tracing.
+I3RC_HD int make_le_task(const Problem& p, Lane& L, int d, LeTask& t) {
+  const float* dv = p.dirs + d * DIR_STRIDE;
+  float phat;
   if (L.comp < 1) {
-    L.phat = 1.0f / F_PI;  // quirk Q10 (MCRT:1479)
+    phat = 1.0f / F_PI;  // quirk Q10 (MCRT:1479)
   } else {
-    float proj = L.ux * ddx + L.uy * ddy + L.uz * ddz;
+    float proj = L.ux * I3RC_LDG(dv + 0) + L.uy * I3RC_LDG(dv + 1) + L.uz * I3RC_LDG(dv + 2);
     proj = fminf(fmaxf(proj, -1.0f), 1.0f);
     float ang = acosf(proj);
     const TableDesc& T = p.tables[L.comp - 1];
     const float* tab = (p.useHybrid && L.order <= p.numOrdersOrig) ? T.fwdOrig : T.fwd;
     float val = phase_lookup(tab + (size_t)L.pfi * T.nFwd, T.nFwd, ang);
-    L.phat = val / I3RC_LDG(dv + 6);
+    phat = val / I3RC_LDG(dv + 6);
   }
-  float lim = INFINITY;
-  if (!p.useRRIntensity) {
-    L.mode = MODE_LE_PLAIN;
-  } else {
-    L.tauFree = draw_tau(L);  // MCRT:1542
-    if (F_PI * L.phat <= p.zetaMin) {
+  int mode = MODE_LE_PLAIN;
+  float lim = INFINITY, tauFree = 0.0f;
+  if (p.useRRIntensity) {
+    tauFree = draw_tau(L);  // MCRT:1542
+    if (F_PI * phat <= p.zetaMin) {
       // Iwabuchi Eq 13 (MCRT:1546-1559).  The acceptance draw does not depend on the ray, so it is taken
       // first and rejected rays are never traced (the reference traces them and then discards them).
       float xi = draw(L);
-      if (!(xi <= F_PI * L.phat / p.zetaMin)) return 0;
-      L.mode = MODE_LE_SMALL;
-      lim = L.tauFree;
+      if (!(xi <= F_PI * phat / p.zetaMin)) return 0;
+      mode = MODE_LE_SMALL;
+      lim = tauFree;
     } else {
-      L.mode = MODE_LE_BIG1;  // MCRT:1566-1569
-      lim = -I3RC_LOG(p.zetaMin / fmaxf(F_TINY, F_PI * L.phat));
+      mode = MODE_LE_BIG1;  // MCRT:1566-1569
+      lim = -I3RC_LOG(p.zetaMin / fmaxf(F_TINY, F_PI * phat));
     }
   }
-  start_ray(p, L, ddx, ddy, ddz, I3RC_LDG(dv + 3), I3RC_LDG(dv + 4), I3RC_LDG(dv + 5), lim);
+  t.xy = (uint32_t)L.cx | ((uint32_t)L.cy << 16);
+  t.zdmc = (uint32_t)L.cz | ((uint32_t)d << 16) | ((uint32_t)mode << 21) | ((uint32_t)L.comp << 24);
+  t.fx = L.fx;
+  t.fy = L.fy;
+  t.fz = L.fz;
+  t.tauLimit = lim;
+  t.cw = L.w * phat;
+  t.cfix = L.w * p.zetaMin / F_PI;
+  t.tauFree = tauFree;
   return 1;
+}
+
+// Make the task the lane's current ray.
+I3RC_HD void start_le_task(const Problem& p, Lane& L, const LeTask& t) {
+  int d = (t.zdmc >> 16) & 31;
+  const float* dv = p.dirs + d * DIR_STRIDE;
+  L.td = d;
+  L.mode = (t.zdmc >> 21) & 7;
+  L.tcomp = t.zdmc >> 24;
+  L.tcw = t.cw;
+  L.tcfix = t.cfix;
+  L.ttauFree = t.tauFree;
+  // start_ray reads the origin from (cx,cy,cz ; fx,fy,fz): pass the task's origin without touching the lane's photon
+  int ix = t.xy & 0xffff, iy = t.xy >> 16, iz = t.zdmc & 0xffff;
+  float ddx = I3RC_LDG(dv + 0), ddy = I3RC_LDG(dv + 1), ddz = I3RC_LDG(dv + 2);
+  L.ix = ix;
+  L.iy = iy;
+  L.iz = iz;
+  L.idx = (iz * p.ny + iy) * p.nx + ix;
+  L.iax = I3RC_LDG(dv + 3);
+  L.iay = I3RC_LDG(dv + 4);
+  L.iaz = I3RC_LDG(dv + 5);
+  L.sgn = (ddx >= 0.0f ? 1 : 0) | (ddy >= 0.0f ? 2 : 0) | (ddz >= 0.0f ? 4 : 0);
+  float wx = cell_w(p.xe, p.xyRegular, p.dx, ix);
+  float wy = cell_w(p.ye, p.xyRegular, p.dy, iy);
+  float wz = cell_w(p.ze, p.zRegular, p.dz, iz);
+  L.rx = isinf(L.iax) ? INFINITY : ((L.sgn & 1) ? (1.0f - t.fx) : t.fx) * wx * L.iax;
+  L.ry = isinf(L.iay) ? INFINITY : ((L.sgn & 2) ? (1.0f - t.fy) : t.fy) * wy * L.iay;
+  L.rz = isinf(L.iaz) ? INFINITY : ((L.sgn & 4) ? (1.0f - t.fz) : t.fz) * wz * L.iaz;
+  L.tau = 0.0f;
+  L.tauLimit = t.tauLimit;
+  L.nsteps = 0;
+  L.done = DONE_RUN;
 }
 
 I3RC_HD void tally_intensity(const Problem& p, Lane& L, float c) {
   if (p.limitContrib && c > p.maxContrib) {  // MCRT:1598-1609
-    I3RC_ATOMIC_ADD(p.excess + L.comp * p.nDir + L.d, c - p.maxContrib);
+    I3RC_ATOMIC_ADD(p.excess + L.tcomp * p.nDir + L.td, c - p.maxContrib);
     c = p.maxContrib;
   }
   if (c != 0.0f) {
     int col = L.iy * p.nx + L.ix;
     size_t ncol = (size_t)p.nx * p.ny;
-    I3RC_ATOMIC_ADD(p.intensity + (size_t)L.d * ncol + col, c);
-    if (p.trackByComponent) I3RC_ATOMIC_ADD(p.intByComp + ((size_t)L.comp * p.nDir + L.d) * ncol + col, c);
+    I3RC_ATOMIC_ADD(p.intensity + (size_t)L.td * ncol + col, c);
+    if (p.trackByComponent) I3RC_ATOMIC_ADD(p.intByComp + ((size_t)L.tcomp * p.nDir + L.td) * ncol + col, c);
     L.cnt[CNT_CONTRIB]++;
   }
+}
+
+// A local-estimate ray has stopped (L.done != 0).  Returns 1 when the same ray goes on with its second stage
+// (Iwabuchi's chained trace, MCRT:1576-1578), 0 when it is finished and its contribution has been tallied.
+I3RC_HD int finish_le_ray(const Problem& p, Lane& L) {
+  int done = L.done;
+  L.done = DONE_RUN;
+  L.cnt[CNT_CROSS_LE] += L.nsteps;
+  L.nsteps = 0;
+  float c = 0.0f;
+  if (done != DONE_BAD) {
+    switch (L.mode) {
+      case MODE_LE_PLAIN:  // MCRT:1529-1535
+        c = L.tcw * I3RC_EXP(-L.tau);
+        break;
+      case MODE_LE_BIG1:  // MCRT:1570-1593 (escape is detected at the TOP only: quirk Q4)
+        if (done == DONE_TOP) {
+          c = L.tcw * I3RC_EXP(-L.tau);
+        } else if (done == DONE_INSIDE) {
+          L.mode = MODE_LE_BIG2;
+          L.tau = 0.0f;
+          L.tauLimit = L.ttauFree;
+          return 1;
+        }
+        break;
+      default:  // MODE_LE_SMALL (MCRT:1554-1559), MODE_LE_BIG2 (MCRT:1583-1587)
+        if (done == DONE_TOP) c = L.tcfix;
+        break;
+    }
+  }
+  tally_intensity(p, L, c);
+  return 0;
+}
+
+// The photon's own path segment has stopped: record where (event point) and how, and free the ray registers.
+I3RC_HD void segment_finished(const Problem& p, Lane& L) {
+  L.segDone = L.done;
+  L.done = DONE_RUN;
+  L.cnt[CNT_CROSS_PH] += L.nsteps;
+  L.nsteps = 0;
+  ray_local(p, L, &L.fx, &L.fy, &L.fz);
+  L.cx = L.ix;
+  L.cy = L.iy;
+  L.cz = L.iz;
+}
+
+// Boundary and collision handling of a finished segment up to (not including) the local estimate
+// (MCRT:499-561, 581-649).  Returns 1 if the photon lives on (and then wants its local estimate when
+// computeIntensity), 0 if it is finished.
+I3RC_HD int photon_event(const Problem& p, Lane& L) {
+  const int done = L.segDone;
+  if (done == DONE_BAD) {
+    L.cnt[CNT_BAD]++;
+    L.active = 0;
+    return 0;
+  }
+  if (done == DONE_TOP) {  // MCRT:499-514
+    I3RC_ATOMIC_ADD(p.fluxUp + L.cy * p.nx + L.cx, L.w);
+    L.cnt[CNT_TOP]++;
+    L.active = 0;
+    return 0;
+  }
+  if (done == DONE_BOTTOM) {  // MCRT:515-580
+    L.order++;
+    L.cz = 0;
+    L.fz = 0.0f;
+    I3RC_ATOMIC_ADD(p.fluxDown + L.cy * p.nx + L.cx, L.w);
+    L.cnt[CNT_SURF]++;
+    float mu;
+    do {
+      mu = sqrtf(draw(L));
+    } while (!(fabsf(mu) > 2.0f * F_TINY));
+    float phi = 2.0f * F_PI * draw(L);
+    if (p.useSurfaceBDRF)
+      L.w *= surface_reflectance(p, abs_x(p, L.cx, L.fx), abs_y(p, L.cy, L.fy));
+    else
+      L.w *= p.surfaceAlbedo;
+    if (L.w <= F_TINY) {
+      L.active = 0;
+      return 0;
+    }
+    make_direction(mu, phi, &L.ux, &L.uy, &L.uz);
+    L.comp = 0;
+    L.pfi = 0;
+  } else {  // collision, MCRT:581-668
+    L.order++;
+    L.cnt[CNT_COLL]++;
+    const size_t ncell = (size_t)p.nx * p.ny * p.nz;
+    const size_t cell = ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx;
+    int comp = 1;
+    if (p.nc > 1) {  // findIndex(xi, (/0, cumulativeExt(:)/)), MCRT:637-638
+      float xi = draw(L);
+      while (comp < p.nc && xi >= I3RC_LDG(p.cumExt + (size_t)(comp - 1) * ncell + cell)) comp++;
+    }
+    L.comp = comp;
+    float ssa = I3RC_LDG(p.ssa + (size_t)(comp - 1) * ncell + cell);
+    L.pfi = I3RC_LDG(p.pfIdx + (size_t)(comp - 1) * ncell + cell) - 1;
+    if (L.pfi < 0) L.pfi = 0;
+    if (ssa < 1.0f) {  // MCRT:642-649
+      float a = L.w * (1.0f - ssa);
+      I3RC_ATOMIC_ADD(p.fluxAbs + L.cy * p.nx + L.cx, a);
+      I3RC_ATOMIC_ADD(p.volAbs + cell, a);
+      L.w *= ssa;
+      L.cnt[CNT_ABS]++;
+    }
+  }
+  return 1;
 }
 
 // After the local estimate (or directly, when no intensity is wanted): roulette, scattering, next segment
@@ -610,79 +774,25 @@ I3RC_HD void continue_photon(const Problem& p, Lane& L) {
   start_segment(p, L);
 }
 
-// Walk the local-estimate directions from L.d on; returns when a ray is in flight or all are done.
+// ---- per-lane scheduler (one lane owns the photon AND traces its local-estimate rays one after the other).
+// Used by the single-lane CPU harness of the test-suite and by the deterministic probes; the production kernel
+// (k_transport, kernels.cuh) schedules the same functions warp-cooperatively.
 I3RC_HD void advance_le(const Problem& p, Lane& L) {
   while (L.d < p.nDir) {
-    if (start_le_ray(p, L)) return;
-    L.d++;
+    LeTask t;
+    int d = L.d++;
+    if (make_le_task(p, L, d, t)) {
+      start_le_task(p, L, t);
+      return;
+    }
   }
   continue_photon(p, L);
 }
 
-// A ray has finished (L.done != 0): do what computeRT / computeIntensityContribution do next.
 I3RC_HD void handle_event(const Problem& p, Lane& L) {
-  int done = L.done;
-  L.done = DONE_RUN;
   if (L.mode == MODE_PHOTON) {
-    L.cnt[CNT_CROSS_PH] += L.nsteps;
-    if (done == DONE_BAD) {
-      L.cnt[CNT_BAD]++;
-      L.active = 0;
-      return;
-    }
-    if (done == DONE_TOP) {  // MCRT:499-514
-      I3RC_ATOMIC_ADD(p.fluxUp + L.iy * p.nx + L.ix, L.w);
-      L.cnt[CNT_TOP]++;
-      L.active = 0;
-      return;
-    }
-    ray_local(p, L, &L.fx, &L.fy, &L.fz);
-    L.cx = L.ix;
-    L.cy = L.iy;
-    if (done == DONE_BOTTOM) {  // MCRT:515-580
-      L.order++;
-      L.cz = 0;
-      L.fz = 0.0f;
-      I3RC_ATOMIC_ADD(p.fluxDown + L.cy * p.nx + L.cx, L.w);
-      L.cnt[CNT_SURF]++;
-      float mu;
-      do {
-        mu = sqrtf(draw(L));
-      } while (!(fabsf(mu) > 2.0f * F_TINY));
-      float phi = 2.0f * F_PI * draw(L);
-      if (p.useSurfaceBDRF)
-        L.w *= surface_reflectance(p, abs_x(p, L.cx, L.fx), abs_y(p, L.cy, L.fy));
-      else
-        L.w *= p.surfaceAlbedo;
-      if (L.w <= F_TINY) {
-        L.active = 0;
-        return;
-      }
-      make_direction(mu, phi, &L.ux, &L.uy, &L.uz);
-      L.comp = 0;
-      L.pfi = 0;
-    } else {  // collision, MCRT:581-668
-      L.cz = L.iz;
-      L.order++;
-      L.cnt[CNT_COLL]++;
-      size_t ncell = (size_t)p.nx * p.ny * p.nz;
-      int comp = 1;
-      if (p.nc > 1) {  // findIndex(xi, (/0, cumulativeExt(:)/)), MCRT:637-638
-        float xi = draw(L);
-        while (comp < p.nc && xi >= I3RC_LDG(p.cumExt + (size_t)(comp - 1) * ncell + L.idx)) comp++;
-      }
-      L.comp = comp;
-      float ssa = I3RC_LDG(p.ssa + (size_t)(comp - 1) * ncell + L.idx);
-      L.pfi = I3RC_LDG(p.pfIdx + (size_t)(comp - 1) * ncell + L.idx) - 1;
-      if (L.pfi < 0) L.pfi = 0;
-      if (ssa < 1.0f) {  // MCRT:642-649
-        float a = L.w * (1.0f - ssa);
-        I3RC_ATOMIC_ADD(p.fluxAbs + L.cy * p.nx + L.cx, a);
-        I3RC_ATOMIC_ADD(p.volAbs + L.idx, a);
-        L.w *= ssa;
-        L.cnt[CNT_ABS]++;
-      }
-    }
+    segment_finished(p, L);
+    if (!photon_event(p, L)) return;
     if (p.computeIntensity) {
       L.d = 0;
       advance_le(p, L);
@@ -691,36 +801,7 @@ I3RC_HD void handle_event(const Problem& p, Lane& L) {
     }
     return;
   }
-  // ---- a local-estimate ray has finished ----
-  L.cnt[CNT_CROSS_LE] += L.nsteps;
-  float c = 0.0f;
-  if (done != DONE_BAD) {
-    switch (L.mode) {
-      case MODE_LE_PLAIN:  // MCRT:1529-1535
-        c = L.w * L.phat * I3RC_EXP(-L.tau);
-        break;
-      case MODE_LE_SMALL:  // MCRT:1554-1559 (escape is detected at the TOP only: quirk Q4)
-        if (done == DONE_TOP) c = L.w * p.zetaMin / F_PI;
-        break;
-      case MODE_LE_BIG1:  // MCRT:1570-1593
-        if (done == DONE_TOP) {
-          c = L.w * L.phat * I3RC_EXP(-L.tau);
-        } else if (done == DONE_INSIDE) {
-          // tau reached tauMax inside the domain: chain a second trace of tauFree from here (MCRT:1576-1578)
-          L.mode = MODE_LE_BIG2;
-          L.tau = 0.0f;
-          L.tauLimit = L.tauFree;
-          L.nsteps = 0;
-          return;
-        }
-        break;
-      default:  // MODE_LE_BIG2, MCRT:1583-1587
-        if (done == DONE_TOP) c = L.w * p.zetaMin / F_PI;
-        break;
-    }
-  }
-  tally_intensity(p, L, c);
-  L.d++;
+  if (finish_le_ray(p, L)) return;
   advance_le(p, L);
 }
 
