@@ -15,7 +15,7 @@ namespace i3rc {
 //                warp-uniform loop over the radiance directions in which every such lane builds its local-estimate
 //                ray as a 36-byte TASK and pushes it into the warp's shared-memory ring, then roulette + scattering
 //                and the start of the next path segment;
-//   TRACE phase  (one DDA cell crossing per iteration for every lane): a lane traces its own path segment; when that
+//   TRACE phase  (rounds of a few DDA cell crossings for every lane, then ray bookkeeping for all lanes at once): a lane traces its own path segment; when that
 //                ends it pops local-estimate tasks -- of ANY photon of the warp -- from the ring and traces those,
 //                so lanes stay busy while the longest segment of the warp is still running.  The phase ends when the
 //                ring is empty and at least `eventThreshold` lanes wait for their event.
@@ -25,7 +25,7 @@ namespace i3rc {
 constexpr int QCAP = 128;  // local-estimate tasks per warp (ring, power of two): 4.5 KB of shared memory per warp
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_transport(const Problem p, const int checkEvery, const int eventThreshold) {
+__global__ void __launch_bounds__(BLOCK) k_transport(const Problem p, const int stepsPerRound, const int eventThreshold) {
   __shared__ LeTask s_task[BLOCK / 32][QCAP];
   __shared__ int s_head[BLOCK / 32];
   const unsigned full = 0xffffffffu;
@@ -48,18 +48,19 @@ __global__ void __launch_bounds__(BLOCK) k_transport(const Problem p, const int 
   bool pending = false;   // own segment ended, event not processed yet
   bool exhausted = false;
 
-  // one DDA crossing for every lane + bookkeeping of finished rays + popping of tasks
-  auto trace_iteration = [&]() {
-    if (hasRay) {
-      if (L.done == DONE_RUN) dda_step(p, L);
-      if (L.done != DONE_RUN) {
-        if (L.mode == MODE_PHOTON) {
-          segment_finished(p, L);
-          pending = true;
-          hasRay = false;
-        } else if (!finish_le_ray(p, L)) {
-          hasRay = false;
-        }
+  // `stepsPerRound` DDA crossings for every lane that has a running ray, then -- for all lanes at once, so that the
+  // divergent bookkeeping code runs with as many lanes as possible -- finished rays are closed and idle lanes pop tasks
+  auto trace_round = [&]() {
+#pragma unroll 1
+    for (int k = 0; k < stepsPerRound; k++)
+      if (hasRay && L.done == DONE_RUN) dda_step(p, L);
+    if (hasRay && L.done != DONE_RUN) {
+      if (L.mode == MODE_PHOTON) {
+        segment_finished(p, L);
+        pending = true;
+        hasRay = false;
+      } else if (!finish_le_ray(p, L)) {
+        hasRay = false;
       }
     }
     if (!hasRay && *(volatile int*)headp < tail) {
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(BLOCK) k_transport(const Problem p, const int 
             // ring full: every lane (also the ones in the middle of their event) helps to drain it; lanes of this
             // event phase must be free again before they start their next segment
             for (;;) {
-              trace_iteration();
+              trace_round();
               const bool stillQueued = __shfl_sync(full, *(volatile int*)headp, 0) < tail;
               if (!stillQueued && !__any_sync(full, ev && hasRay)) break;
             }
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(BLOCK) k_transport(const Problem p, const int 
     const int nActive = __popc(__ballot_sync(full, L.active != 0));
     const int threshold = min(eventThreshold, max(1, nActive >> 1));
     for (;;) {
-      for (int k = 0; k < checkEvery; k++) trace_iteration();
+      trace_round();
       const unsigned busy = __ballot_sync(full, hasRay);
       const int ready = __popc(__ballot_sync(full, pending && !hasRay));
       if (busy == 0) {
