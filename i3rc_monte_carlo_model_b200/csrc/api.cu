@@ -104,7 +104,7 @@ struct i3rc_integrator {
   double traceMs = 0.0;
   long long traceLaunches = 0, otherLaunches = 0;
   // tuning
-  int blockSize = 128, blocksPerSM = 0, kSteps = 4, eventThreshold = 16;
+  int blockSize = 128, blocksPerSM = 0, kSteps = 6, eventThreshold = 16;
   // nccl
   void* nccl = nullptr;
   void* ncclLib = nullptr;
@@ -448,19 +448,25 @@ int fill_source(i3rc_integrator* h, const i3rc_photon_source* s, SourceDev& d) {
   return I3RC_SUCCESS;
 }
 
-template <int BLOCK>
+template <int BLOCK, bool REG>
 int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   int perSM = h->blocksPerSM;
   if (perSM <= 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_transport<BLOCK>, BLOCK, 0) != cudaSuccess || perSM <= 0)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_transport<BLOCK, REG>, BLOCK, 0) != cudaSuccess || perSM <= 0)
       perSM = 1;
   }
   long long want = (p.src.n + BLOCK - 1) / BLOCK;
   long long grid = (long long)h->numSMs * perSM;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  k_transport<BLOCK><<<(unsigned)grid, BLOCK, 0, h->stream>>>(p, h->kSteps, h->eventThreshold);
+  ProblemT<REG> pt;
+  static_cast<Problem&>(pt) = p;
+  k_transport<BLOCK, REG><<<(unsigned)grid, BLOCK, 0, h->stream>>>(pt, h->kSteps, h->eventThreshold);
   return I3RC_SUCCESS;
+}
+template <int BLOCK>
+int launch_transport_b(i3rc_integrator* h, const Problem& p) {
+  return (p.xyRegular && p.zRegular) ? launch_transport_t<BLOCK, true>(h, p) : launch_transport_t<BLOCK, false>(h, p);
 }
 
 // zero tallies, trace one batch, post-process (MCRT:296-395); no host synchronisation
@@ -496,13 +502,13 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
   int rc;
   switch (h->blockSize) {
     case 64:
-      rc = launch_transport_t<64>(h, p);
+      rc = launch_transport_b<64>(h, p);
       break;
     case 256:
-      rc = launch_transport_t<256>(h, p);
+      rc = launch_transport_b<256>(h, p);
       break;
     default:
-      rc = launch_transport_t<128>(h, p);
+      rc = launch_transport_b<128>(h, p);
       break;
   }
   if (rc != I3RC_SUCCESS) return rc;
@@ -1182,7 +1188,7 @@ int i3rc_trace_rays(i3rc_integrator* h, int n, const float* pos, const float* di
     CUDA_OK(h, cudaMalloc(&d_tau, sizeof(float) * n));
     CUDA_OK(h, cudaMalloc(&d_po, sizeof(float) * 3 * n));
     CUDA_OK(h, cudaMalloc(&d_idx, sizeof(int) * 3 * n));
-    Problem p;
+    ProblemT<false> p;
     fill_problem(h, p);
     k_trace_rays<<<(n + 127) / 128, 128, 0, h->stream>>>(p, n, d_pos, d_dir, d_lim, d_tau, d_po, d_idx);
     h->otherLaunches++;

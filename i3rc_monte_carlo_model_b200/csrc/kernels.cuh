@@ -24,8 +24,8 @@ namespace i3rc {
 // which lane traces which ray (up to float summation order in the tallies).
 constexpr int QCAP = 128;  // local-estimate tasks per warp (ring, power of two): 4.5 KB of shared memory per warp
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_transport(const Problem p, const int stepsPerRound, const int eventThreshold) {
+template <int BLOCK, bool REG>
+__global__ void __launch_bounds__(BLOCK, 640 / BLOCK) k_transport(const ProblemT<REG> p, const int stepsPerRound, const int eventThreshold) {
   __shared__ LeTask s_task[BLOCK / 32][QCAP];
   __shared__ int s_head[BLOCK / 32];
   const unsigned full = 0xffffffffu;
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(BLOCK) k_transport(const Problem p, const int 
 }
 
 // ---- probes: accumulateExtinctionAlongPath for explicit rays (deterministic sub-path parity) ---------------
-__global__ void k_trace_rays(const Problem p, int n, const float* __restrict__ pos, const float* __restrict__ dir,
+__global__ void k_trace_rays(const ProblemT<false> p, int n, const float* __restrict__ pos, const float* __restrict__ dir,
                              const float* __restrict__ tauLimit, float* __restrict__ tauOut,
                              float* __restrict__ posOut, int* __restrict__ idxOut) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;

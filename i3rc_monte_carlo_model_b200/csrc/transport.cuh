@@ -102,11 +102,19 @@ struct Problem {
   long long firstPhoton;  // photon ids of this launch are firstPhoton + [0, src.n)
 };
 
+// Compile-time specialisation of the hot loop: REG = x, y and z are all regularly spaced (the I3RC cases), so a
+// ray's path length per cell is a per-ray constant and no edge arrays are read while stepping.
+template <bool REG>
+struct ProblemT : Problem {
+  static constexpr bool kRegular = REG;
+};
+
 struct Lane {
   // current ray
   int ix, iy, iz, idx;
   float rx, ry, rz, tau, tauLimit;  // path length left to the next x/y/z cell face; optical path so far / target
-  float iax, iay, iaz;
+  float e;                          // extinction of the current cell
+  float iax, iay, iaz;  // kRegular: path length per cell along the ray (cell width / |direction cosine|); else 1/|cosine|
   int sgn;
   int done;
   int nsteps;
@@ -238,38 +246,57 @@ I3RC_HD void next_direct(Lane& L, float cs) {
 
 // ---- the ray ------------------------------------------------------------------------------------
 // Start a ray at the event point (cx,cy,cz ; fx,fy,fz) of the lane along direction (dx,dy,dz).
-I3RC_HD void start_ray(const Problem& p, Lane& L, float dx, float dy, float dz, float iax, float iay, float iaz,
-                       float tauLimit) {
-  L.ix = L.cx;
-  L.iy = L.cy;
-  L.iz = L.cz;
-  L.idx = (L.cz * p.ny + L.cy) * p.nx + L.cx;
+// per-cell path length of the ray along one axis (w = width of cell i)
+template <class P>
+I3RC_HD float ray_dt(const P& p, float ia, const float* edges, int regular, float d, int i) {
+  if (P::kRegular) return ia;
+  return cell_w(edges, regular, d, i) * ia;
+}
+
+template <class P>
+I3RC_HD void start_ray_at(const P& p, Lane& L, int ix, int iy, int iz, float fx, float fy, float fz, float dx, float dy,
+                          float dz, float iax, float iay, float iaz, float tauLimit) {
+  L.ix = ix;
+  L.iy = iy;
+  L.iz = iz;
+  L.idx = (iz * p.ny + iy) * p.nx + ix;
+  if (P::kRegular) {
+    iax *= p.dx;
+    iay *= p.dy;
+    iaz *= p.dz;
+  }
   L.iax = iax;
   L.iay = iay;
   L.iaz = iaz;
   L.sgn = (dx >= 0.0f ? 1 : 0) | (dy >= 0.0f ? 2 : 0) | (dz >= 0.0f ? 4 : 0);
-  float wx = cell_w(p.xe, p.xyRegular, p.dx, L.cx);
-  float wy = cell_w(p.ye, p.xyRegular, p.dy, L.cy);
-  float wz = cell_w(p.ze, p.zRegular, p.dz, L.cz);
-  L.rx = isinf(iax) ? INFINITY : ((L.sgn & 1) ? (1.0f - L.fx) : L.fx) * wx * iax;
-  L.ry = isinf(iay) ? INFINITY : ((L.sgn & 2) ? (1.0f - L.fy) : L.fy) * wy * iay;
-  L.rz = isinf(iaz) ? INFINITY : ((L.sgn & 4) ? (1.0f - L.fz) : L.fz) * wz * iaz;
+  L.rx = isinf(iax) ? INFINITY : ((L.sgn & 1) ? (1.0f - fx) : fx) * ray_dt(p, iax, p.xe, p.xyRegular, p.dx, ix);
+  L.ry = isinf(iay) ? INFINITY : ((L.sgn & 2) ? (1.0f - fy) : fy) * ray_dt(p, iay, p.ye, p.xyRegular, p.dy, iy);
+  L.rz = isinf(iaz) ? INFINITY : ((L.sgn & 4) ? (1.0f - fz) : fz) * ray_dt(p, iaz, p.ze, p.zRegular, p.dz, iz);
   L.tau = 0.0f;
   L.tauLimit = tauLimit;
   L.nsteps = 0;
   L.done = DONE_RUN;
+  L.e = I3RC_LDG(p.ext + L.idx);
+}
+
+// Start a ray at the event point (cx,cy,cz ; fx,fy,fz) of the lane along direction (dx,dy,dz).
+template <class P>
+I3RC_HD void start_ray(const P& p, Lane& L, float dx, float dy, float dz, float iax, float iay, float iaz,
+                       float tauLimit) {
+  start_ray_at(p, L, L.cx, L.cy, L.cz, L.fx, L.fy, L.fz, dx, dy, dz, iax, iay, iaz, tauLimit);
 }
 
 // ONE cell crossing (the body of accumulateExtinctionAlongPath's loop, MCRT:1690-1806).
 // The ray carries the path length left to the next face on each axis (rx, ry, rz): all quantities stay of the
 // order of one cell, so the accumulated optical path does not lose precision with the distance travelled.
-I3RC_HD void dda_step(const Problem& p, Lane& L) {
-  float e = I3RC_LDG(p.ext + L.idx);
-  float s = fminf(L.rx, fminf(L.ry, L.rz));
-  float dtau = s * e;
+template <class P>
+I3RC_HD void dda_step(const P& p, Lane& L) {
+  const float e = L.e;  // extinction of the current cell: loaded when the cell was entered (hides the gather latency)
+  const float s = fminf(L.rx, fminf(L.ry, L.rz));
+  const float dtau = s * e;
   L.nsteps++;
   if (L.tau + dtau > L.tauLimit) {  // MCRT:1721-1731: the target optical path is reached inside this cell
-    float sp = (L.tauLimit - L.tau) / e;
+    const float sp = I3RC_FDIV(L.tauLimit - L.tau, e);
     L.rx -= sp;
     L.ry -= sp;
     L.rz -= sp;
@@ -298,7 +325,7 @@ I3RC_HD void dda_step(const Problem& p, Lane& L) {
         L.idx += p.nx;
       }
     }
-    L.rx = cell_w(p.xe, p.xyRegular, p.dx, L.ix) * L.iax;
+    L.rx = ray_dt(p, L.iax, p.xe, p.xyRegular, p.dx, L.ix);
   }
   if (cy) {
     if (L.sgn & 2) {
@@ -316,7 +343,7 @@ I3RC_HD void dda_step(const Problem& p, Lane& L) {
         L.idx += p.nx * p.ny;
       }
     }
-    L.ry = cell_w(p.ye, p.xyRegular, p.dy, L.iy) * L.iay;
+    L.ry = ray_dt(p, L.iay, p.ye, p.xyRegular, p.dy, L.iy);
   }
   if (cz) {
     if (L.sgn & 4) {
@@ -334,25 +361,27 @@ I3RC_HD void dda_step(const Problem& p, Lane& L) {
       }
       L.idx -= p.nx * p.ny;
     }
-    L.rz = cell_w(p.ze, p.zRegular, p.dz, L.iz) * L.iaz;
+    L.rz = ray_dt(p, L.iaz, p.ze, p.zRegular, p.dz, L.iz);
   }
+  L.e = I3RC_LDG(p.ext + L.idx);
   if (L.nsteps > MAX_RAY_STEPS) L.done = DONE_BAD;
 }
 
 // offset inside the current cell of the ray's current point, per axis (keeps f where the ray does not move)
-I3RC_HD void ray_local(const Problem& p, const Lane& L, float* fx, float* fy, float* fz) {
+template <class P>
+I3RC_HD void ray_local(const P& p, const Lane& L, float* fx, float* fy, float* fz) {
   if (!isinf(L.iax)) {
-    float rem = L.rx / (cell_w(p.xe, p.xyRegular, p.dx, L.ix) * L.iax);
+    float rem = I3RC_FDIV(L.rx, ray_dt(p, L.iax, p.xe, p.xyRegular, p.dx, L.ix));
     rem = fminf(fmaxf(rem, 0.0f), 1.0f);
     *fx = (L.sgn & 1) ? 1.0f - rem : rem;
   }
   if (!isinf(L.iay)) {
-    float rem = L.ry / (cell_w(p.ye, p.xyRegular, p.dy, L.iy) * L.iay);
+    float rem = I3RC_FDIV(L.ry, ray_dt(p, L.iay, p.ye, p.xyRegular, p.dy, L.iy));
     rem = fminf(fmaxf(rem, 0.0f), 1.0f);
     *fy = (L.sgn & 2) ? 1.0f - rem : rem;
   }
   if (L.iz >= 0 && L.iz < p.nz && !isinf(L.iaz)) {
-    float rem = L.rz / (cell_w(p.ze, p.zRegular, p.dz, L.iz) * L.iaz);
+    float rem = I3RC_FDIV(L.rz, ray_dt(p, L.iaz, p.ze, p.zRegular, p.dz, L.iz));
     rem = fminf(fmaxf(rem, 0.0f), 1.0f);
     *fz = (L.sgn & 4) ? 1.0f - rem : rem;
   }
@@ -380,7 +409,8 @@ I3RC_HD float abs_z(const Problem& p, int iz, float fz) {
 
 // Maximum cross-section flight (MCRT:491-497, 504-511, 521-528, 586-588) from the event point to the
 // next boundary or PHYSICAL collision.  Cell indices are looked up after every move (deviation Q11).
-I3RC_HD void max_cross_section_flight(const Problem& p, Lane& L) {
+template <class P>
+I3RC_HD void max_cross_section_flight(const P& p, Lane& L) {
   float x = abs_x(p, L.cx, L.fx), y = abs_y(p, L.cy, L.fy), z = abs_z(p, L.cz, L.fz);
   float Lx = p.xmax - p.x0, Ly = p.ymax - p.y0;
   for (;;) {
@@ -424,7 +454,8 @@ I3RC_HD void max_cross_section_flight(const Problem& p, Lane& L) {
 }
 
 // Begin the next path segment of the photon from its event point (MCRT:474-497).
-I3RC_HD void start_segment(const Problem& p, Lane& L) {
+template <class P>
+I3RC_HD void start_segment(const P& p, Lane& L) {
   L.mode = MODE_PHOTON;
   if (p.useRayTracing) {
     start_ray(p, L, L.ux, L.uy, L.uz, inv_abs(L.ux), inv_abs(L.uy), inv_abs(L.uz), draw_tau(L));
@@ -438,7 +469,8 @@ I3RC_HD void start_segment(const Problem& p, Lane& L) {
 }
 
 // Draw a photon from the source descriptor (Code/monteCarloIllumination.f95:62-424) and start it (MCRT:453-470).
-I3RC_HD void init_photon(const Problem& p, Lane& L, long long id) {
+template <class P>
+I3RC_HD void init_photon(const P& p, Lane& L, long long id) {
   const SourceDev& s = p.src;
   L.rng.init(p.key0, p.key1, (uint64_t)(p.firstPhoton + id));
   float qx, qy, qz = 1.0f, mu, phi;
@@ -598,7 +630,8 @@ I3RC_HD int make_le_task(const Problem& p, Lane& L, int d, LeTask& t) {
 }
 
 // Make the task the lane's current ray.
-I3RC_HD void start_le_task(const Problem& p, Lane& L, const LeTask& t) {
+template <class P>
+I3RC_HD void start_le_task(const P& p, Lane& L, const LeTask& t) {
   int d = (t.zdmc >> 16) & 31;
   const float* dv = p.dirs + d * DIR_STRIDE;
   L.td = d;
@@ -607,27 +640,8 @@ I3RC_HD void start_le_task(const Problem& p, Lane& L, const LeTask& t) {
   L.tcw = t.cw;
   L.tcfix = t.cfix;
   L.ttauFree = t.tauFree;
-  // start_ray reads the origin from (cx,cy,cz ; fx,fy,fz): pass the task's origin without touching the lane's photon
-  int ix = t.xy & 0xffff, iy = t.xy >> 16, iz = t.zdmc & 0xffff;
-  float ddx = I3RC_LDG(dv + 0), ddy = I3RC_LDG(dv + 1), ddz = I3RC_LDG(dv + 2);
-  L.ix = ix;
-  L.iy = iy;
-  L.iz = iz;
-  L.idx = (iz * p.ny + iy) * p.nx + ix;
-  L.iax = I3RC_LDG(dv + 3);
-  L.iay = I3RC_LDG(dv + 4);
-  L.iaz = I3RC_LDG(dv + 5);
-  L.sgn = (ddx >= 0.0f ? 1 : 0) | (ddy >= 0.0f ? 2 : 0) | (ddz >= 0.0f ? 4 : 0);
-  float wx = cell_w(p.xe, p.xyRegular, p.dx, ix);
-  float wy = cell_w(p.ye, p.xyRegular, p.dy, iy);
-  float wz = cell_w(p.ze, p.zRegular, p.dz, iz);
-  L.rx = isinf(L.iax) ? INFINITY : ((L.sgn & 1) ? (1.0f - t.fx) : t.fx) * wx * L.iax;
-  L.ry = isinf(L.iay) ? INFINITY : ((L.sgn & 2) ? (1.0f - t.fy) : t.fy) * wy * L.iay;
-  L.rz = isinf(L.iaz) ? INFINITY : ((L.sgn & 4) ? (1.0f - t.fz) : t.fz) * wz * L.iaz;
-  L.tau = 0.0f;
-  L.tauLimit = t.tauLimit;
-  L.nsteps = 0;
-  L.done = DONE_RUN;
+  start_ray_at(p, L, (int)(t.xy & 0xffff), (int)(t.xy >> 16), (int)(t.zdmc & 0xffff), t.fx, t.fy, t.fz, I3RC_LDG(dv + 0),
+               I3RC_LDG(dv + 1), I3RC_LDG(dv + 2), I3RC_LDG(dv + 3), I3RC_LDG(dv + 4), I3RC_LDG(dv + 5), t.tauLimit);
 }
 
 I3RC_HD void tally_intensity(const Problem& p, Lane& L, float c) {
@@ -677,7 +691,8 @@ I3RC_HD int finish_le_ray(const Problem& p, Lane& L) {
 }
 
 // The photon's own path segment has stopped: record where (event point) and how, and free the ray registers.
-I3RC_HD void segment_finished(const Problem& p, Lane& L) {
+template <class P>
+I3RC_HD void segment_finished(const P& p, Lane& L) {
   L.segDone = L.done;
   L.done = DONE_RUN;
   L.cnt[CNT_CROSS_PH] += L.nsteps;
@@ -753,7 +768,8 @@ I3RC_HD int photon_event(const Problem& p, Lane& L) {
 
 // After the local estimate (or directly, when no intensity is wanted): roulette, scattering, next segment
 // (MCRT:670-688); for a surface event just continue with the reflected direction.
-I3RC_HD void continue_photon(const Problem& p, Lane& L) {
+template <class P>
+I3RC_HD void continue_photon(const P& p, Lane& L) {
   if (L.comp >= 1) {
     if (p.useRussianRoulette && L.w < p.rouletteW * 0.5f) {  // MCRT:673-679
       if (draw(L) >= L.w / p.rouletteW) {
@@ -777,7 +793,8 @@ I3RC_HD void continue_photon(const Problem& p, Lane& L) {
 // ---- per-lane scheduler (one lane owns the photon AND traces its local-estimate rays one after the other).
 // Used by the single-lane CPU harness of the test-suite and by the deterministic probes; the production kernel
 // (k_transport, kernels.cuh) schedules the same functions warp-cooperatively.
-I3RC_HD void advance_le(const Problem& p, Lane& L) {
+template <class P>
+I3RC_HD void advance_le(const P& p, Lane& L) {
   while (L.d < p.nDir) {
     LeTask t;
     int d = L.d++;
@@ -789,7 +806,8 @@ I3RC_HD void advance_le(const Problem& p, Lane& L) {
   continue_photon(p, L);
 }
 
-I3RC_HD void handle_event(const Problem& p, Lane& L) {
+template <class P>
+I3RC_HD void handle_event(const P& p, Lane& L) {
   if (L.mode == MODE_PHOTON) {
     segment_finished(p, L);
     if (!photon_event(p, L)) return;

@@ -108,11 +108,12 @@ static void fill(const HostSimArgs* a, Problem& p, std::vector<TableDesc>& td, s
   p.counters = a->counters; p.nextPhoton = nullptr; p.firstPhoton = 0;
 }
 
-int hostsim_run(const HostSimArgs* a) {
-  Problem p;
-  std::vector<TableDesc> td;
-  std::vector<float> dirs;
-  fill(a, p, td, dirs);
+}  // extern "C"
+
+template <bool REG>
+static void run_lanes(const HostSimArgs* a, const Problem& p0) {
+  ProblemT<REG> p;
+  static_cast<Problem&>(p) = p0;
   Lane L;
   memset(&L, 0, sizeof(L));
   for (long long id = 0; id < a->n; id++) {
@@ -124,12 +125,24 @@ int hostsim_run(const HostSimArgs* a) {
     }
   }
   for (int i = 0; i < CNT_N; i++) a->counters[i] += L.cnt[i];
+}
+
+extern "C" {
+
+int hostsim_run(const HostSimArgs* a) {
+  Problem p;
+  std::vector<TableDesc> td;
+  std::vector<float> dirs;
+  fill(a, p, td, dirs);
+  // the same specialisation rule as the product's launcher (api.cu)
+  if (p.xyRegular && p.zRegular) run_lanes<true>(a, p);
+  else run_lanes<false>(a, p);
   return 0;
 }
 
 int hostsim_trace_rays(const HostSimArgs* a, int n, const float* pos, const float* dir, const float* tauLimit,
                        float* tauOut, float* posOut, int* idxOut) {
-  Problem p;
+  ProblemT<false> p;
   std::vector<TableDesc> td;
   std::vector<float> dirs;
   fill(a, p, td, dirs);

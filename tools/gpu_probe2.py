@@ -39,7 +39,6 @@ if __name__ == "__main__":
     wls = sys.argv[1:] or ["landsat"]
     for wl in wls:
         nph = 2_000_000 if wl != "les" else 500_000
-        for tune in ({}, {"steps_per_event_phase": 1}, {"steps_per_event_phase": 2}, {"steps_per_event_phase": 3}, {"steps_per_event_phase": 6},
-                     {"steps_per_event_phase": 8}, {"steps_per_event_phase": 3, "event_threshold": 24}, {"steps_per_event_phase": 6, "event_threshold": 24},
-                     {"steps_per_event_phase": 3, "block_size": 64}, {"steps_per_event_phase": 3, "block_size": 256}):
+        for tune in ({}, {"steps_per_event_phase": 4}, {"steps_per_event_phase": 8}, {"steps_per_event_phase": 12},
+                     {"event_threshold": 24}, {"block_size": 64}, {"block_size": 256}, {"blocks_per_sm": 4}, {"blocks_per_sm": 3}):
             run(wl, nph, 2, tune)
