@@ -104,7 +104,7 @@ struct i3rc_integrator {
   double traceMs = 0.0;
   long long traceLaunches = 0, otherLaunches = 0;
   // tuning
-  int blockSize = 128, blocksPerSM = 0, kSteps = 6, eventThreshold = 16;
+  int blockSize = 128, blocksPerSM = 0, residentBlocks = 6, kSteps = 6, eventThreshold = 16;
   // nccl
   void* nccl = nullptr;
   void* ncclLib = nullptr;
@@ -448,11 +448,11 @@ int fill_source(i3rc_integrator* h, const i3rc_photon_source* s, SourceDev& d) {
   return I3RC_SUCCESS;
 }
 
-template <int BLOCK, bool REG>
+template <int BLOCK, bool REG, int MINB>
 int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   int perSM = h->blocksPerSM;
   if (perSM <= 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_transport<BLOCK, REG>, BLOCK, 0) != cudaSuccess || perSM <= 0)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_transport<BLOCK, REG, MINB>, BLOCK, 0) != cudaSuccess || perSM <= 0)
       perSM = 1;
   }
   long long want = (p.src.n + BLOCK - 1) / BLOCK;
@@ -461,12 +461,32 @@ int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   if (grid < 1) grid = 1;
   ProblemT<REG> pt;
   static_cast<Problem&>(pt) = p;
-  k_transport<BLOCK, REG><<<(unsigned)grid, BLOCK, 0, h->stream>>>(pt, h->kSteps, h->eventThreshold);
+  k_transport<BLOCK, REG, MINB><<<(unsigned)grid, BLOCK, 0, h->stream>>>(pt, h->kSteps, h->eventThreshold);
   return I3RC_SUCCESS;
 }
-template <int BLOCK>
+// MINB = resident blocks per SM the kernel is compiled for (register cap 65536 / (MINB * BLOCK))
+template <int BLOCK, int MINB>
 int launch_transport_b(i3rc_integrator* h, const Problem& p) {
-  return (p.xyRegular && p.zRegular) ? launch_transport_t<BLOCK, true>(h, p) : launch_transport_t<BLOCK, false>(h, p);
+  return (p.xyRegular && p.zRegular) ? launch_transport_t<BLOCK, true, MINB>(h, p) : launch_transport_t<BLOCK, false, MINB>(h, p);
+}
+int launch_transport(i3rc_integrator* h, const Problem& p) {
+  switch (h->blockSize) {
+    case 64:
+      return launch_transport_b<64, 10>(h, p);
+    case 256:
+      return launch_transport_b<256, 3>(h, p);
+    default:
+      switch (h->residentBlocks) {
+        case 5:
+          return launch_transport_b<128, 5>(h, p);
+        case 7:
+          return launch_transport_b<128, 7>(h, p);
+        case 8:
+          return launch_transport_b<128, 8>(h, p);
+        default:
+          return launch_transport_b<128, 6>(h, p);
+      }
+  }
 }
 
 // zero tallies, trace one batch, post-process (MCRT:296-395); no host synchronisation
@@ -499,18 +519,7 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
     h->ev.push_back(b);
   }
   CUDA_OK(h, cudaEventRecord(h->ev[h->evUsed], h->stream));
-  int rc;
-  switch (h->blockSize) {
-    case 64:
-      rc = launch_transport_b<64>(h, p);
-      break;
-    case 256:
-      rc = launch_transport_b<256>(h, p);
-      break;
-    default:
-      rc = launch_transport_b<128>(h, p);
-      break;
-  }
+  int rc = launch_transport(h, p);
   if (rc != I3RC_SUCCESS) return rc;
   CUDA_OK(h, cudaGetLastError());
   CUDA_OK(h, cudaEventRecord(h->ev[h->evUsed + 1], h->stream));
@@ -1169,6 +1178,7 @@ int i3rc_copy_Integrator(const i3rc_integrator* s, i3rc_integrator** out) {
   h->blocksPerSM = s->blocksPerSM;
   h->kSteps = s->kSteps;
   h->eventThreshold = s->eventThreshold;
+  h->residentBlocks = s->residentBlocks;
   h->message.clear();
   *out = h;
   return I3RC_SUCCESS;
@@ -1447,6 +1457,8 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->blocksPerSM = value;
   else if (k == "steps_per_event_phase" && value >= 1)
     h->kSteps = value;
+  else if (k == "resident_blocks" && value >= 5 && value <= 8)
+    h->residentBlocks = value;
   else if (k == "event_threshold" && value >= 1 && value <= 32)
     h->eventThreshold = value;
   else if (k == "track_by_component")

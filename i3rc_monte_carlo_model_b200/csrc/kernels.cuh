@@ -24,10 +24,11 @@ namespace i3rc {
 // which lane traces which ray (up to float summation order in the tallies).
 constexpr int QCAP = 128;  // local-estimate tasks per warp (ring, power of two): 4.5 KB of shared memory per warp
 
-template <int BLOCK, bool REG>
-__global__ void __launch_bounds__(BLOCK, 640 / BLOCK) k_transport(const ProblemT<REG> p, const int stepsPerRound, const int eventThreshold) {
+template <int BLOCK, bool REG, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG> p, const int stepsPerRound, const int eventThreshold) {
   __shared__ LeTask s_task[BLOCK / 32][QCAP];
   __shared__ int s_head[BLOCK / 32];
+  __shared__ uint32_t s_cnt[BLOCK / 32][CNT_N];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
@@ -38,8 +39,9 @@ __global__ void __launch_bounds__(BLOCK, 640 / BLOCK) k_transport(const ProblemT
   __syncwarp();
 
   Lane L;
-#pragma unroll
-  for (int i = 0; i < CNT_N; i++) L.cnt[i] = 0;
+  L.cnt = s_cnt[warp];
+  if (lane < CNT_N) s_cnt[warp][lane] = 0;
+  __syncwarp();
   L.active = 0;
   L.done = DONE_RUN;
   L.mode = MODE_PHOTON;
@@ -81,15 +83,19 @@ __global__ void __launch_bounds__(BLOCK, 640 / BLOCK) k_transport(const ProblemT
     // ================= EVENT phase =================
     const bool ev = pending && !hasRay;
     bool alive = false;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;  // the event's block of deviates
     if (ev) {
       pending = false;
-      alive = photon_event(p, L) != 0;
+      L.rng.next4(p.key0, p.key1, a0, a1, a2, a3);
+      alive = photon_event(p, L, a0, a1) != 0;
     }
     if (p.computeIntensity) {
       if (__any_sync(full, alive)) {
+        float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
         for (int d = 0; d < p.nDir; d++) {
+          if ((d & 1) == 0 && alive) L.rng.next4(p.key0, p.key1, c0, c1, c2, c3);  // one block per two directions
           LeTask t;
-          const bool push = alive && make_le_task(p, L, d, t);
+          const bool push = alive && make_le_task(p, L, d, (d & 1) ? c2 : c0, (d & 1) ? c3 : c1, t);
           const unsigned m = __ballot_sync(full, push);
           const int n = __popc(m);
           if (n == 0) continue;
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(BLOCK, 640 / BLOCK) k_transport(const ProblemT
       }
     }
     if (alive) {
-      continue_photon(p, L);  // roulette, scattering, start of the next own segment
+      continue_photon(p, L, a1, a2, a3);  // roulette, scattering, start of the next own segment
       if (L.active) hasRay = true;
     }
     // refill finished slots
@@ -157,13 +163,9 @@ __global__ void __launch_bounds__(BLOCK, 640 / BLOCK) k_transport(const ProblemT
     fix_head();
     if (!anything && !__any_sync(full, L.active || !exhausted)) break;
   }
-  // flush the per-thread counters: warp reduce, one atomic per warp and counter
-#pragma unroll
-  for (int i = 0; i < CNT_N; i++) {
-    unsigned long long v = L.cnt[i];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(full, v, o);
-    if (lane == 0 && v) atomicAdd(p.counters + i, v);
-  }
+  // flush the warp's counters
+  __syncwarp();
+  if (lane < CNT_N && s_cnt[warp][lane]) atomicAdd(p.counters + lane, (unsigned long long)s_cnt[warp][lane]);
 }
 
 // ---- probes: accumulateExtinctionAlongPath for explicit rays (deterministic sub-path parity) ---------------
@@ -173,7 +175,9 @@ __global__ void k_trace_rays(const ProblemT<false> p, int n, const float* __rest
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   Lane L;
-  for (int i = 0; i < CNT_N; i++) L.cnt[i] = 0;
+  uint32_t cnt[CNT_N];
+  for (int i = 0; i < CNT_N; i++) cnt[i] = 0;
+  L.cnt = cnt;
   locate_abs(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, p.dx, pos[3 * r], 1, &L.cx, &L.fx);
   locate_abs(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, p.dy, pos[3 * r + 1], 1, &L.cy, &L.fy);
   locate_abs(p.ze, p.zRegular, p.nz, p.z0, p.zmax, p.dz, pos[3 * r + 2], 0, &L.cz, &L.fz);

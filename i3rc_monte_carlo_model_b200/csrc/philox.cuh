@@ -51,39 +51,26 @@ I3RC_HD u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1) {
 // RandomNumbersForMC.f95:275-299): exactly 0 and exactly 1 are possible and guarded by the callers.
 I3RC_HD float u01(uint32_t x) { return (float)x * 2.3283064365386963e-10f; }
 
-// Per-photon stream: buffers the four words of one Philox block.
+// Per-photon stream, consumed in whole BLOCKS of four deviates.  The transport code asks for a fresh block at
+// fixed points of a photon's life (birth, every event, every pair of local-estimate directions, every pair of
+// rejection rounds of the direction change), so that all lanes of a warp that are in the same phase generate their
+// blocks together instead of refilling a per-lane buffer at data-dependent times.
 struct Rng {
-  uint32_t k0, k1, id_lo, id_hi, block;
-  uint32_t b0, b1, b2, b3;
-  int n;  // words left in the buffer
-  I3RC_HD void init(uint32_t key0, uint32_t key1, uint64_t photon) {
-    k0 = key0;
-    k1 = key1;
+  uint32_t id_lo, id_hi, block;
+  I3RC_HD void init(uint64_t photon) {
     id_lo = (uint32_t)photon;
     id_hi = (uint32_t)(photon >> 32);
     block = 0;
-    n = 0;
-    b0 = b1 = b2 = b3 = 0;
   }
-  I3RC_HD uint32_t next_u32() {
-    if (n == 0) {
-      u32x4 c = {id_lo, id_hi, block, 0u};
-      u32x4 r = philox4x32_10(c, k0, k1);
-      b0 = r.x;
-      b1 = r.y;
-      b2 = r.z;
-      b3 = r.w;
-      block++;
-      n = 4;
-    }
-    uint32_t v = b0;
-    b0 = b1;
-    b1 = b2;
-    b2 = b3;
-    n--;
-    return v;
+  I3RC_HD void next4(uint32_t k0, uint32_t k1, float& a, float& b, float& c, float& d) {
+    u32x4 ctr = {id_lo, id_hi, block, 0u};
+    u32x4 r = philox4x32_10(ctr, k0, k1);
+    block++;
+    a = u01(r.x);
+    b = u01(r.y);
+    c = u01(r.z);
+    d = u01(r.w);
   }
-  I3RC_HD float next() { return u01(next_u32()); }
 };
 
 }  // namespace i3rc

@@ -28,6 +28,7 @@
 #ifdef __CUDA_ARCH__
 #define I3RC_LDG(p) __ldg(p)
 #define I3RC_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define I3RC_COUNT(L, i, v) atomicAdd((L).cnt + (i), (uint32_t)(v))
 #define I3RC_LOG(x) __logf(x)
 #define I3RC_EXP(x) __expf(x)
 #define I3RC_COS(x) __cosf(x)
@@ -36,6 +37,7 @@
 #else
 #define I3RC_LDG(p) (*(p))
 #define I3RC_ATOMIC_ADD(p, v) (*(p) += (v))
+#define I3RC_COUNT(L, i, v) ((L).cnt[(i)] += (uint32_t)(v))
 #define I3RC_LOG(x) logf(x)
 #define I3RC_EXP(x) expf(x)
 #define I3RC_COS(x) cosf(x)
@@ -128,12 +130,13 @@ struct Lane {
   int mode;        // what the current ray is: MODE_PHOTON (own path segment) or a local-estimate stage
   int comp, pfi;   // photon: component (0 = surface) and phase-function entry of the last event
   int d;           // photon: next local-estimate direction to generate (per-lane scheduler only)
+  float ev1, ev2, ev3, le2, le3;  // deviates of the current event kept between its stages (per-lane scheduler only)
   // local-estimate ray being traced (may belong to ANOTHER lane's photon in the warp-cooperative kernel)
   int td, tcomp;
   float tcw, tcfix, ttauFree;
   Rng rng;
   int active;
-  uint32_t cnt[CNT_N];
+  uint32_t* cnt;  // event counters [CNT_N]: the warp's shared-memory block on the device, a plain array on the host
 };
 
 // ---- small helpers ------------------------------------------------------------------------------
@@ -224,14 +227,21 @@ I3RC_HD float phase_lookup(const float* T, int n, float angle) {
   return I3RC_LDG(T + n - 1);
 }
 
-// next_direct, MCRT:2086-2113 (Marchuk rotation, rejection sampling in the unit disc)
-I3RC_HD void next_direct(Lane& L, float cs) {
+// next_direct, MCRT:2086-2113 (Marchuk rotation, rejection sampling in the unit disc; one block = two rounds)
+template <class P>
+I3RC_HD void next_direct(const P& p, Lane& L, float cs) {
   float D = 2.0f, AX = 0.0f, AY = 0.0f;
   while (D > 1.0f) {
-    AX = 1.0f - 2.0f * L.rng.next();
-    AY = 1.0f - 2.0f * L.rng.next();
-    L.cnt[CNT_RNG] += 2;
+    float r0, r1, r2, r3;
+    L.rng.next4(p.key0, p.key1, r0, r1, r2, r3);
+    AX = 1.0f - 2.0f * r0;
+    AY = 1.0f - 2.0f * r1;
     D = AX * AX + AY * AY;
+    if (D > 1.0f) {
+      AX = 1.0f - 2.0f * r2;
+      AY = 1.0f - 2.0f * r3;
+      D = AX * AX + AY * AY;
+    }
   }
   float B = sqrtf(fmaxf(1.0f - cs * cs, 0.0f) / D);
   AX *= B;
@@ -305,64 +315,25 @@ I3RC_HD void dda_step(const P& p, Lane& L) {
     return;
   }
   L.tau += dtau;
+  // branch-free face crossing: every lane runs the same instructions whichever face(s) it crosses
   const bool cx = L.rx <= s, cy = L.ry <= s, cz = L.rz <= s;
-  L.rx -= s;
-  L.ry -= s;
-  L.rz -= s;
-  if (cx) {
-    if (L.sgn & 1) {
-      L.ix++;
-      L.idx++;
-      if (L.ix >= p.nx) {
-        L.ix = 0;
-        L.idx -= p.nx;
-      }
-    } else {
-      L.ix--;
-      L.idx--;
-      if (L.ix < 0) {
-        L.ix = p.nx - 1;
-        L.idx += p.nx;
-      }
-    }
-    L.rx = ray_dt(p, L.iax, p.xe, p.xyRegular, p.dx, L.ix);
+  int ix = L.ix + (cx ? ((L.sgn & 1) ? 1 : -1) : 0);
+  int iy = L.iy + (cy ? ((L.sgn & 2) ? 1 : -1) : 0);
+  const int iz = L.iz + (cz ? ((L.sgn & 4) ? 1 : -1) : 0);
+  ix = ix >= p.nx ? 0 : (ix < 0 ? p.nx - 1 : ix);  // periodic in x and y (MCRT:1774-1788)
+  iy = iy >= p.ny ? 0 : (iy < 0 ? p.ny - 1 : iy);
+  L.ix = ix;
+  L.iy = iy;
+  L.iz = iz;
+  L.rx = cx ? ray_dt(p, L.iax, p.xe, p.xyRegular, p.dx, ix) : L.rx - s;
+  L.ry = cy ? ray_dt(p, L.iay, p.ye, p.xyRegular, p.dy, iy) : L.ry - s;
+  if ((unsigned)iz >= (unsigned)p.nz) {  // MCRT:1793-1804
+    L.done = iz < 0 ? DONE_BOTTOM : DONE_TOP;
+    L.rz -= s;
+    return;
   }
-  if (cy) {
-    if (L.sgn & 2) {
-      L.iy++;
-      L.idx += p.nx;
-      if (L.iy >= p.ny) {
-        L.iy = 0;
-        L.idx -= p.nx * p.ny;
-      }
-    } else {
-      L.iy--;
-      L.idx -= p.nx;
-      if (L.iy < 0) {
-        L.iy = p.ny - 1;
-        L.idx += p.nx * p.ny;
-      }
-    }
-    L.ry = ray_dt(p, L.iay, p.ye, p.xyRegular, p.dy, L.iy);
-  }
-  if (cz) {
-    if (L.sgn & 4) {
-      L.iz++;
-      if (L.iz >= p.nz) {
-        L.done = DONE_TOP;
-        return;
-      }
-      L.idx += p.nx * p.ny;
-    } else {
-      L.iz--;
-      if (L.iz < 0) {
-        L.done = DONE_BOTTOM;
-        return;
-      }
-      L.idx -= p.nx * p.ny;
-    }
-    L.rz = ray_dt(p, L.iaz, p.ze, p.zRegular, p.dz, L.iz);
-  }
+  L.rz = cz ? ray_dt(p, L.iaz, p.ze, p.zRegular, p.dz, iz) : L.rz - s;
+  L.idx = (iz * p.ny + iy) * p.nx + ix;
   L.e = I3RC_LDG(p.ext + L.idx);
   if (L.nsteps > MAX_RAY_STEPS) L.done = DONE_BAD;
 }
@@ -388,11 +359,7 @@ I3RC_HD void ray_local(const P& p, const Lane& L, float* fx, float* fy, float* f
 }
 
 // ---- photon life ----------------------------------------------------------------------------------
-I3RC_HD float draw(Lane& L) {
-  L.cnt[CNT_RNG]++;
-  return L.rng.next();
-}
-I3RC_HD float draw_tau(Lane& L) { return -I3RC_LOG(fmaxf(F_TINY, draw(L))); }  // MCRT:480
+I3RC_HD float tau_of(float xi) { return -I3RC_LOG(fmaxf(F_TINY, xi)); }  // MCRT:480
 
 I3RC_HD float abs_x(const Problem& p, int ix, float fx) {
   float a = p.xyRegular ? p.x0 + (float)ix * p.dx : I3RC_LDG(p.xe + ix);
@@ -410,11 +377,14 @@ I3RC_HD float abs_z(const Problem& p, int iz, float fz) {
 // Maximum cross-section flight (MCRT:491-497, 504-511, 521-528, 586-588) from the event point to the
 // next boundary or PHYSICAL collision.  Cell indices are looked up after every move (deviation Q11).
 template <class P>
-I3RC_HD void max_cross_section_flight(const P& p, Lane& L) {
+I3RC_HD void max_cross_section_flight(const P& p, Lane& L, float xiFirst) {
   float x = abs_x(p, L.cx, L.fx), y = abs_y(p, L.cy, L.fy), z = abs_z(p, L.cz, L.fz);
   float Lx = p.xmax - p.x0, Ly = p.ymax - p.y0;
-  for (;;) {
-    float dist = draw_tau(L) / p.maxExt;
+  float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f, r3 = 0.0f;
+  for (int it = 0;; it++) {
+    if ((it & 1) == 0) L.rng.next4(p.key0, p.key1, r0, r1, r2, r3);  // (flight, acceptance) pairs: two per block
+    const float xiTau = (it & 1) ? r2 : r0, xiAcc = (it & 1) ? r3 : r1;
+    float dist = tau_of(it == 0 ? xiFirst : xiTau) / p.maxExt;
     x += L.ux * dist;
     y += L.uy * dist;
     z += L.uz * dist;
@@ -445,26 +415,27 @@ I3RC_HD void max_cross_section_flight(const P& p, Lane& L) {
     locate_abs(p.ze, p.zRegular, p.nz, p.z0, p.zmax, p.dz, z, 0, &L.iz, &L.fz);
     L.idx = (L.iz * p.ny + L.iy) * p.nx + L.ix;
     float e = I3RC_LDG(p.ext + L.idx);
-    if (draw(L) < e / p.maxExt) {
+    if (xiAcc < e / p.maxExt) {
       L.done = DONE_INSIDE;
       return;
     }
-    L.cnt[CNT_NULL]++;
+    I3RC_COUNT(L, CNT_NULL, 1);
   }
 }
 
-// Begin the next path segment of the photon from its event point (MCRT:474-497).
+// Begin the next path segment of the photon from its event point (MCRT:474-497); xiTau is the deviate of its
+// optical path length.
 template <class P>
-I3RC_HD void start_segment(const P& p, Lane& L) {
+I3RC_HD void start_segment(const P& p, Lane& L, float xiTau) {
   L.mode = MODE_PHOTON;
   if (p.useRayTracing) {
-    start_ray(p, L, L.ux, L.uy, L.uz, inv_abs(L.ux), inv_abs(L.uy), inv_abs(L.uz), draw_tau(L));
+    start_ray(p, L, L.ux, L.uy, L.uz, inv_abs(L.ux), inv_abs(L.uy), inv_abs(L.uz), tau_of(xiTau));
   } else {
     L.nsteps = 0;
     L.iax = L.iay = L.iaz = INFINITY;  // ray_local keeps the offsets set by the flight
     L.rx = L.ry = L.rz = INFINITY;
     L.sgn = 0;
-    max_cross_section_flight(p, L);
+    max_cross_section_flight(p, L, xiTau);
   }
 }
 
@@ -472,28 +443,33 @@ I3RC_HD void start_segment(const P& p, Lane& L) {
 template <class P>
 I3RC_HD void init_photon(const P& p, Lane& L, long long id) {
   const SourceDev& s = p.src;
-  L.rng.init(p.key0, p.key1, (uint64_t)(p.firstPhoton + id));
-  float qx, qy, qz = 1.0f, mu, phi;
+  L.rng.init((uint64_t)(p.firstPhoton + id));
+  float r0, r1, r2, r3;  // the photon's first block: position, direction, first optical path (as far as it reaches)
+  L.rng.next4(p.key0, p.key1, r0, r1, r2, r3);
+  float qx, qy, qz = 1.0f, mu, phi, xiTau = r3;
   const float twoPi = 2.0f * F_PI;
   switch (s.kind) {
     case 1:
-      qx = draw(L);
-      qy = draw(L);
+      qx = r0;
+      qy = r1;
       mu = s.mu;
       phi = s.phi;
       break;
     case 2:
-      qx = draw(L);
-      qy = draw(L);
-      phi = draw(L) * twoPi;
+      qx = r0;
+      qy = r1;
+      phi = r2 * twoPi;
       mu = s.mu;
       break;
-    case 3:
-      qx = draw(L);
-      qy = draw(L);
-      mu = -sqrtf(draw(L));
-      phi = draw(L) * twoPi;
+    case 3: {
+      qx = r0;
+      qy = r1;
+      mu = -sqrtf(r2);
+      phi = r3 * twoPi;
+      float t1, t2, t3;
+      L.rng.next4(p.key0, p.key1, xiTau, t1, t2, t3);
       break;
+    }
     case 4:
       qx = s.x;
       qy = s.y;
@@ -504,12 +480,18 @@ I3RC_HD void init_photon(const P& p, Lane& L, long long id) {
       qx = s.x;
       qy = s.y;
       qz = s.z;
-      mu = sqrtf(draw(L));
-      phi = draw(L) * twoPi;
-      while (fabsf(mu) < 2.0f * F_TINY) mu = sqrtf(draw(L));
+      mu = sqrtf(r0);
+      phi = r1 * twoPi;
+      while (fabsf(mu) < 2.0f * F_TINY) {
+        float t1, t2, t3;
+        L.rng.next4(p.key0, p.key1, mu, t1, t2, t3);
+        mu = sqrtf(mu);
+      }
       if (!s.pointsUp) mu = -mu;
-      if (s.hasDx) qx += s.deltaX * (1.0f - 0.5f * draw(L));
-      if (s.hasDy) qy += s.deltaY * (1.0f - 0.5f * draw(L));
+      float d0, d1, d2;
+      L.rng.next4(p.key0, p.key1, d0, d1, d2, xiTau);
+      if (s.hasDx) qx += s.deltaX * (1.0f - 0.5f * d0);
+      if (s.hasDy) qy += s.deltaY * (1.0f - 0.5f * d1);
       break;
     }
     case 6:
@@ -518,8 +500,8 @@ I3RC_HD void init_photon(const P& p, Lane& L, long long id) {
       qz = s.z;
       mu = s.detectorMu;
       phi = s.detectorPhi;  // stored as given, like the reference (monteCarloIllumination.f95:392)
-      if (s.hasDx) qx += s.deltaX * (1.0f - 0.5f * draw(L));
-      if (s.hasDy) qy += s.deltaY * (1.0f - 0.5f * draw(L));
+      if (s.hasDx) qx += s.deltaX * (1.0f - 0.5f * r0);
+      if (s.hasDy) qy += s.deltaY * (1.0f - 0.5f * r1);
       break;
     default:
       qx = I3RC_LDG(s.ax + id);
@@ -550,8 +532,8 @@ I3RC_HD void init_photon(const P& p, Lane& L, long long id) {
   L.w = 1.0f;
   L.order = 0;
   L.active = 1;
-  L.cnt[CNT_PHOTONS]++;
-  start_segment(p, L);
+  I3RC_COUNT(L, CNT_PHOTONS, 1);
+  start_segment(p, L, xiTau);
 }
 
 // Lambertian albedo map lookup (Code/surfaceProperties.f95:121-162)
@@ -585,9 +567,10 @@ struct LeTask {
   float tauFree;  // second-stage optical path (MCRT:1576-1578)
 };
 
-// Build the local-estimate task towards direction d from the lane's event point (MCRT:1473-1510, 1540-1569).
-// Returns 0 when the contribution is known to be zero without tracing.
-I3RC_HD int make_le_task(const Problem& p, Lane& L, int d, LeTask& t) {
+// Build the local-estimate task towards direction d from the lane's event point (MCRT:1473-1510, 1540-1569); xiTau and
+// xiAcc are the two deviates Iwabuchi's roulette may need.  Returns 0 when the contribution is known to be zero
+// without tracing.
+I3RC_HD int make_le_task(const Problem& p, Lane& L, int d, float xiTau, float xiAcc, LeTask& t) {
   const float* dv = p.dirs + d * DIR_STRIDE;
   float phat;
   if (L.comp < 1) {
@@ -604,12 +587,11 @@ I3RC_HD int make_le_task(const Problem& p, Lane& L, int d, LeTask& t) {
   int mode = MODE_LE_PLAIN;
   float lim = INFINITY, tauFree = 0.0f;
   if (p.useRRIntensity) {
-    tauFree = draw_tau(L);  // MCRT:1542
+    tauFree = tau_of(xiTau);  // MCRT:1542
     if (F_PI * phat <= p.zetaMin) {
       // Iwabuchi Eq 13 (MCRT:1546-1559).  The acceptance draw does not depend on the ray, so it is taken
       // first and rejected rays are never traced (the reference traces them and then discards them).
-      float xi = draw(L);
-      if (!(xi <= F_PI * phat / p.zetaMin)) return 0;
+      if (!(xiAcc <= F_PI * phat / p.zetaMin)) return 0;
       mode = MODE_LE_SMALL;
       lim = tauFree;
     } else {
@@ -654,7 +636,7 @@ I3RC_HD void tally_intensity(const Problem& p, Lane& L, float c) {
     size_t ncol = (size_t)p.nx * p.ny;
     I3RC_ATOMIC_ADD(p.intensity + (size_t)L.td * ncol + col, c);
     if (p.trackByComponent) I3RC_ATOMIC_ADD(p.intByComp + ((size_t)L.tcomp * p.nDir + L.td) * ncol + col, c);
-    L.cnt[CNT_CONTRIB]++;
+    I3RC_COUNT(L, CNT_CONTRIB, 1);
   }
 }
 
@@ -663,7 +645,7 @@ I3RC_HD void tally_intensity(const Problem& p, Lane& L, float c) {
 I3RC_HD int finish_le_ray(const Problem& p, Lane& L) {
   int done = L.done;
   L.done = DONE_RUN;
-  L.cnt[CNT_CROSS_LE] += L.nsteps;
+  I3RC_COUNT(L, CNT_CROSS_LE, L.nsteps);
   L.nsteps = 0;
   float c = 0.0f;
   if (done != DONE_BAD) {
@@ -695,7 +677,7 @@ template <class P>
 I3RC_HD void segment_finished(const P& p, Lane& L) {
   L.segDone = L.done;
   L.done = DONE_RUN;
-  L.cnt[CNT_CROSS_PH] += L.nsteps;
+  I3RC_COUNT(L, CNT_CROSS_PH, L.nsteps);
   L.nsteps = 0;
   ray_local(p, L, &L.fx, &L.fy, &L.fz);
   L.cx = L.ix;
@@ -703,20 +685,26 @@ I3RC_HD void segment_finished(const P& p, Lane& L) {
   L.cz = L.iz;
 }
 
+// The photon is finished: its slot can be refilled.  The number of random deviates it consumed is counted here.
+I3RC_HD void photon_done(Lane& L) {
+  L.active = 0;
+  I3RC_COUNT(L, CNT_RNG, L.rng.block * 4u);
+}
+
 // Boundary and collision handling of a finished segment up to (not including) the local estimate
-// (MCRT:499-561, 581-649).  Returns 1 if the photon lives on (and then wants its local estimate when
-// computeIntensity), 0 if it is finished.
-I3RC_HD int photon_event(const Problem& p, Lane& L) {
+// (MCRT:499-561, 581-649).  xi0, xi1: deviates of the event (surface: mu, phi; collision: component pick).
+// Returns 1 if the photon lives on (and then wants its local estimate when computeIntensity), 0 if it is finished.
+I3RC_HD int photon_event(const Problem& p, Lane& L, float xi0, float xi1) {
   const int done = L.segDone;
   if (done == DONE_BAD) {
-    L.cnt[CNT_BAD]++;
-    L.active = 0;
+    I3RC_COUNT(L, CNT_BAD, 1);
+    photon_done(L);
     return 0;
   }
   if (done == DONE_TOP) {  // MCRT:499-514
     I3RC_ATOMIC_ADD(p.fluxUp + L.cy * p.nx + L.cx, L.w);
-    L.cnt[CNT_TOP]++;
-    L.active = 0;
+    I3RC_COUNT(L, CNT_TOP, 1);
+    photon_done(L);
     return 0;
   }
   if (done == DONE_BOTTOM) {  // MCRT:515-580
@@ -724,18 +712,20 @@ I3RC_HD int photon_event(const Problem& p, Lane& L) {
     L.cz = 0;
     L.fz = 0.0f;
     I3RC_ATOMIC_ADD(p.fluxDown + L.cy * p.nx + L.cx, L.w);
-    L.cnt[CNT_SURF]++;
-    float mu;
-    do {
-      mu = sqrtf(draw(L));
-    } while (!(fabsf(mu) > 2.0f * F_TINY));
-    float phi = 2.0f * F_PI * draw(L);
+    I3RC_COUNT(L, CNT_SURF, 1);
+    float mu = sqrtf(xi0);
+    while (!(fabsf(mu) > 2.0f * F_TINY)) {  // MCRT:542-549 (needs a deviate of exactly 0: once in 2^32)
+      float t1, t2, t3;
+      L.rng.next4(p.key0, p.key1, mu, t1, t2, t3);
+      mu = sqrtf(mu);
+    }
+    float phi = 2.0f * F_PI * xi1;
     if (p.useSurfaceBDRF)
       L.w *= surface_reflectance(p, abs_x(p, L.cx, L.fx), abs_y(p, L.cy, L.fy));
     else
       L.w *= p.surfaceAlbedo;
     if (L.w <= F_TINY) {
-      L.active = 0;
+      photon_done(L);
       return 0;
     }
     make_direction(mu, phi, &L.ux, &L.uy, &L.uz);
@@ -743,12 +733,12 @@ I3RC_HD int photon_event(const Problem& p, Lane& L) {
     L.pfi = 0;
   } else {  // collision, MCRT:581-668
     L.order++;
-    L.cnt[CNT_COLL]++;
+    I3RC_COUNT(L, CNT_COLL, 1);
     const size_t ncell = (size_t)p.nx * p.ny * p.nz;
     const size_t cell = ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx;
     int comp = 1;
     if (p.nc > 1) {  // findIndex(xi, (/0, cumulativeExt(:)/)), MCRT:637-638
-      float xi = draw(L);
+      const float xi = xi0;
       while (comp < p.nc && xi >= I3RC_LDG(p.cumExt + (size_t)(comp - 1) * ncell + cell)) comp++;
     }
     L.comp = comp;
@@ -760,34 +750,35 @@ I3RC_HD int photon_event(const Problem& p, Lane& L) {
       I3RC_ATOMIC_ADD(p.fluxAbs + L.cy * p.nx + L.cx, a);
       I3RC_ATOMIC_ADD(p.volAbs + cell, a);
       L.w *= ssa;
-      L.cnt[CNT_ABS]++;
+      I3RC_COUNT(L, CNT_ABS, 1);
     }
   }
   return 1;
 }
 
 // After the local estimate (or directly, when no intensity is wanted): roulette, scattering, next segment
-// (MCRT:670-688); for a surface event just continue with the reflected direction.
+// (MCRT:670-688); for a surface event just continue with the reflected direction.  xiRoulette, xiAngle, xiTau:
+// deviates of the event's block.
 template <class P>
-I3RC_HD void continue_photon(const P& p, Lane& L) {
+I3RC_HD void continue_photon(const P& p, Lane& L, float xiRoulette, float xiAngle, float xiTau) {
   if (L.comp >= 1) {
     if (p.useRussianRoulette && L.w < p.rouletteW * 0.5f) {  // MCRT:673-679
-      if (draw(L) >= L.w / p.rouletteW) {
+      if (xiRoulette >= L.w / p.rouletteW) {
         L.w = 0.0f;
-        L.cnt[CNT_KILL]++;
+        I3RC_COUNT(L, CNT_KILL, 1);
       } else {
         L.w = p.rouletteW;
       }
     }
     if (L.w <= F_TINY) {
-      L.active = 0;
+      photon_done(L);
       return;
     }
     const TableDesc& T = p.tables[L.comp - 1];
-    float theta = scattering_angle(T.inv + (size_t)L.pfi * T.nInv, T.nInv, draw(L));
-    next_direct(L, I3RC_COS(theta));
+    float theta = scattering_angle(T.inv + (size_t)L.pfi * T.nInv, T.nInv, xiAngle);
+    next_direct(p, L, I3RC_COS(theta));
   }
-  start_segment(p, L);
+  start_segment(p, L, xiTau);
 }
 
 // ---- per-lane scheduler (one lane owns the photon AND traces its local-estimate rays one after the other).
@@ -798,24 +789,33 @@ I3RC_HD void advance_le(const P& p, Lane& L) {
   while (L.d < p.nDir) {
     LeTask t;
     int d = L.d++;
-    if (make_le_task(p, L, d, t)) {
+    float xiTau, xiAcc;
+    if ((d & 1) == 0) {  // one block serves two directions, exactly like the warp-cooperative kernel
+      L.rng.next4(p.key0, p.key1, xiTau, xiAcc, L.le2, L.le3);
+    } else {
+      xiTau = L.le2;
+      xiAcc = L.le3;
+    }
+    if (make_le_task(p, L, d, xiTau, xiAcc, t)) {
       start_le_task(p, L, t);
       return;
     }
   }
-  continue_photon(p, L);
+  continue_photon(p, L, L.ev1, L.ev2, L.ev3);
 }
 
 template <class P>
 I3RC_HD void handle_event(const P& p, Lane& L) {
   if (L.mode == MODE_PHOTON) {
     segment_finished(p, L);
-    if (!photon_event(p, L)) return;
+    float xi0;
+    L.rng.next4(p.key0, p.key1, xi0, L.ev1, L.ev2, L.ev3);  // the event's block
+    if (!photon_event(p, L, xi0, L.ev1)) return;
     if (p.computeIntensity) {
       L.d = 0;
       advance_le(p, L);
     } else {
-      continue_photon(p, L);
+      continue_photon(p, L, L.ev1, L.ev2, L.ev3);
     }
     return;
   }

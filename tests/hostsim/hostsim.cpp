@@ -116,6 +116,8 @@ static void run_lanes(const HostSimArgs* a, const Problem& p0) {
   static_cast<Problem&>(p) = p0;
   Lane L;
   memset(&L, 0, sizeof(L));
+  uint32_t cnt[CNT_N] = {0};
+  L.cnt = cnt;
   for (long long id = 0; id < a->n; id++) {
     L.active = 0; L.done = DONE_RUN; L.mode = MODE_PHOTON;
     init_photon(p, L, id);
@@ -124,7 +126,7 @@ static void run_lanes(const HostSimArgs* a, const Problem& p0) {
       else handle_event(p, L);
     }
   }
-  for (int i = 0; i < CNT_N; i++) a->counters[i] += L.cnt[i];
+  for (int i = 0; i < CNT_N; i++) a->counters[i] += cnt[i];
 }
 
 extern "C" {
@@ -149,6 +151,8 @@ int hostsim_trace_rays(const HostSimArgs* a, int n, const float* pos, const floa
   for (int r = 0; r < n; r++) {
     Lane L;
     memset(&L, 0, sizeof(L));
+    uint32_t cnt[CNT_N] = {0};
+    L.cnt = cnt;
     locate_abs(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, p.dx, pos[3 * r], 1, &L.cx, &L.fx);
     locate_abs(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, p.dy, pos[3 * r + 1], 1, &L.cy, &L.fy);
     locate_abs(p.ze, p.zRegular, p.nz, p.z0, p.zmax, p.dz, pos[3 * r + 2], 0, &L.cz, &L.fz);

@@ -228,7 +228,7 @@ def test_photon_arrays_source(cuda, oracle):
     for name, be in (("g", cuda), ("o", oracle)):
         I = make_integrator(be, d, surfaceAlbedo=0.0)
         vals = []
-        for b in range(16):
+        for b in range(32):
             r2 = np.random.default_rng(100 + b)
             ph = new_PhotonStream(0.5, 0.0, numberOfPhotons=n)
             ph.xPosition, ph.yPosition = r2.random(n, dtype=np.float32), r2.random(n, dtype=np.float32)

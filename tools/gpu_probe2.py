@@ -39,6 +39,7 @@ if __name__ == "__main__":
     wls = sys.argv[1:] or ["landsat"]
     for wl in wls:
         nph = 2_000_000 if wl != "les" else 500_000
-        for tune in ({}, {"steps_per_event_phase": 4}, {"steps_per_event_phase": 8}, {"steps_per_event_phase": 12},
-                     {"event_threshold": 24}, {"block_size": 64}, {"block_size": 256}, {"blocks_per_sm": 4}, {"blocks_per_sm": 3}):
+        for tune in ({"resident_blocks": 5}, {"resident_blocks": 6}, {"resident_blocks": 7}, {"resident_blocks": 8},
+                     {"resident_blocks": 7, "steps_per_event_phase": 4}, {"resident_blocks": 7, "steps_per_event_phase": 8},
+                     {"resident_blocks": 7, "event_threshold": 24}, {"resident_blocks": 7, "event_threshold": 10}):
             run(wl, nph, 2, tune)
