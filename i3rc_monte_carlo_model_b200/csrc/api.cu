@@ -104,7 +104,7 @@ struct i3rc_integrator {
   double traceMs = 0.0;
   long long traceLaunches = 0, otherLaunches = 0;
   // tuning
-  int blockSize = 128, blocksPerSM = 0, residentBlocks = 6, kSteps = 6, eventThreshold = 16;
+  int blockSize = 128, blocksPerSM = 0, residentBlocks = 6, kSteps = 8, eventThreshold = 16;
   // nccl
   void* nccl = nullptr;
   void* ncclLib = nullptr;
