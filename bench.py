@@ -46,7 +46,7 @@ def make_workload(name):
         return dict(workload="i3rcLandsatCloud 128x128x119, HG g=0.85 (299 moments), ssa=1, mu0=0.5, 3 radiance directions, "
                              "Russian roulette for intensity (zetaMin 0.3)",
                     domain=lambda: fields.landsat_cloud(1.0), params=dict(surfaceAlbedo=0.0, **dirs3, **rr), source=src,
-                    photons=4_000_000, cpu_photons=60_000)
+                    photons=16_000_000, cpu_photons=60_000)
     if name == "step":
         return dict(workload="i3rcStepCloud 32x1x32, HG g=0.85 (64 moments), ssa=0.99, mu0=0.5, 3 radiance directions, RR",
                     domain=lambda: fields.step_cloud(0.99), params=dict(surfaceAlbedo=0.0, **dirs3, **rr), source=src,
@@ -93,7 +93,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+                                          "-lms", "50"], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 

@@ -448,11 +448,11 @@ int fill_source(i3rc_integrator* h, const i3rc_photon_source* s, SourceDev& d) {
   return I3RC_SUCCESS;
 }
 
-template <int BLOCK, bool REG, int MINB>
+template <int BLOCK, bool REG, int MINB, int STEPS>
 int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   int perSM = h->blocksPerSM;
   if (perSM <= 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_transport<BLOCK, REG, MINB>, BLOCK, 0) != cudaSuccess || perSM <= 0)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_transport<BLOCK, REG, MINB, STEPS>, BLOCK, 0) != cudaSuccess || perSM <= 0)
       perSM = 1;
   }
   long long want = (p.src.n + BLOCK - 1) / BLOCK;
@@ -461,31 +461,27 @@ int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   if (grid < 1) grid = 1;
   ProblemT<REG> pt;
   static_cast<Problem&>(pt) = p;
-  k_transport<BLOCK, REG, MINB><<<(unsigned)grid, BLOCK, 0, h->stream>>>(pt, h->kSteps, h->eventThreshold);
+  k_transport<BLOCK, REG, MINB, STEPS><<<(unsigned)grid, BLOCK, 0, h->stream>>>(pt, h->eventThreshold);
   return I3RC_SUCCESS;
 }
-// MINB = resident blocks per SM the kernel is compiled for (register cap 65536 / (MINB * BLOCK))
-template <int BLOCK, int MINB>
+// MINB = resident blocks per SM the kernel is compiled for (register cap 65536 / (MINB * BLOCK));
+// STEPS = DDA crossings per bookkeeping round (unrolled)
+template <int BLOCK, int MINB, int STEPS>
 int launch_transport_b(i3rc_integrator* h, const Problem& p) {
-  return (p.xyRegular && p.zRegular) ? launch_transport_t<BLOCK, true, MINB>(h, p) : launch_transport_t<BLOCK, false, MINB>(h, p);
+  return (p.xyRegular && p.zRegular) ? launch_transport_t<BLOCK, true, MINB, STEPS>(h, p)
+                                     : launch_transport_t<BLOCK, false, MINB, STEPS>(h, p);
 }
 int launch_transport(i3rc_integrator* h, const Problem& p) {
-  switch (h->blockSize) {
-    case 64:
-      return launch_transport_b<64, 10>(h, p);
-    case 256:
-      return launch_transport_b<256, 3>(h, p);
+  const int steps = h->kSteps <= 4 ? 4 : (h->kSteps <= 6 ? 6 : 8);
+  switch (h->residentBlocks) {
+    case 5:
+      return steps == 4 ? launch_transport_b<128, 5, 4>(h, p) : steps == 6 ? launch_transport_b<128, 5, 6>(h, p) : launch_transport_b<128, 5, 8>(h, p);
+    case 7:
+      return steps == 4 ? launch_transport_b<128, 7, 4>(h, p) : steps == 6 ? launch_transport_b<128, 7, 6>(h, p) : launch_transport_b<128, 7, 8>(h, p);
+    case 8:
+      return steps == 4 ? launch_transport_b<128, 8, 4>(h, p) : steps == 6 ? launch_transport_b<128, 8, 6>(h, p) : launch_transport_b<128, 8, 8>(h, p);
     default:
-      switch (h->residentBlocks) {
-        case 5:
-          return launch_transport_b<128, 5>(h, p);
-        case 7:
-          return launch_transport_b<128, 7>(h, p);
-        case 8:
-          return launch_transport_b<128, 8>(h, p);
-        default:
-          return launch_transport_b<128, 6>(h, p);
-      }
+      return steps == 4 ? launch_transport_b<128, 6, 4>(h, p) : steps == 6 ? launch_transport_b<128, 6, 6>(h, p) : launch_transport_b<128, 6, 8>(h, p);
   }
 }
 
@@ -967,6 +963,8 @@ int i3rc_specifyParameters(i3rc_integrator* h, const i3rc_params* p) {
       d[2] = mu;
       for (int a = 0; a < 3; a++) d[3 + a] = fabsf(d[a]) >= 2.0f * F_TINY ? 1.0f / fabsf(d[a]) : INFINITY;
       d[6] = 4.0f * F_PI * fabsf(mu);
+    d[7] = 1.0f / d[6];
+      d[7] = 1.0f / d[6];
     }
     CUDA_OK(h, upload(&h->d_dirs, h->dirs.data(), h->dirs.size(), h->stream));
     dfree(h->d_intensity);
@@ -1451,7 +1449,7 @@ int i3rc_reset_timing(i3rc_integrator* h) {
 int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
   if (!h || !key) return I3RC_FAILURE;
   std::string k(key);
-  if (k == "block_size" && (value == 64 || value == 128 || value == 256))
+  if (k == "block_size" && value == 128)
     h->blockSize = value;
   else if (k == "blocks_per_sm" && value >= 0)
     h->blocksPerSM = value;

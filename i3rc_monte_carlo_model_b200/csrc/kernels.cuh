@@ -24,8 +24,8 @@ namespace i3rc {
 // which lane traces which ray (up to float summation order in the tallies).
 constexpr int QCAP = 128;  // local-estimate tasks per warp (ring, power of two): 4.5 KB of shared memory per warp
 
-template <int BLOCK, bool REG, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG> p, const int stepsPerRound, const int eventThreshold) {
+template <int BLOCK, bool REG, int MINB, int STEPS>
+__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG> p, const int eventThreshold) {
   __shared__ LeTask s_task[BLOCK / 32][QCAP];
   __shared__ int s_head[BLOCK / 32];
   __shared__ uint32_t s_cnt[BLOCK / 32][CNT_N];
@@ -50,11 +50,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG> p
   bool pending = false;   // own segment ended, event not processed yet
   bool exhausted = false;
 
-  // `stepsPerRound` DDA crossings for every lane that has a running ray, then -- for all lanes at once, so that the
+  // STEPS DDA crossings for every lane that has a running ray, then -- for all lanes at once, so that the
   // divergent bookkeeping code runs with as many lanes as possible -- finished rays are closed and idle lanes pop tasks
   auto trace_round = [&]() {
 #pragma unroll 1
-    for (int k = 0; k < stepsPerRound; k++)
+    for (int k = 0; k < STEPS; k++)
       if (hasRay && L.done == DONE_RUN) dda_step(p, L);
     if (hasRay && L.done != DONE_RUN) {
       if (L.mode == MODE_PHOTON) {

@@ -90,7 +90,7 @@ struct Problem {
   float maxExt;
   const TableDesc* tables;
   int computeIntensity, nDir;
-  const float* dirs;  // [nDir][DIR_STRIDE]: d.x d.y d.z 1/|d.x| 1/|d.y| 1/|d.z| 4*pi*|mu| pad
+  const float* dirs;  // [nDir][DIR_STRIDE]: d.x d.y d.z 1/|d.x| 1/|d.y| 1/|d.z| 4*pi*|mu| 1/(4*pi*|mu|)
   int useRayTracing, useRussianRoulette, useRRIntensity, useHybrid, numOrdersOrig, limitContrib, useSurfaceBDRF;
   int trackByComponent;
   float rouletteW, surfaceAlbedo, zetaMin, maxContrib;
@@ -143,7 +143,7 @@ struct Lane {
 I3RC_HD float cell_w(const float* edges, int regular, float d, int i) {
   return regular ? d : (I3RC_LDG(edges + i + 1) - I3RC_LDG(edges + i));
 }
-I3RC_HD float inv_abs(float d) { return fabsf(d) >= 2.0f * F_TINY ? 1.0f / fabsf(d) : INFINITY; }
+I3RC_HD float inv_abs(float d) { return fabsf(d) >= 2.0f * F_TINY ? I3RC_FDIV(1.0f, fabsf(d)) : INFINITY; }
 
 // largest i in [0, n-1] with edges[i] <= v (edges has n+1 entries); clamps
 I3RC_HD int search_edges(const float* edges, int n, float v) {
@@ -210,7 +210,7 @@ I3RC_HD void make_direction(float mu, float phi, float* ux, float* uy, float* uz
 I3RC_HD float scattering_angle(const float* T, int n, float xi) {
   int k = (int)(xi * (float)n);  // angleIndex - 1
   if (k + 1 < n) {
-    float leftOver = xi - (float)k / (float)n;
+    float leftOver = xi - I3RC_FDIV((float)k, (float)n);
     return (1.0f - leftOver) * I3RC_LDG(T + k) + leftOver * I3RC_LDG(T + k + 1);
   }
   return I3RC_LDG(T + n - 1);
@@ -218,10 +218,10 @@ I3RC_HD float scattering_angle(const float* T, int n, float xi) {
 
 // lookUpPhaseFuncValsFromTable, MCRT:1613-1652
 I3RC_HD float phase_lookup(const float* T, int n, float angle) {
-  float deltaTheta = F_PI / (float)(n - 1);
-  int k = (int)(angle / deltaTheta);  // angleIndex - 1
+  float deltaTheta = I3RC_FDIV(F_PI, (float)(n - 1));
+  int k = (int)I3RC_FDIV(angle, deltaTheta);  // angleIndex - 1
   if (k + 1 < n) {
-    float wgt = 1.0f - (angle - (float)k * deltaTheta) / deltaTheta;
+    float wgt = 1.0f - I3RC_FDIV(angle - (float)k * deltaTheta, deltaTheta);
     return wgt * I3RC_LDG(T + k) + (1.0f - wgt) * I3RC_LDG(T + k + 1);
   }
   return I3RC_LDG(T + n - 1);
@@ -243,11 +243,11 @@ I3RC_HD void next_direct(const P& p, Lane& L, float cs) {
       D = AX * AX + AY * AY;
     }
   }
-  float B = sqrtf(fmaxf(1.0f - cs * cs, 0.0f) / D);
+  float B = sqrtf(I3RC_FDIV(fmaxf(1.0f - cs * cs, 0.0f), D));
   AX *= B;
   AY *= B;
   B = L.ux * AX - L.uy * AY;
-  D = cs - B / (1.0f + fabsf(L.uz));
+  D = cs - I3RC_FDIV(B, 1.0f + fabsf(L.uz));
   L.ux = L.ux * D + AX;
   L.uy = L.uy * D - AY;
   float sb = (L.uz * B >= 0.0f) ? fabsf(B) : -fabsf(B);
@@ -582,7 +582,7 @@ I3RC_HD int make_le_task(const Problem& p, Lane& L, int d, float xiTau, float xi
     const TableDesc& T = p.tables[L.comp - 1];
     const float* tab = (p.useHybrid && L.order <= p.numOrdersOrig) ? T.fwdOrig : T.fwd;
     float val = phase_lookup(tab + (size_t)L.pfi * T.nFwd, T.nFwd, ang);
-    phat = val / I3RC_LDG(dv + 6);
+    phat = val * I3RC_LDG(dv + 7);  // 1 / (4 pi |mu|), MCRT:1509
   }
   int mode = MODE_LE_PLAIN;
   float lim = INFINITY, tauFree = 0.0f;
@@ -591,12 +591,12 @@ I3RC_HD int make_le_task(const Problem& p, Lane& L, int d, float xiTau, float xi
     if (F_PI * phat <= p.zetaMin) {
       // Iwabuchi Eq 13 (MCRT:1546-1559).  The acceptance draw does not depend on the ray, so it is taken
       // first and rejected rays are never traced (the reference traces them and then discards them).
-      if (!(xiAcc <= F_PI * phat / p.zetaMin)) return 0;
+      if (!(xiAcc * p.zetaMin <= F_PI * phat)) return 0;
       mode = MODE_LE_SMALL;
       lim = tauFree;
     } else {
       mode = MODE_LE_BIG1;  // MCRT:1566-1569
-      lim = -I3RC_LOG(p.zetaMin / fmaxf(F_TINY, F_PI * phat));
+      lim = -I3RC_LOG(I3RC_FDIV(p.zetaMin, fmaxf(F_TINY, F_PI * phat)));
     }
   }
   t.xy = (uint32_t)L.cx | ((uint32_t)L.cy << 16);
@@ -606,7 +606,7 @@ I3RC_HD int make_le_task(const Problem& p, Lane& L, int d, float xiTau, float xi
   t.fz = L.fz;
   t.tauLimit = lim;
   t.cw = L.w * phat;
-  t.cfix = L.w * p.zetaMin / F_PI;
+  t.cfix = L.w * p.zetaMin * (1.0f / F_PI);
   t.tauFree = tauFree;
   return 1;
 }
@@ -763,7 +763,7 @@ template <class P>
 I3RC_HD void continue_photon(const P& p, Lane& L, float xiRoulette, float xiAngle, float xiTau) {
   if (L.comp >= 1) {
     if (p.useRussianRoulette && L.w < p.rouletteW * 0.5f) {  // MCRT:673-679
-      if (xiRoulette >= L.w / p.rouletteW) {
+      if (xiRoulette * p.rouletteW >= L.w) {
         L.w = 0.0f;
         I3RC_COUNT(L, CNT_KILL, 1);
       } else {

@@ -89,6 +89,7 @@ static void fill(const HostSimArgs* a, Problem& p, std::vector<TableDesc>& td, s
     d[0] = st * cosf(phi); d[1] = st * sinf(phi); d[2] = mu;
     for (int k = 0; k < 3; k++) d[3 + k] = fabsf(d[k]) >= 2.0f * F_TINY ? 1.0f / fabsf(d[k]) : INFINITY;
     d[6] = 4.0f * F_PI * fabsf(mu);
+    d[7] = 1.0f / d[6];
   }
   p.dirs = dirs.data();
   p.useRayTracing = a->useRayTracing; p.useRussianRoulette = a->useRussianRoulette; p.useRRIntensity = a->useRRIntensity;

@@ -39,7 +39,7 @@ if __name__ == "__main__":
     wls = sys.argv[1:] or ["landsat"]
     for wl in wls:
         nph = 2_000_000 if wl != "les" else 500_000
-        for tune in ({"resident_blocks": 5}, {"resident_blocks": 6}, {"resident_blocks": 7}, {"resident_blocks": 8},
-                     {"resident_blocks": 7, "steps_per_event_phase": 4}, {"resident_blocks": 7, "steps_per_event_phase": 8},
-                     {"resident_blocks": 7, "event_threshold": 24}, {"resident_blocks": 7, "event_threshold": 10}):
+        for tune in ({"resident_blocks": 6}, {"resident_blocks": 6, "steps_per_event_phase": 6}, {"resident_blocks": 6, "steps_per_event_phase": 4},
+                     {"resident_blocks": 7}, {"resident_blocks": 5}, {"resident_blocks": 8}, {"resident_blocks": 7, "steps_per_event_phase": 6},
+                     {"event_threshold": 20}, {"event_threshold": 12}):
             run(wl, nph, 2, tune)
