@@ -448,41 +448,50 @@ int fill_source(i3rc_integrator* h, const i3rc_photon_source* s, SourceDev& d) {
   return I3RC_SUCCESS;
 }
 
-template <int BLOCK, bool REG, int MINB, int STEPS>
+template <int BLOCK, bool REG, bool FAST, int MINB, int STEPS>
 int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   int perSM = h->blocksPerSM;
   if (perSM <= 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_transport<BLOCK, REG, MINB, STEPS>, BLOCK, 0) != cudaSuccess || perSM <= 0)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_transport<BLOCK, REG, FAST, MINB, STEPS>, BLOCK, 0) != cudaSuccess || perSM <= 0)
       perSM = 1;
   }
   long long want = (p.src.n + BLOCK - 1) / BLOCK;
   long long grid = (long long)h->numSMs * perSM;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  ProblemT<REG> pt;
+  ProblemT<REG, FAST> pt;
   static_cast<Problem&>(pt) = p;
-  k_transport<BLOCK, REG, MINB, STEPS><<<(unsigned)grid, BLOCK, 0, h->stream>>>(pt, h->eventThreshold);
+  k_transport<BLOCK, REG, FAST, MINB, STEPS><<<(unsigned)grid, BLOCK, 0, h->stream>>>(pt, h->eventThreshold);
   return I3RC_SUCCESS;
 }
 // MINB = resident blocks per SM the kernel is compiled for (register cap 65536 / (MINB * BLOCK));
-// STEPS = DDA crossings per bookkeeping round (unrolled)
-template <int BLOCK, int MINB, int STEPS>
-int launch_transport_b(i3rc_integrator* h, const Problem& p) {
-  return (p.xyRegular && p.zRegular) ? launch_transport_t<BLOCK, true, MINB, STEPS>(h, p)
-                                     : launch_transport_t<BLOCK, false, MINB, STEPS>(h, p);
+// STEPS = DDA crossings per bookkeeping round.  The tuning grid exists for the common configuration only (regular
+// grid + the FAST feature set, see ProblemT); everything else runs the general kernel at its default shape.
+template <int MINB>
+int launch_transport_fast(i3rc_integrator* h, const Problem& p) {
+  const int steps = h->kSteps <= 4 ? 4 : (h->kSteps <= 6 ? 6 : 8);
+  return steps == 4   ? launch_transport_t<128, true, true, MINB, 4>(h, p)
+         : steps == 6 ? launch_transport_t<128, true, true, MINB, 6>(h, p)
+                      : launch_transport_t<128, true, true, MINB, 8>(h, p);
 }
 int launch_transport(i3rc_integrator* h, const Problem& p) {
-  const int steps = h->kSteps <= 4 ? 4 : (h->kSteps <= 6 ? 6 : 8);
-  switch (h->residentBlocks) {
-    case 5:
-      return steps == 4 ? launch_transport_b<128, 5, 4>(h, p) : steps == 6 ? launch_transport_b<128, 5, 6>(h, p) : launch_transport_b<128, 5, 8>(h, p);
-    case 7:
-      return steps == 4 ? launch_transport_b<128, 7, 4>(h, p) : steps == 6 ? launch_transport_b<128, 7, 6>(h, p) : launch_transport_b<128, 7, 8>(h, p);
-    case 8:
-      return steps == 4 ? launch_transport_b<128, 8, 4>(h, p) : steps == 6 ? launch_transport_b<128, 8, 6>(h, p) : launch_transport_b<128, 8, 8>(h, p);
-    default:
-      return steps == 4 ? launch_transport_b<128, 6, 4>(h, p) : steps == 6 ? launch_transport_b<128, 6, 6>(h, p) : launch_transport_b<128, 6, 8>(h, p);
+  const bool reg = p.xyRegular && p.zRegular;
+  const bool fast = p.useRayTracing && p.src.kind != 5 && p.src.kind != 6 && !p.useSurfaceBDRF && !p.useHybrid && !p.limitContrib &&
+                    !p.trackByComponent;
+  if (reg && fast) {
+    switch (h->residentBlocks) {
+      case 5:
+        return launch_transport_fast<5>(h, p);
+      case 7:
+        return launch_transport_fast<7>(h, p);
+      case 8:
+        return launch_transport_fast<8>(h, p);
+      default:
+        return launch_transport_fast<6>(h, p);
+    }
   }
+  if (reg) return launch_transport_t<128, true, false, 6, 8>(h, p);
+  return fast ? launch_transport_t<128, false, true, 6, 8>(h, p) : launch_transport_t<128, false, false, 6, 8>(h, p);
 }
 
 // zero tallies, trace one batch, post-process (MCRT:296-395); no host synchronisation

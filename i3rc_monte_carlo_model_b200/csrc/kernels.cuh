@@ -24,8 +24,8 @@ namespace i3rc {
 // which lane traces which ray (up to float summation order in the tallies).
 constexpr int QCAP = 128;  // local-estimate tasks per warp (ring, power of two): 4.5 KB of shared memory per warp
 
-template <int BLOCK, bool REG, int MINB, int STEPS>
-__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG> p, const int eventThreshold) {
+template <int BLOCK, bool REG, bool FAST, int MINB, int STEPS>
+__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, FAST> p, const int eventThreshold) {
   __shared__ LeTask s_task[BLOCK / 32][QCAP];
   __shared__ int s_head[BLOCK / 32];
   __shared__ uint32_t s_cnt[BLOCK / 32][CNT_N];

@@ -106,9 +106,13 @@ struct Problem {
 
 // Compile-time specialisation of the hot loop: REG = x, y and z are all regularly spaced (the I3RC cases), so a
 // ray's path length per cell is a per-ray constant and no edge arrays are read while stepping.
-template <bool REG>
+// FAST = the common configuration (ray tracing, a top-of-domain source, constant Lambertian albedo, original phase
+// functions, no contribution limiting): the rarely used code paths are compiled out, which keeps the kernel's
+// instruction footprint small (the SM's instruction cache holds ~32 KB).
+template <bool REG, bool FAST = false>
 struct ProblemT : Problem {
   static constexpr bool kRegular = REG;
+  static constexpr bool kFast = FAST;
 };
 
 struct Lane {
@@ -428,7 +432,7 @@ I3RC_HD void max_cross_section_flight(const P& p, Lane& L, float xiFirst) {
 template <class P>
 I3RC_HD void start_segment(const P& p, Lane& L, float xiTau) {
   L.mode = MODE_PHOTON;
-  if (p.useRayTracing) {
+  if (P::kFast || p.useRayTracing) {
     start_ray(p, L, L.ux, L.uy, L.uz, inv_abs(L.ux), inv_abs(L.uy), inv_abs(L.uz), tau_of(xiTau));
   } else {
     L.nsteps = 0;
@@ -476,40 +480,48 @@ I3RC_HD void init_photon(const P& p, Lane& L, long long id) {
       mu = s.mu;
       phi = s.phi;
       break;
-    case 5: {
-      qx = s.x;
-      qy = s.y;
-      qz = s.z;
-      mu = sqrtf(r0);
-      phi = r1 * twoPi;
-      while (fabsf(mu) < 2.0f * F_TINY) {
-        float t1, t2, t3;
-        L.rng.next4(p.key0, p.key1, mu, t1, t2, t3);
-        mu = sqrtf(mu);
-      }
-      if (!s.pointsUp) mu = -mu;
-      float d0, d1, d2;
-      L.rng.next4(p.key0, p.key1, d0, d1, d2, xiTau);
-      if (s.hasDx) qx += s.deltaX * (1.0f - 0.5f * d0);
-      if (s.hasDy) qy += s.deltaY * (1.0f - 0.5f * d1);
-      break;
-    }
-    case 6:
-      qx = s.x;
-      qy = s.y;
-      qz = s.z;
-      mu = s.detectorMu;
-      phi = s.detectorPhi;  // stored as given, like the reference (monteCarloIllumination.f95:392)
-      if (s.hasDx) qx += s.deltaX * (1.0f - 0.5f * r0);
-      if (s.hasDy) qy += s.deltaY * (1.0f - 0.5f * r1);
-      break;
-    default:
+    case 7:  // hand-filled public arrays of the reference type
       qx = I3RC_LDG(s.ax + id);
       qy = I3RC_LDG(s.ay + id);
       qz = I3RC_LDG(s.az + id);
       mu = I3RC_LDG(s.amu + id);
       phi = I3RC_LDG(s.aphi + id);
       break;
+    default:
+      break;
+  }
+  if (!P::kFast && (s.kind == 5 || s.kind == 6)) {  // internal sources
+    switch (s.kind) {
+      case 5: {
+        qx = s.x;
+        qy = s.y;
+        qz = s.z;
+        mu = sqrtf(r0);
+        phi = r1 * twoPi;
+        while (fabsf(mu) < 2.0f * F_TINY) {
+          float t1, t2, t3;
+          L.rng.next4(p.key0, p.key1, mu, t1, t2, t3);
+          mu = sqrtf(mu);
+        }
+        if (!s.pointsUp) mu = -mu;
+        float d0, d1, d2;
+        L.rng.next4(p.key0, p.key1, d0, d1, d2, xiTau);
+        if (s.hasDx) qx += s.deltaX * (1.0f - 0.5f * d0);
+        if (s.hasDy) qy += s.deltaY * (1.0f - 0.5f * d1);
+        break;
+      }
+      case 6:
+        qx = s.x;
+        qy = s.y;
+        qz = s.z;
+        mu = s.detectorMu;
+        phi = s.detectorPhi;  // stored as given, like the reference (monteCarloIllumination.f95:392)
+        if (s.hasDx) qx += s.deltaX * (1.0f - 0.5f * r0);
+        if (s.hasDy) qy += s.deltaY * (1.0f - 0.5f * r1);
+        break;
+      default:
+        break;
+    }
   }
   locate_frac(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, qx, &L.cx, &L.fx);
   locate_frac(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, qy, &L.cy, &L.fy);
@@ -570,7 +582,8 @@ struct LeTask {
 // Build the local-estimate task towards direction d from the lane's event point (MCRT:1473-1510, 1540-1569); xiTau and
 // xiAcc are the two deviates Iwabuchi's roulette may need.  Returns 0 when the contribution is known to be zero
 // without tracing.
-I3RC_HD int make_le_task(const Problem& p, Lane& L, int d, float xiTau, float xiAcc, LeTask& t) {
+template <class P>
+I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, LeTask& t) {
   const float* dv = p.dirs + d * DIR_STRIDE;
   float phat;
   if (L.comp < 1) {
@@ -580,7 +593,7 @@ I3RC_HD int make_le_task(const Problem& p, Lane& L, int d, float xiTau, float xi
     proj = fminf(fmaxf(proj, -1.0f), 1.0f);
     float ang = acosf(proj);
     const TableDesc& T = p.tables[L.comp - 1];
-    const float* tab = (p.useHybrid && L.order <= p.numOrdersOrig) ? T.fwdOrig : T.fwd;
+    const float* tab = (!P::kFast && p.useHybrid && L.order <= p.numOrdersOrig) ? T.fwdOrig : T.fwd;
     float val = phase_lookup(tab + (size_t)L.pfi * T.nFwd, T.nFwd, ang);
     phat = val * I3RC_LDG(dv + 7);  // 1 / (4 pi |mu|), MCRT:1509
   }
@@ -626,8 +639,9 @@ I3RC_HD void start_le_task(const P& p, Lane& L, const LeTask& t) {
                I3RC_LDG(dv + 1), I3RC_LDG(dv + 2), I3RC_LDG(dv + 3), I3RC_LDG(dv + 4), I3RC_LDG(dv + 5), t.tauLimit);
 }
 
-I3RC_HD void tally_intensity(const Problem& p, Lane& L, float c) {
-  if (p.limitContrib && c > p.maxContrib) {  // MCRT:1598-1609
+template <class P>
+I3RC_HD void tally_intensity(const P& p, Lane& L, float c) {
+  if (!P::kFast && p.limitContrib && c > p.maxContrib) {  // MCRT:1598-1609
     I3RC_ATOMIC_ADD(p.excess + L.tcomp * p.nDir + L.td, c - p.maxContrib);
     c = p.maxContrib;
   }
@@ -635,14 +649,15 @@ I3RC_HD void tally_intensity(const Problem& p, Lane& L, float c) {
     int col = L.iy * p.nx + L.ix;
     size_t ncol = (size_t)p.nx * p.ny;
     I3RC_ATOMIC_ADD(p.intensity + (size_t)L.td * ncol + col, c);
-    if (p.trackByComponent) I3RC_ATOMIC_ADD(p.intByComp + ((size_t)L.tcomp * p.nDir + L.td) * ncol + col, c);
+    if (!P::kFast && p.trackByComponent) I3RC_ATOMIC_ADD(p.intByComp + ((size_t)L.tcomp * p.nDir + L.td) * ncol + col, c);
     I3RC_COUNT(L, CNT_CONTRIB, 1);
   }
 }
 
 // A local-estimate ray has stopped (L.done != 0).  Returns 1 when the same ray goes on with its second stage
 // (Iwabuchi's chained trace, MCRT:1576-1578), 0 when it is finished and its contribution has been tallied.
-I3RC_HD int finish_le_ray(const Problem& p, Lane& L) {
+template <class P>
+I3RC_HD int finish_le_ray(const P& p, Lane& L) {
   int done = L.done;
   L.done = DONE_RUN;
   I3RC_COUNT(L, CNT_CROSS_LE, L.nsteps);
@@ -694,7 +709,8 @@ I3RC_HD void photon_done(Lane& L) {
 // Boundary and collision handling of a finished segment up to (not including) the local estimate
 // (MCRT:499-561, 581-649).  xi0, xi1: deviates of the event (surface: mu, phi; collision: component pick).
 // Returns 1 if the photon lives on (and then wants its local estimate when computeIntensity), 0 if it is finished.
-I3RC_HD int photon_event(const Problem& p, Lane& L, float xi0, float xi1) {
+template <class P>
+I3RC_HD int photon_event(const P& p, Lane& L, float xi0, float xi1) {
   const int done = L.segDone;
   if (done == DONE_BAD) {
     I3RC_COUNT(L, CNT_BAD, 1);
@@ -720,7 +736,7 @@ I3RC_HD int photon_event(const Problem& p, Lane& L, float xi0, float xi1) {
       mu = sqrtf(mu);
     }
     float phi = 2.0f * F_PI * xi1;
-    if (p.useSurfaceBDRF)
+    if (!P::kFast && p.useSurfaceBDRF)
       L.w *= surface_reflectance(p, abs_x(p, L.cx, L.fx), abs_y(p, L.cy, L.fy));
     else
       L.w *= p.surfaceAlbedo;
