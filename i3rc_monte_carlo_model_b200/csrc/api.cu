@@ -448,11 +448,11 @@ int fill_source(i3rc_integrator* h, const i3rc_photon_source* s, SourceDev& d) {
   return I3RC_SUCCESS;
 }
 
-template <int BLOCK, bool REG, bool FAST, int MINB, int STEPS>
+template <int BLOCK, bool REG, bool FAST, int MINB, int STEPS, int NSLOT, int QCAP>
 int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   int perSM = h->blocksPerSM;
   if (perSM <= 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_transport<BLOCK, REG, FAST, MINB, STEPS>, BLOCK, 0) != cudaSuccess || perSM <= 0)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_transport<BLOCK, REG, FAST, MINB, STEPS, NSLOT, QCAP>, BLOCK, 0) != cudaSuccess || perSM <= 0)
       perSM = 1;
   }
   long long want = (p.src.n + BLOCK - 1) / BLOCK;
@@ -461,18 +461,18 @@ int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   if (grid < 1) grid = 1;
   ProblemT<REG, FAST> pt;
   static_cast<Problem&>(pt) = p;
-  k_transport<BLOCK, REG, FAST, MINB, STEPS><<<(unsigned)grid, BLOCK, 0, h->stream>>>(pt, h->eventThreshold);
+  k_transport<BLOCK, REG, FAST, MINB, STEPS, NSLOT, QCAP><<<(unsigned)grid, BLOCK, 0, h->stream>>>(pt, h->eventThreshold);
   return I3RC_SUCCESS;
 }
 // MINB = resident blocks per SM the kernel is compiled for (register cap 65536 / (MINB * BLOCK));
 // STEPS = DDA crossings per bookkeeping round.  The tuning grid exists for the common configuration only (regular
 // grid + the FAST feature set, see ProblemT); everything else runs the general kernel at its default shape.
-template <int MINB>
+template <int MINB, int NSLOT>
 int launch_transport_fast(i3rc_integrator* h, const Problem& p) {
   const int steps = h->kSteps <= 4 ? 4 : (h->kSteps <= 6 ? 6 : 8);
-  return steps == 4   ? launch_transport_t<128, true, true, MINB, 4>(h, p)
-         : steps == 6 ? launch_transport_t<128, true, true, MINB, 6>(h, p)
-                      : launch_transport_t<128, true, true, MINB, 8>(h, p);
+  return steps == 4   ? launch_transport_t<128, true, true, MINB, 4, NSLOT, 128>(h, p)
+         : steps == 6 ? launch_transport_t<128, true, true, MINB, 6, NSLOT, 128>(h, p)
+                      : launch_transport_t<128, true, true, MINB, 8, NSLOT, 128>(h, p);
 }
 int launch_transport(i3rc_integrator* h, const Problem& p) {
   const bool reg = p.xyRegular && p.zRegular;
@@ -481,17 +481,15 @@ int launch_transport(i3rc_integrator* h, const Problem& p) {
   if (reg && fast) {
     switch (h->residentBlocks) {
       case 5:
-        return launch_transport_fast<5>(h, p);
-      case 7:
-        return launch_transport_fast<7>(h, p);
-      case 8:
-        return launch_transport_fast<8>(h, p);
+        return launch_transport_fast<5, 96>(h, p);
+      case 4:
+        return launch_transport_fast<4, 96>(h, p);
       default:
-        return launch_transport_fast<6>(h, p);
+        return launch_transport_fast<6, 64>(h, p);
     }
   }
-  if (reg) return launch_transport_t<128, true, false, 6, 8>(h, p);
-  return fast ? launch_transport_t<128, false, true, 6, 8>(h, p) : launch_transport_t<128, false, false, 6, 8>(h, p);
+  if (reg) return launch_transport_t<128, true, false, 6, 8, 64, 128>(h, p);
+  return fast ? launch_transport_t<128, false, true, 6, 8, 64, 128>(h, p) : launch_transport_t<128, false, false, 6, 8, 64, 128>(h, p);
 }
 
 // zero tallies, trace one batch, post-process (MCRT:296-395); no host synchronisation
@@ -1464,7 +1462,7 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->blocksPerSM = value;
   else if (k == "steps_per_event_phase" && value >= 1)
     h->kSteps = value;
-  else if (k == "resident_blocks" && value >= 5 && value <= 8)
+  else if (k == "resident_blocks" && value >= 4 && value <= 8)
     h->residentBlocks = value;
   else if (k == "event_threshold" && value >= 1 && value <= 32)
     h->eventThreshold = value;

@@ -8,160 +8,337 @@
 namespace i3rc {
 
 // ---- K1: persistent, warp-cooperative photon transport ---------------------------------------------------------
-// grid = (#SMs x resident blocks).  Every lane owns one photon slot and refills it from the device photon counter
-// (one warp-aggregated atomicAdd per refill round).  A warp alternates between two phases:
-//
-//   EVENT phase  (uniform code over the lanes whose path segment has ended): boundary / collision handling, then a
-//                warp-uniform loop over the radiance directions in which every such lane builds its local-estimate
-//                ray as a 36-byte TASK and pushes it into the warp's shared-memory ring, then roulette + scattering
-//                and the start of the next path segment;
-//   TRACE phase  (rounds of a few DDA cell crossings for every lane, then ray bookkeeping for all lanes at once): a lane traces its own path segment; when that
-//                ends it pops local-estimate tasks -- of ANY photon of the warp -- from the ring and traces those,
-//                so lanes stay busy while the longest segment of the warp is still running.  The phase ends when the
-//                ring is empty and at least `eventThreshold` lanes wait for their event.
-//
+// grid = (#SMs x resident blocks).  Lanes are NOT tied to photons.  Every warp owns, in shared memory,
+//   * a pool of NSLOT photon slots (position, direction, weight, Philox counter: 52 bytes each),
+//   * a ring of QCAP ray TASKS (36 bytes each): a photon's next path segment, or one local-estimate ray,
+//   * the list of slots whose path segment has ended and whose event (boundary / collision) is due,
+// and alternates, as a warp-uniform state machine, between
+//   TRACE rounds:  STEPS cell crossings for every lane that holds a ray; then, for all lanes at once, finished rays are
+//                  closed (a segment's end point goes back to its slot, which joins the event list; a local-estimate
+//                  ray is tallied) and idle lanes pop the next tasks from the ring;
+//   EVENT batches: when 32 events are due (or the ring has run dry) lane i takes the i-th due slot: boundary or
+//                  collision handling, then a warp-uniform loop over the radiance directions in which every lane
+//                  turns its local-estimate ray into a task, then roulette + scattering, refill of dead slots from the
+//                  device photon counter (one warp-aggregated atomicAdd), and the task of the next path segment.
+// So both the cell-crossing loop and the event code run with (nearly) full warps, whatever the individual photons do.
+// A batch that finds the ring full is suspended between two directions and resumed after more trace rounds.
 // The physics functions are the ones of transport.cuh; the per-photon Philox streams make the result independent of
 // which lane traces which ray (up to float summation order in the tallies).
-constexpr int QCAP = 128;  // local-estimate tasks per warp (ring, power of two): 4.5 KB of shared memory per warp
+template <int NSLOT>
+struct SlotPool {  // structure of arrays: lane i touches slot[k] of every array
+  uint32_t xy[NSLOT];   // cx | cy << 16
+  uint32_t zs[NSLOT];   // cz | segDone << 16
+  float fx[NSLOT], fy[NSLOT], fz[NSLOT];
+  float ux[NSLOT], uy[NSLOT], uz[NSLOT];
+  float w[NSLOT];
+  int order[NSLOT];
+  uint32_t id[NSLOT];     // photon number inside this launch
+  uint32_t block[NSLOT];  // Philox blocks consumed so far
+};
 
-template <int BLOCK, bool REG, bool FAST, int MINB, int STEPS>
-__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, FAST> p, const int eventThreshold) {
-  __shared__ LeTask s_task[BLOCK / 32][QCAP];
-  __shared__ int s_head[BLOCK / 32];
-  __shared__ uint32_t s_cnt[BLOCK / 32][CNT_N];
+template <int BLOCK, bool REG, bool FAST, int MINB, int STEPS, int NSLOT, int QCAP>
+__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, FAST> p, const int lowWater) {
+  constexpr int NW = BLOCK / 32;
+  static_assert((QCAP & (QCAP - 1)) == 0 && QCAP >= 64, "ring size: power of two, room for one push of 32");
+  static_assert(NSLOT >= 32 && NSLOT <= 255, "slot ids are bytes");
+  __shared__ LeTask s_task[NW][QCAP];
+  __shared__ SlotPool<NSLOT> s_pool[NW];
+  __shared__ uint8_t s_pend[NW][NSLOT];
+  __shared__ uint32_t s_cnt[NW][CNT_N];
+  __shared__ uint32_t s_susp[NW][7][32];  // per-lane state of a suspended event batch
+  __shared__ uint32_t s_ray[NW][4][32];   // per lane: what its ray is for (photon slot, or local-estimate parameters)
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   LeTask* q = s_task[warp];
-  int* headp = &s_head[warp];
-  int tail = 0;  // warp-uniform; the ring holds positions [head, tail)
-  if (lane == 0) *headp = 0;
-  __syncwarp();
+  SlotPool<NSLOT>& pool = s_pool[warp];
+  uint8_t* pend = s_pend[warp];
 
-  Lane L;
-  L.cnt = s_cnt[warp];
+  // warp-uniform bookkeeping (registers): ring positions [head, tail), number of due events
+  int head = 0, tail = 0, npend = NSLOT;
+  bool exhausted = false;
+  for (int k = lane; k < NSLOT; k += 32) {  // every slot starts by asking for a photon
+    pend[k] = (uint8_t)k;
+    pool.zs[k] = (uint32_t)DONE_NEW << 16;
+  }
   if (lane < CNT_N) s_cnt[warp][lane] = 0;
   __syncwarp();
-  L.active = 0;
-  L.done = DONE_RUN;
-  L.mode = MODE_PHOTON;
-  L.nsteps = 0;
-  bool hasRay = false;    // the ray registers hold a ray in flight (own segment if L.mode == MODE_PHOTON)
-  bool pending = false;   // own segment ended, event not processed yet
-  bool exhausted = false;
 
-  // STEPS DDA crossings for every lane that has a running ray, then -- for all lanes at once, so that the
-  // divergent bookkeeping code runs with as many lanes as possible -- finished rays are closed and idle lanes pop tasks
-  auto trace_round = [&]() {
-#pragma unroll 1
-    for (int k = 0; k < STEPS; k++)
-      if (hasRay && L.done == DONE_RUN) dda_step(p, L);
-    if (hasRay && L.done != DONE_RUN) {
-      if (L.mode == MODE_PHOTON) {
-        segment_finished(p, L);
-        pending = true;
-        hasRay = false;
-      } else if (!finish_le_ray(p, L)) {
-        hasRay = false;
-      }
-    }
-    if (!hasRay && *(volatile int*)headp < tail) {
-      int h = atomicAdd(headp, 1);
-      if (h < tail) {
-        start_le_task(p, L, q[h & (QCAP - 1)]);
-        hasRay = true;
-      }
-    }
-  };
-  auto fix_head = [&]() {  // pops may overshoot the tail
-    __syncwarp();
-    if (lane == 0 && *headp > tail) *headp = tail;
-    __syncwarp();
-  };
+  Lane R;  // the ray this lane is tracing
+  R.cnt = s_cnt[warp];
+  R.done = DONE_IDLE;
+  R.mode = MODE_PHOTON;
+  R.nsteps = 0;
+  R.slot = 0;
+
+  // event batch control (kept across trace rounds); everything else of a suspended batch waits in shared memory
+  int stage = 0;  // 0: no batch in progress, 1: local-estimate directions (next: dcur), 2: scattering + next segment
+  int dcur = 0;
 
   for (;;) {
-    // ================= EVENT phase =================
-    const bool ev = pending && !hasRay;
-    bool alive = false;
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;  // the event's block of deviates
-    if (ev) {
-      pending = false;
-      L.rng.next4(p.key0, p.key1, a0, a1, a2, a3);
-      alive = photon_event(p, L, a0, a1) != 0;
-    }
-    if (p.computeIntensity) {
-      if (__any_sync(full, alive)) {
-        float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
-        for (int d = 0; d < p.nDir; d++) {
-          if ((d & 1) == 0 && alive) L.rng.next4(p.key0, p.key1, c0, c1, c2, c3);  // one block per two directions
-          LeTask t;
-          const bool push = alive && make_le_task(p, L, d, (d & 1) ? c2 : c0, (d & 1) ? c3 : c1, t);
-          const unsigned m = __ballot_sync(full, push);
-          const int n = __popc(m);
-          if (n == 0) continue;
-          int head = __shfl_sync(full, *(volatile int*)headp, 0);
-          if (tail - head + n > QCAP) {
-            // ring full: every lane (also the ones in the middle of their event) helps to drain it; lanes of this
-            // event phase must be free again before they start their next segment
-            for (;;) {
-              trace_round();
-              const bool stillQueued = __shfl_sync(full, *(volatile int*)headp, 0) < tail;
-              if (!stillQueued && !__any_sync(full, ev && hasRay)) break;
-            }
-            fix_head();
-          }
-          if (push) q[(tail + __popc(m & lt)) & (QCAP - 1)] = t;
-          tail += n;
-          __syncwarp();
-        }
+    // ================= EVENT batch =================
+    // A batch starts when 32 events are due, or when the ring has run dry and few lanes are tracing.  It normally
+    // runs to its end here; if the ring gets full it is suspended (state to shared memory) and resumed after the
+    // next trace round.
+    bool run = stage != 0;
+    int eslot = 0;
+    bool has = false, alive = false;
+    if (stage == 0) {
+      const int busy = __popc(__ballot_sync(full, R.done != DONE_IDLE));
+      const int queued = tail - head;
+      if (npend >= 32 || (npend > 0 && queued == 0 && busy <= lowWater)) {
+        const int k = min(32, npend);
+        has = lane < k;
+        eslot = has ? pend[npend - k + lane] : 0;
+        npend -= k;
+        run = true;
+      } else if (npend == 0 && queued == 0 && busy == 0) {
+        break;  // nothing in flight, nothing queued, nothing due: all slots are empty
       }
     }
-    if (alive) {
-      continue_photon(p, L, a1, a2, a3);  // roulette, scattering, start of the next own segment
-      if (L.active) hasRay = true;
-    }
-    // refill finished slots
-    {
-      const bool need = !L.active && !exhausted && !hasRay && !pending;
-      const unsigned m = __ballot_sync(full, need);
-      if (m) {
-        unsigned long long base = 0;
-        const int leader = __ffs(m) - 1;
-        if (lane == leader) base = atomicAdd(p.nextPhoton, (unsigned long long)__popc(m));
-        base = __shfl_sync(full, base, leader);
-        if (need) {
-          const long long id = (long long)base + __popc(m & lt);
-          if (id < p.src.n) {
-            init_photon(p, L, id);
-            hasRay = true;
-          } else {
-            exhausted = true;
-          }
+    if (run) {
+      if (stage != 0) {  // resuming a suspended batch
+        const uint32_t w = s_susp[warp][6][lane];
+        eslot = (int)(w & 0xffu);
+        has = (w & 0x100u) != 0;
+      }
+      Lane E;  // the photon whose event this lane is processing
+      E.cnt = s_cnt[warp];
+      E.active = 0;
+      E.comp = 0;
+      E.pfi = 0;
+      float a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;  // deviates of the event's block still to be used
+      float c2 = 0.0f, c3 = 0.0f;             // second half of the block shared by two local-estimate directions
+      if (has) {
+        const uint32_t zs = pool.zs[eslot];
+        E.segDone = (int)(zs >> 16);
+        if (E.segDone != DONE_NEW) {
+          const uint32_t xy = pool.xy[eslot];
+          E.cx = (int)(xy & 0xffffu);
+          E.cy = (int)(xy >> 16);
+          E.cz = (int)(int16_t)(zs & 0xffffu);
+          E.fx = pool.fx[eslot];
+          E.fy = pool.fy[eslot];
+          E.fz = pool.fz[eslot];
+          E.ux = pool.ux[eslot];
+          E.uy = pool.uy[eslot];
+          E.uz = pool.uz[eslot];
+          E.w = pool.w[eslot];
+          E.order = pool.order[eslot];
+          E.rng.init((uint64_t)(p.firstPhoton + (long long)pool.id[eslot]));
+          E.rng.block = pool.block[eslot];
+          E.active = 1;
         }
+      }
+      if (stage == 0) {  // boundary / collision handling (MCRT:499-561, 581-649)
+        alive = false;
+        if (has && E.segDone != DONE_NEW) {
+          float a0;
+          E.rng.next4(p.key0, p.key1, a0, a1, a2, a3);
+          alive = photon_event(p, E, a0, a1) != 0;
+        }
+        dcur = 0;
+        stage = (p.computeIntensity && __any_sync(full, alive)) ? 1 : 2;
+      } else {  // resume: the rest of the batch state comes back from shared memory
+        const uint32_t* sv = s_susp[warp][0] + lane;
+        alive = (sv[6 * 32] & 0x200u) != 0;
+        a1 = __uint_as_float(sv[0 * 32]);
+        a2 = __uint_as_float(sv[1 * 32]);
+        a3 = __uint_as_float(sv[2 * 32]);
+        c2 = __uint_as_float(sv[3 * 32]);
+        c3 = __uint_as_float(sv[4 * 32]);
+        E.comp = (int)(sv[5 * 32] >> 16);
+        E.pfi = (int)(sv[5 * 32] & 0xffffu);
+      }
+      if (stage == 1) {  // local-estimate tasks, one direction at a time (MCRT:1473-1569)
+        while (dcur < p.nDir && QCAP - (tail - head) >= 32) {
+          float c0 = c2, c1 = c3;
+          if ((dcur & 1) == 0 && alive) E.rng.next4(p.key0, p.key1, c0, c1, c2, c3);  // one block per two directions
+          LeTask t;
+          const bool push = alive && make_le_task(p, E, dcur, c0, c1, t);
+          const unsigned m = __ballot_sync(full, push);
+          if (push) q[(tail + __popc(m & lt)) & (QCAP - 1)] = t;
+          tail += __popc(m);
+          dcur++;
+        }
+        if (dcur >= p.nDir) stage = 2;
+      }
+      if (stage == 2 && QCAP - (tail - head) >= 32) {
+        bool go = false;
+        float xiTau = a3;
+        if (alive) {
+          scatter_photon(p, E, a1, a2);  // roulette, new direction (MCRT:670-688)
+          go = E.active != 0;
+        }
+        // slots whose photon is finished (or that never had one) take the next photon of the batch
+        const bool need = has && !go && !exhausted;
+        const unsigned mn = __ballot_sync(full, need);
+        if (mn) {
+          unsigned long long base = 0;
+          const int leader = __ffs(mn) - 1;
+          if (lane == leader) base = atomicAdd(p.nextPhoton, (unsigned long long)__popc(mn));
+          base = __shfl_sync(full, base, leader);
+          if (need) {
+            const long long id = (long long)base + __popc(mn & lt);
+            if (id < p.src.n) {
+              xiTau = init_photon_state(p, E, id);
+              pool.id[eslot] = (uint32_t)id;
+              go = true;
+            }
+          }
+          exhausted = (long long)base + __popc(mn) >= p.src.n;
+        }
+        // the next path segment becomes a task (MCRT:474-497)
+        const unsigned mg = __ballot_sync(full, go);
+        if (go) {
+          LeTask t;
+          t.xy = (uint32_t)E.cx | ((uint32_t)E.cy << 16);
+          t.zdmc = (uint32_t)E.cz | ((uint32_t)MODE_PHOTON << 21);
+          t.fx = E.fx;
+          t.fy = E.fy;
+          t.fz = E.fz;
+          t.tauLimit = tau_of(xiTau);
+          t.cw = __int_as_float(eslot);
+          t.cfix = 0.0f;
+          t.tauFree = xiTau;
+          q[(tail + __popc(mg & lt)) & (QCAP - 1)] = t;
+          pool.fx[eslot] = E.fx;
+          pool.fy[eslot] = E.fy;
+          pool.fz[eslot] = E.fz;
+          pool.ux[eslot] = E.ux;
+          pool.uy[eslot] = E.uy;
+          pool.uz[eslot] = E.uz;
+          pool.w[eslot] = E.w;
+          pool.order[eslot] = E.order;
+          pool.block[eslot] = E.rng.block;
+        }
+        tail += __popc(mg);
+        stage = 0;
+      }
+      if (stage != 0) {  // suspended: park the photon in its slot, the rest of the batch state in the scratch
+        if (has) {
+          pool.xy[eslot] = (uint32_t)E.cx | ((uint32_t)E.cy << 16);
+          pool.zs[eslot] = ((uint32_t)E.cz & 0xffffu) | ((uint32_t)(E.active ? DONE_INSIDE : DONE_NEW) << 16);
+          pool.fx[eslot] = E.fx;
+          pool.fy[eslot] = E.fy;
+          pool.fz[eslot] = E.fz;
+          pool.ux[eslot] = E.ux;
+          pool.uy[eslot] = E.uy;
+          pool.uz[eslot] = E.uz;
+          pool.w[eslot] = E.w;
+          pool.order[eslot] = E.order;
+          pool.block[eslot] = E.rng.block;
+        }
+        uint32_t* sv = s_susp[warp][0] + lane;
+        sv[0 * 32] = __float_as_uint(a1);
+        sv[1 * 32] = __float_as_uint(a2);
+        sv[2 * 32] = __float_as_uint(a3);
+        sv[3 * 32] = __float_as_uint(c2);
+        sv[4 * 32] = __float_as_uint(c3);
+        sv[5 * 32] = ((uint32_t)E.comp << 16) | ((uint32_t)E.pfi & 0xffffu);
+        sv[6 * 32] = (uint32_t)eslot | (has ? 0x100u : 0u) | (alive ? 0x200u : 0u);
       }
     }
     __syncwarp();
-    // ================= TRACE phase =================
-    bool anything = false;
-    // towards the end of a batch fewer lanes hold photons: do not wait for more events than can come
-    const int nActive = __popc(__ballot_sync(full, L.active != 0));
-    const int threshold = min(eventThreshold, max(1, nActive >> 1));
-    for (;;) {
-      trace_round();
-      const unsigned busy = __ballot_sync(full, hasRay);
-      const int ready = __popc(__ballot_sync(full, pending && !hasRay));
-      if (busy == 0) {
-        anything = ready > 0;
-        break;
-      }
-      const bool queued = __shfl_sync(full, *(volatile int*)headp, 0) < tail;
-      if (!queued && ready >= threshold) {
-        anything = true;
-        break;
+
+    // ================= TRACE round =================
+    // (pairs of steps: the two extinction registers of a ray swap roles on every step, see dda_step)
+#pragma unroll 1
+    for (int k = 0; k < STEPS / 2; k++) {
+      if (R.done == DONE_RUN) dda_step<0>(p, R);
+      if (R.done == DONE_RUN) dda_step<1>(p, R);
+    }
+    ray_after_steps(R);
+    // close finished rays
+    bool segEnd = false;
+    if (R.done != DONE_RUN && R.done != DONE_IDLE) {
+      uint32_t* rv = s_ray[warp][0] + lane;  // what the ray is for waits in shared memory while it is traced
+      if (R.mode == MODE_PHOTON) {
+        const int done = R.done;
+        R.slot = (int)rv[0];
+        I3RC_COUNT(R, CNT_CROSS_PH, R.nsteps);
+        float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+        int cx, cy, cz;
+        if (FAST || p.useRayTracing) {
+          if (done == DONE_INSIDE) ray_stop_inside(p, R);
+          fx = pool.fx[R.slot];  // offsets stay where the ray does not move along an axis
+          fy = pool.fy[R.slot];
+          fz = pool.fz[R.slot];
+          ray_local(p, R, &fx, &fy, &fz);
+          cx = ray_ix(p, R);
+          cy = ray_iy(p, R);
+          cz = ray_iz(p, R);
+        } else {  // maximum cross-section flight: the event point is already in the photon registers
+          fx = R.fx;
+          fy = R.fy;
+          fz = R.fz;
+          cx = R.cx;
+          cy = R.cy;
+          cz = R.cz;
+          pool.block[R.slot] = R.rng.block;
+        }
+        pool.fx[R.slot] = fx;
+        pool.fy[R.slot] = fy;
+        pool.fz[R.slot] = fz;
+        pool.xy[R.slot] = (uint32_t)cx | ((uint32_t)cy << 16);
+        pool.zs[R.slot] = ((uint32_t)cz & 0xffffu) | ((uint32_t)done << 16);
+        segEnd = true;
+        R.done = DONE_IDLE;
+      } else {
+        I3RC_COUNT(R, CNT_CROSS_LE, R.nsteps);
+        R.td = (int)(rv[0] & 0xffu);
+        R.tcomp = (int)(rv[0] >> 8);
+        R.tcw = __uint_as_float(rv[1 * 32]);
+        R.tcfix = __uint_as_float(rv[2 * 32]);
+        R.ttauFree = __uint_as_float(rv[3 * 32]);
+        if (!finish_le_ray(p, R)) R.done = DONE_IDLE;
       }
     }
-    fix_head();
-    if (!anything && !__any_sync(full, L.active || !exhausted)) break;
+    const unsigned ms = __ballot_sync(full, segEnd);
+    if (segEnd) pend[npend + __popc(ms & lt)] = (uint8_t)s_ray[warp][0][lane];
+    npend += __popc(ms);
+    // idle lanes take the next tasks
+    const bool idle = R.done == DONE_IDLE;
+    const unsigned mi = __ballot_sync(full, idle);
+    const int avail = tail - head;
+    const int rank = __popc(mi & lt);
+    if (idle && rank < avail) {
+      const LeTask t = q[(head + rank) & (QCAP - 1)];
+      const int mode = (int)((t.zdmc >> 21) & 7u);
+      uint32_t* rv = s_ray[warp][0] + lane;
+      if (mode == MODE_PHOTON) {
+        const int slot = __float_as_int(t.cw);
+        rv[0] = (uint32_t)slot;
+        R.mode = MODE_PHOTON;
+        const float ux = pool.ux[slot], uy = pool.uy[slot], uz = pool.uz[slot];
+        if (FAST || p.useRayTracing) {
+          start_ray_at(p, R, (int)(t.xy & 0xffffu), (int)(t.xy >> 16), (int)(t.zdmc & 0xffffu), t.fx, t.fy, t.fz, ux, uy,
+                       uz, inv_abs(ux), inv_abs(uy), inv_abs(uz), t.tauLimit);
+        } else {  // maximum cross-section: the whole flight at once; its end is handled by the next round
+          R.cx = (int)(t.xy & 0xffffu);
+          R.cy = (int)(t.xy >> 16);
+          R.cz = (int)(t.zdmc & 0xffffu);
+          R.fx = t.fx;
+          R.fy = t.fy;
+          R.fz = t.fz;
+          R.ux = ux;
+          R.uy = uy;
+          R.uz = uz;
+          R.rng.init((uint64_t)(p.firstPhoton + (long long)pool.id[slot]));
+          R.rng.block = pool.block[slot];
+          R.nsteps = 0;
+          max_cross_section_flight(p, R, t.tauFree);
+        }
+      } else {
+        start_le_task(p, R, t);
+        rv[0] = (uint32_t)R.td | ((uint32_t)R.tcomp << 8);
+        rv[1 * 32] = __float_as_uint(R.tcw);
+        rv[2 * 32] = __float_as_uint(R.tcfix);
+        rv[3 * 32] = __float_as_uint(R.ttauFree);
+      }
+    }
+    head += min(__popc(mi), avail);
+    __syncwarp();
   }
   // flush the warp's counters
   __syncwarp();
@@ -183,18 +360,23 @@ __global__ void k_trace_rays(const ProblemT<false> p, int n, const float* __rest
   locate_abs(p.ze, p.zRegular, p.nz, p.z0, p.zmax, p.dz, pos[3 * r + 2], 0, &L.cz, &L.fz);
   float dx = dir[3 * r], dy = dir[3 * r + 1], dz = dir[3 * r + 2];
   start_ray(p, L, dx, dy, dz, inv_abs(dx), inv_abs(dy), inv_abs(dz), tauLimit ? tauLimit[r] : INFINITY);
-  while (L.done == DONE_RUN) dda_step(p, L);
+  while (L.done == DONE_RUN) {
+    dda_step(p, L);
+    ray_after_steps(L);
+  }
+  if (L.done == DONE_INSIDE) ray_stop_inside(p, L);
   tauOut[r] = L.done == DONE_BAD ? -2.0f : L.tau;
   ray_local(p, L, &L.fx, &L.fy, &L.fz);
+  const int ix = ray_ix(p, L), iy = ray_iy(p, L), iz = ray_iz(p, L);
   if (posOut) {
-    posOut[3 * r] = abs_x(p, L.ix, L.fx);
-    posOut[3 * r + 1] = abs_y(p, L.iy, L.fy);
-    posOut[3 * r + 2] = L.done == DONE_TOP ? p.zmax : (L.done == DONE_BOTTOM ? p.z0 : abs_z(p, L.iz, L.fz));
+    posOut[3 * r] = abs_x(p, ix, L.fx);
+    posOut[3 * r + 1] = abs_y(p, iy, L.fy);
+    posOut[3 * r + 2] = L.done == DONE_TOP ? p.zmax : (L.done == DONE_BOTTOM ? p.z0 : abs_z(p, iz, L.fz));
   }
   if (idxOut) {
-    idxOut[3 * r] = L.ix + 1;
-    idxOut[3 * r + 1] = L.iy + 1;
-    idxOut[3 * r + 2] = L.iz + 1;
+    idxOut[3 * r] = ix + 1;
+    idxOut[3 * r + 1] = iy + 1;
+    idxOut[3 * r + 2] = iz + 1;
   }
 }
 __global__ void k_sample_angles(const float* __restrict__ T, int nSteps, int n, const float* __restrict__ xi,

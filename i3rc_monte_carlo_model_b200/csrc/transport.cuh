@@ -56,7 +56,10 @@ constexpr int MAX_RAY_STEPS = 1 << 26;  // hang protection: a ray that long is d
 enum { CNT_PHOTONS = 0, CNT_BAD, CNT_CROSS_PH, CNT_CROSS_LE, CNT_COLL, CNT_ABS, CNT_CONTRIB, CNT_TOP, CNT_SURF,
        CNT_RNG, CNT_KILL, CNT_NULL, CNT_N };
 
-enum { DONE_RUN = 0, DONE_INSIDE = 1, DONE_TOP = 2, DONE_BOTTOM = 3, DONE_BAD = 4 };
+enum { DONE_RUN = 0, DONE_INSIDE = 1, DONE_TOP = 2, DONE_BOTTOM = 3, DONE_BAD = 4,
+       DONE_IDLE = 5,   // warp-cooperative kernel: the lane holds no ray
+       DONE_NEW = 6,    // warp-cooperative kernel: the photon slot waits for a new photon
+       DONE_STOP = 7 }; // the ray has ended; how (INSIDE / TOP / BOTTOM) is resolved by ray_after_steps()
 enum { MODE_PHOTON = 0, MODE_LE_PLAIN = 1, MODE_LE_SMALL = 2, MODE_LE_BIG1 = 3, MODE_LE_BIG2 = 4 };
 
 struct TableDesc {
@@ -116,12 +119,21 @@ struct ProblemT : Problem {
 };
 
 struct Lane {
-  // current ray
-  int ix, iy, iz, idx;
+  // current ray (regular or irregular grid): linear cell index, signed index strides per axis, and the number of
+  // cells left on each axis before the ray wraps around (x, y) or leaves the domain (z), counting the current one
+  int idx;
+  int stx, sty, stz;
+  int cntx, cnty, cntz;
   float rx, ry, rz, tau, tauLimit;  // path length left to the next x/y/z cell face; optical path so far / target
-  float e;                          // extinction of the current cell
+  // The geometry (idx, cnt*, r*) runs ONE CELL AHEAD of the optical path: the cell whose optical path is still to be
+  // added ("pending") has path length sp; mk = faces crossed when the geometry left it (1, 2, 4 = x, y, z; 8 = that
+  // crossing left the domain).  The extinctions of the pending cell and of the cell the geometry is in live in
+  // e0 / e1, which swap roles on every step (dda_step<PAR>), so that a gather is issued a whole step before its value
+  // is needed and no register move ever waits for it.  e = extinction of the pending cell of a ray that has stopped.
+  float sp, e0, e1, e;
+  int mk;
+  int par;  // which of e0 / e1 holds the pending cell (run-time copy for callers that step one lane at a time)
   float iax, iay, iaz;  // kRegular: path length per cell along the ray (cell width / |direction cosine|); else 1/|cosine|
-  int sgn;
   int done;
   int nsteps;
   int segDone;  // how the photon's last own segment ended (DONE_*), kept until its event is processed
@@ -135,9 +147,10 @@ struct Lane {
   int comp, pfi;   // photon: component (0 = surface) and phase-function entry of the last event
   int d;           // photon: next local-estimate direction to generate (per-lane scheduler only)
   float ev1, ev2, ev3, le2, le3;  // deviates of the current event kept between its stages (per-lane scheduler only)
-  // local-estimate ray being traced (may belong to ANOTHER lane's photon in the warp-cooperative kernel)
+  // local-estimate ray being traced (may belong to ANOTHER photon of the warp in the warp-cooperative kernel)
   int td, tcomp;
   float tcw, tcfix, ttauFree;
+  int slot;  // warp-cooperative kernel: photon slot an own segment belongs to
   Rng rng;
   int active;
   uint32_t* cnt;  // event counters [CNT_N]: the warp's shared-memory block on the device, a plain array on the host
@@ -259,7 +272,6 @@ I3RC_HD void next_direct(const P& p, Lane& L, float cs) {
 }
 
 // ---- the ray ------------------------------------------------------------------------------------
-// Start a ray at the event point (cx,cy,cz ; fx,fy,fz) of the lane along direction (dx,dy,dz).
 // per-cell path length of the ray along one axis (w = width of cell i)
 template <class P>
 I3RC_HD float ray_dt(const P& p, float ia, const float* edges, int regular, float d, int i) {
@@ -267,13 +279,58 @@ I3RC_HD float ray_dt(const P& p, float ia, const float* edges, int regular, floa
   return cell_w(edges, regular, d, i) * ia;
 }
 
+// cell indices of the ray's current cell, recovered from the per-axis counters
+template <class P>
+I3RC_HD int ray_ix(const P& p, const Lane& L) { return L.stx > 0 ? p.nx - L.cntx : L.cntx - 1; }
+template <class P>
+I3RC_HD int ray_iy(const P& p, const Lane& L) { return L.sty > 0 ? p.ny - L.cnty : L.cnty - 1; }
+template <class P>
+I3RC_HD int ray_iz(const P& p, const Lane& L) { return L.stz > 0 ? p.nz - L.cntz : L.cntz - 1; }  // nz / -1: outside
+
+// Move the geometry through the cell it is in, which becomes the pending cell.  Returns true when that leaves the
+// domain (no next cell to gather).  Face crossing with selects, not branches: a warp's lanes cross different faces.
+template <class P>
+I3RC_HD bool ray_advance(const P& p, Lane& L) {
+  const float s = fminf(L.rx, fminf(L.ry, L.rz));
+  const bool cx = L.rx <= s, cy = L.ry <= s, cz = L.rz <= s;
+  const int nx_ = L.cntx - (cx ? 1 : 0), ny_ = L.cnty - (cy ? 1 : 0), nz_ = L.cntz - (cz ? 1 : 0);
+  const bool wx = nx_ == 0, wy = ny_ == 0, out = nz_ == 0;  // periodic in x and y (MCRT:1774-1788); z: MCRT:1793-1804
+  int idx = L.idx + (cx ? L.stx : 0) + (cy ? L.sty : 0) + (cz ? L.stz : 0);
+  idx -= (wx ? L.stx * p.nx : 0) + (wy ? L.sty * p.ny : 0);
+  L.idx = idx;
+  L.cntx = wx ? p.nx : nx_;
+  L.cnty = wy ? p.ny : ny_;
+  L.cntz = nz_;
+  const float qx = L.rx - s, qy = L.ry - s, qz = L.rz - s;
+  L.rx = cx ? ray_dt(p, L.iax, p.xe, p.xyRegular, p.dx, ray_ix(p, L)) : qx;
+  L.ry = cy ? ray_dt(p, L.iay, p.ye, p.xyRegular, p.dy, ray_iy(p, L)) : qy;
+  L.rz = (cz && (P::kRegular || !out)) ? ray_dt(p, L.iaz, p.ze, p.zRegular, p.dz, ray_iz(p, L)) : qz;
+  L.sp = s;
+  L.mk = (cx ? 1 : 0) | (cy ? 2 : 0) | (cz ? 4 : 0) | (out ? 8 : 0);
+  return out;
+}
+// (Re)start the pipeline from the cell the geometry is in, whose extinction is eCell: it becomes the pending cell
+// (in e0: rays always start on an even step) and the gather of the next cell is issued (into e1).
+template <class P>
+I3RC_HD void ray_begin(const P& p, Lane& L, float eCell) {
+  L.e0 = eCell;
+  L.par = 0;
+  if (!ray_advance(p, L)) L.e1 = I3RC_LDG(p.ext + L.idx);
+}
+
+// Start a ray in cell (ix,iy,iz) at offset (fx,fy,fz) inside it along direction (dx,dy,dz); ia* = 1/|cosine|.
 template <class P>
 I3RC_HD void start_ray_at(const P& p, Lane& L, int ix, int iy, int iz, float fx, float fy, float fz, float dx, float dy,
                           float dz, float iax, float iay, float iaz, float tauLimit) {
-  L.ix = ix;
-  L.iy = iy;
-  L.iz = iz;
-  L.idx = (iz * p.ny + iy) * p.nx + ix;
+  const bool px = dx >= 0.0f, py = dy >= 0.0f, pz = dz >= 0.0f;
+  const int sy = p.nx, sz = p.nx * p.ny;
+  L.idx = iz * sz + iy * sy + ix;
+  L.stx = px ? 1 : -1;
+  L.sty = py ? sy : -sy;
+  L.stz = pz ? sz : -sz;
+  L.cntx = px ? p.nx - ix : ix + 1;
+  L.cnty = py ? p.ny - iy : iy + 1;
+  L.cntz = pz ? p.nz - iz : iz + 1;
   if (P::kRegular) {
     iax *= p.dx;
     iay *= p.dy;
@@ -282,15 +339,14 @@ I3RC_HD void start_ray_at(const P& p, Lane& L, int ix, int iy, int iz, float fx,
   L.iax = iax;
   L.iay = iay;
   L.iaz = iaz;
-  L.sgn = (dx >= 0.0f ? 1 : 0) | (dy >= 0.0f ? 2 : 0) | (dz >= 0.0f ? 4 : 0);
-  L.rx = isinf(iax) ? INFINITY : ((L.sgn & 1) ? (1.0f - fx) : fx) * ray_dt(p, iax, p.xe, p.xyRegular, p.dx, ix);
-  L.ry = isinf(iay) ? INFINITY : ((L.sgn & 2) ? (1.0f - fy) : fy) * ray_dt(p, iay, p.ye, p.xyRegular, p.dy, iy);
-  L.rz = isinf(iaz) ? INFINITY : ((L.sgn & 4) ? (1.0f - fz) : fz) * ray_dt(p, iaz, p.ze, p.zRegular, p.dz, iz);
+  L.rx = isinf(iax) ? INFINITY : (px ? (1.0f - fx) : fx) * ray_dt(p, iax, p.xe, p.xyRegular, p.dx, ix);
+  L.ry = isinf(iay) ? INFINITY : (py ? (1.0f - fy) : fy) * ray_dt(p, iay, p.ye, p.xyRegular, p.dy, iy);
+  L.rz = isinf(iaz) ? INFINITY : (pz ? (1.0f - fz) : fz) * ray_dt(p, iaz, p.ze, p.zRegular, p.dz, iz);
   L.tau = 0.0f;
   L.tauLimit = tauLimit;
   L.nsteps = 0;
   L.done = DONE_RUN;
-  L.e = I3RC_LDG(p.ext + L.idx);
+  ray_begin(p, L, I3RC_LDG(p.ext + L.idx));
 }
 
 // Start a ray at the event point (cx,cy,cz ; fx,fy,fz) of the lane along direction (dx,dy,dz).
@@ -300,65 +356,93 @@ I3RC_HD void start_ray(const P& p, Lane& L, float dx, float dy, float dz, float 
   start_ray_at(p, L, L.cx, L.cy, L.cz, L.fx, L.fy, L.fz, dx, dy, dz, iax, iay, iaz, tauLimit);
 }
 
-// ONE cell crossing (the body of accumulateExtinctionAlongPath's loop, MCRT:1690-1806).
+// ONE cell crossing (the body of accumulateExtinctionAlongPath's loop, MCRT:1690-1806), software-pipelined.
 // The ray carries the path length left to the next face on each axis (rx, ry, rz): all quantities stay of the
-// order of one cell, so the accumulated optical path does not lose precision with the distance travelled.
+// order of one cell, so the accumulated optical path does not lose precision with the distance travelled.  The cell
+// is tracked as a linear index that moves by a signed stride per crossed face; a per-axis countdown replaces the
+// index comparisons of the periodic wrap (x, y) and of the exit test (z).
+//
+// dda_step adds the optical path of the pending cell and, unless the ray ends there, moves the geometry on by one
+// cell (ray_advance).  A ray that ends -- target optical path reached inside the pending cell (MCRT:1721-1731), or the
+// pending cell was the last one of the domain (MCRT:1793-1804) -- just stops with DONE_STOP; which of the two it was
+// and where the ray is then are worked out by ray_after_steps() / ray_stop_inside(), outside the hot loop.
+template <int PAR, class P>
+I3RC_HD void dda_step(const P& p, Lane& L) {
+  float& ePending = PAR ? L.e1 : L.e0;
+  const float t = fmaf(L.sp, ePending, L.tau);
+  L.nsteps++;
+  if (t > L.tauLimit || (L.mk & 8)) {
+    L.e = ePending;
+    L.done = DONE_STOP;
+    return;
+  }
+  L.tau = t;
+  if (!ray_advance(p, L)) ePending = I3RC_LDG(p.ext + L.idx);  // (the register is free now: it becomes the look-ahead)
+}
+// one lane at a time (CPU harness, probes): the parity is kept in the lane
 template <class P>
 I3RC_HD void dda_step(const P& p, Lane& L) {
-  const float e = L.e;  // extinction of the current cell: loaded when the cell was entered (hides the gather latency)
-  const float s = fminf(L.rx, fminf(L.ry, L.rz));
-  const float dtau = s * e;
-  L.nsteps++;
-  if (L.tau + dtau > L.tauLimit) {  // MCRT:1721-1731: the target optical path is reached inside this cell
-    const float sp = I3RC_FDIV(L.tauLimit - L.tau, e);
-    L.rx -= sp;
-    L.ry -= sp;
-    L.rz -= sp;
-    L.tau = L.tauLimit;
-    L.done = DONE_INSIDE;
-    return;
+  if (L.par)
+    dda_step<1>(p, L);
+  else
+    dda_step<0>(p, L);
+  L.par ^= 1;
+}
+
+// After a round of steps: how a stopped ray ended, and the hang protection (a ray of more than MAX_RAY_STEPS
+// crossings is dropped as "bad").
+I3RC_HD void ray_after_steps(Lane& L) {
+  if (L.done == DONE_STOP) {
+    const float t = fmaf(L.sp, L.e, L.tau);
+    if ((L.mk & 8) && !(t > L.tauLimit)) {
+      L.tau = t;
+      L.done = L.stz > 0 ? DONE_TOP : DONE_BOTTOM;
+    } else {
+      L.done = DONE_INSIDE;
+    }
   }
-  L.tau += dtau;
-  // branch-free face crossing: every lane runs the same instructions whichever face(s) it crosses
-  const bool cx = L.rx <= s, cy = L.ry <= s, cz = L.rz <= s;
-  int ix = L.ix + (cx ? ((L.sgn & 1) ? 1 : -1) : 0);
-  int iy = L.iy + (cy ? ((L.sgn & 2) ? 1 : -1) : 0);
-  const int iz = L.iz + (cz ? ((L.sgn & 4) ? 1 : -1) : 0);
-  ix = ix >= p.nx ? 0 : (ix < 0 ? p.nx - 1 : ix);  // periodic in x and y (MCRT:1774-1788)
-  iy = iy >= p.ny ? 0 : (iy < 0 ? p.ny - 1 : iy);
-  L.ix = ix;
-  L.iy = iy;
-  L.iz = iz;
-  L.rx = cx ? ray_dt(p, L.iax, p.xe, p.xyRegular, p.dx, ix) : L.rx - s;
-  L.ry = cy ? ray_dt(p, L.iay, p.ye, p.xyRegular, p.dy, iy) : L.ry - s;
-  if ((unsigned)iz >= (unsigned)p.nz) {  // MCRT:1793-1804
-    L.done = iz < 0 ? DONE_BOTTOM : DONE_TOP;
-    L.rz -= s;
-    return;
-  }
-  L.rz = cz ? ray_dt(p, L.iaz, p.ze, p.zRegular, p.dz, iz) : L.rz - s;
-  L.idx = (iz * p.ny + iy) * p.nx + ix;
-  L.e = I3RC_LDG(p.ext + L.idx);
-  if (L.nsteps > MAX_RAY_STEPS) L.done = DONE_BAD;
+  if (L.done == DONE_RUN && L.nsteps > MAX_RAY_STEPS) L.done = DONE_BAD;
+}
+
+// The ray stopped with DONE_INSIDE: take the geometry back to the entry of the pending cell and move it to the
+// point where the target optical path is reached (MCRT:1721-1731).  Afterwards the geometry is no longer ahead:
+// L.e is the extinction of the cell it is in, and ray_restart() puts a ray that goes on back into step.
+template <class P>
+I3RC_HD void ray_stop_inside(const P& p, Lane& L) {
+  const int m = L.mk;
+  const float spd = I3RC_FDIV(L.tauLimit - L.tau, L.e);
+  L.rx = ((m & 1) ? L.sp : L.rx + L.sp) - spd;
+  L.ry = ((m & 2) ? L.sp : L.ry + L.sp) - spd;
+  L.rz = ((m & 4) ? L.sp : L.rz + L.sp) - spd;
+  if (m & 1) L.cntx = L.cntx == p.nx ? 1 : L.cntx + 1;
+  if (m & 2) L.cnty = L.cnty == p.ny ? 1 : L.cnty + 1;
+  if (m & 4) L.cntz += 1;
+  L.mk = 0;
+  L.tau = L.tauLimit;
+}
+template <class P>
+I3RC_HD void ray_restart(const P& p, Lane& L) {
+  L.idx = (ray_iz(p, L) * p.ny + ray_iy(p, L)) * p.nx + ray_ix(p, L);
+  ray_begin(p, L, L.e);
 }
 
 // offset inside the current cell of the ray's current point, per axis (keeps f where the ray does not move)
 template <class P>
 I3RC_HD void ray_local(const P& p, const Lane& L, float* fx, float* fy, float* fz) {
   if (!isinf(L.iax)) {
-    float rem = I3RC_FDIV(L.rx, ray_dt(p, L.iax, p.xe, p.xyRegular, p.dx, L.ix));
+    float rem = I3RC_FDIV(L.rx, ray_dt(p, L.iax, p.xe, p.xyRegular, p.dx, ray_ix(p, L)));
     rem = fminf(fmaxf(rem, 0.0f), 1.0f);
-    *fx = (L.sgn & 1) ? 1.0f - rem : rem;
+    *fx = L.stx > 0 ? 1.0f - rem : rem;
   }
   if (!isinf(L.iay)) {
-    float rem = I3RC_FDIV(L.ry, ray_dt(p, L.iay, p.ye, p.xyRegular, p.dy, L.iy));
+    float rem = I3RC_FDIV(L.ry, ray_dt(p, L.iay, p.ye, p.xyRegular, p.dy, ray_iy(p, L)));
     rem = fminf(fmaxf(rem, 0.0f), 1.0f);
-    *fy = (L.sgn & 2) ? 1.0f - rem : rem;
+    *fy = L.sty > 0 ? 1.0f - rem : rem;
   }
-  if (L.iz >= 0 && L.iz < p.nz && !isinf(L.iaz)) {
-    float rem = I3RC_FDIV(L.rz, ray_dt(p, L.iaz, p.ze, p.zRegular, p.dz, L.iz));
+  if (L.cntz != 0 && !isinf(L.iaz)) {
+    float rem = I3RC_FDIV(L.rz, ray_dt(p, L.iaz, p.ze, p.zRegular, p.dz, ray_iz(p, L)));
     rem = fminf(fmaxf(rem, 0.0f), 1.0f);
-    *fz = (L.sgn & 4) ? 1.0f - rem : rem;
+    *fz = L.stz > 0 ? 1.0f - rem : rem;
   }
 }
 
@@ -396,9 +480,9 @@ I3RC_HD void max_cross_section_flight(const P& p, Lane& L, float xiFirst) {
       float back = fabsf((z - p.zmax) / L.uz);
       x -= L.ux * back;
       y -= L.uy * back;
-      locate_abs(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, p.dx, x, 1, &L.ix, &L.fx);
-      locate_abs(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, p.dy, y, 1, &L.iy, &L.fy);
-      L.iz = p.nz;
+      locate_abs(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, p.dx, x, 1, &L.cx, &L.fx);
+      locate_abs(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, p.dy, y, 1, &L.cy, &L.fy);
+      L.cz = p.nz;
       L.done = DONE_TOP;
       return;
     }
@@ -406,19 +490,18 @@ I3RC_HD void max_cross_section_flight(const P& p, Lane& L, float xiFirst) {
       float back = fabsf((z - p.z0) / L.uz);
       x -= L.ux * back;
       y -= L.uy * back;
-      locate_abs(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, p.dx, x, 1, &L.ix, &L.fx);
-      locate_abs(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, p.dy, y, 1, &L.iy, &L.fy);
-      L.iz = -1;
+      locate_abs(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, p.dx, x, 1, &L.cx, &L.fx);
+      locate_abs(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, p.dy, y, 1, &L.cy, &L.fy);
+      L.cz = -1;
       L.done = DONE_BOTTOM;
       return;
     }
     x = x - floorf((x - p.x0) / Lx) * Lx;
     y = y - floorf((y - p.y0) / Ly) * Ly;
-    locate_abs(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, p.dx, x, 0, &L.ix, &L.fx);
-    locate_abs(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, p.dy, y, 0, &L.iy, &L.fy);
-    locate_abs(p.ze, p.zRegular, p.nz, p.z0, p.zmax, p.dz, z, 0, &L.iz, &L.fz);
-    L.idx = (L.iz * p.ny + L.iy) * p.nx + L.ix;
-    float e = I3RC_LDG(p.ext + L.idx);
+    locate_abs(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, p.dx, x, 0, &L.cx, &L.fx);
+    locate_abs(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, p.dy, y, 0, &L.cy, &L.fy);
+    locate_abs(p.ze, p.zRegular, p.nz, p.z0, p.zmax, p.dz, z, 0, &L.cz, &L.fz);
+    float e = I3RC_LDG(p.ext + (L.cz * p.ny + L.cy) * p.nx + L.cx);
     if (xiAcc < e / p.maxExt) {
       L.done = DONE_INSIDE;
       return;
@@ -436,16 +519,14 @@ I3RC_HD void start_segment(const P& p, Lane& L, float xiTau) {
     start_ray(p, L, L.ux, L.uy, L.uz, inv_abs(L.ux), inv_abs(L.uy), inv_abs(L.uz), tau_of(xiTau));
   } else {
     L.nsteps = 0;
-    L.iax = L.iay = L.iaz = INFINITY;  // ray_local keeps the offsets set by the flight
-    L.rx = L.ry = L.rz = INFINITY;
-    L.sgn = 0;
     max_cross_section_flight(p, L, xiTau);
   }
 }
 
-// Draw a photon from the source descriptor (Code/monteCarloIllumination.f95:62-424) and start it (MCRT:453-470).
+// Draw a photon from the source descriptor (Code/monteCarloIllumination.f95:62-424) and place it (MCRT:453-470).
+// Returns the deviate of its first optical path.
 template <class P>
-I3RC_HD void init_photon(const P& p, Lane& L, long long id) {
+I3RC_HD float init_photon_state(const P& p, Lane& L, long long id) {
   const SourceDev& s = p.src;
   L.rng.init((uint64_t)(p.firstPhoton + id));
   float r0, r1, r2, r3;  // the photon's first block: position, direction, first optical path (as far as it reaches)
@@ -545,6 +626,11 @@ I3RC_HD void init_photon(const P& p, Lane& L, long long id) {
   L.order = 0;
   L.active = 1;
   I3RC_COUNT(L, CNT_PHOTONS, 1);
+  return xiTau;
+}
+template <class P>
+I3RC_HD void init_photon(const P& p, Lane& L, long long id) {
+  const float xiTau = init_photon_state(p, L, id);
   start_segment(p, L, xiTau);
 }
 
@@ -646,7 +732,7 @@ I3RC_HD void tally_intensity(const P& p, Lane& L, float c) {
     c = p.maxContrib;
   }
   if (c != 0.0f) {
-    int col = L.iy * p.nx + L.ix;
+    int col = ray_iy(p, L) * p.nx + ray_ix(p, L);
     size_t ncol = (size_t)p.nx * p.ny;
     I3RC_ATOMIC_ADD(p.intensity + (size_t)L.td * ncol + col, c);
     if (!P::kFast && p.trackByComponent) I3RC_ATOMIC_ADD(p.intByComp + ((size_t)L.tcomp * p.nDir + L.td) * ncol + col, c);
@@ -660,8 +746,7 @@ template <class P>
 I3RC_HD int finish_le_ray(const P& p, Lane& L) {
   int done = L.done;
   L.done = DONE_RUN;
-  I3RC_COUNT(L, CNT_CROSS_LE, L.nsteps);
-  L.nsteps = 0;
+  L.nsteps = 0;  // (the caller has counted the crossings)
   float c = 0.0f;
   if (done != DONE_BAD) {
     switch (L.mode) {
@@ -672,9 +757,11 @@ I3RC_HD int finish_le_ray(const P& p, Lane& L) {
         if (done == DONE_TOP) {
           c = L.tcw * I3RC_EXP(-L.tau);
         } else if (done == DONE_INSIDE) {
+          ray_stop_inside(p, L);
           L.mode = MODE_LE_BIG2;
           L.tau = 0.0f;
           L.tauLimit = L.ttauFree;
+          ray_restart(p, L);
           return 1;
         }
         break;
@@ -692,12 +779,14 @@ template <class P>
 I3RC_HD void segment_finished(const P& p, Lane& L) {
   L.segDone = L.done;
   L.done = DONE_RUN;
-  I3RC_COUNT(L, CNT_CROSS_PH, L.nsteps);
-  L.nsteps = 0;
-  ray_local(p, L, &L.fx, &L.fy, &L.fz);
-  L.cx = L.ix;
-  L.cy = L.iy;
-  L.cz = L.iz;
+  L.nsteps = 0;  // (the caller has counted the crossings)
+  if (P::kFast || p.useRayTracing) {  // (the maximum cross-section flight has written the event point itself)
+    if (L.segDone == DONE_INSIDE) ray_stop_inside(p, L);
+    ray_local(p, L, &L.fx, &L.fy, &L.fz);
+    L.cx = ray_ix(p, L);
+    L.cy = ray_iy(p, L);
+    L.cz = ray_iz(p, L);
+  }
 }
 
 // The photon is finished: its slot can be refilled.  The number of random deviates it consumed is counted here.
@@ -772,11 +861,11 @@ I3RC_HD int photon_event(const P& p, Lane& L, float xi0, float xi1) {
   return 1;
 }
 
-// After the local estimate (or directly, when no intensity is wanted): roulette, scattering, next segment
-// (MCRT:670-688); for a surface event just continue with the reflected direction.  xiRoulette, xiAngle, xiTau:
-// deviates of the event's block.
+// After the local estimate (or directly, when no intensity is wanted): roulette and scattering (MCRT:670-688); a
+// surface event just keeps its reflected direction.  xiRoulette, xiAngle: deviates of the event's block.  The photon
+// may die here (L.active = 0).
 template <class P>
-I3RC_HD void continue_photon(const P& p, Lane& L, float xiRoulette, float xiAngle, float xiTau) {
+I3RC_HD void scatter_photon(const P& p, Lane& L, float xiRoulette, float xiAngle) {
   if (L.comp >= 1) {
     if (p.useRussianRoulette && L.w < p.rouletteW * 0.5f) {  // MCRT:673-679
       if (xiRoulette * p.rouletteW >= L.w) {
@@ -794,7 +883,12 @@ I3RC_HD void continue_photon(const P& p, Lane& L, float xiRoulette, float xiAngl
     float theta = scattering_angle(T.inv + (size_t)L.pfi * T.nInv, T.nInv, xiAngle);
     next_direct(p, L, I3RC_COS(theta));
   }
-  start_segment(p, L, xiTau);
+}
+// ... and the start of the next path segment (xiTau: deviate of its optical path)
+template <class P>
+I3RC_HD void continue_photon(const P& p, Lane& L, float xiRoulette, float xiAngle, float xiTau) {
+  scatter_photon(p, L, xiRoulette, xiAngle);
+  if (L.active) start_segment(p, L, xiTau);
 }
 
 // ---- per-lane scheduler (one lane owns the photon AND traces its local-estimate rays one after the other).
@@ -822,6 +916,7 @@ I3RC_HD void advance_le(const P& p, Lane& L) {
 
 template <class P>
 I3RC_HD void handle_event(const P& p, Lane& L) {
+  I3RC_COUNT(L, L.mode == MODE_PHOTON ? CNT_CROSS_PH : CNT_CROSS_LE, L.nsteps);
   if (L.mode == MODE_PHOTON) {
     segment_finished(p, L);
     float xi0;

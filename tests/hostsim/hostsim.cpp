@@ -123,7 +123,7 @@ static void run_lanes(const HostSimArgs* a, const Problem& p0) {
     L.active = 0; L.done = DONE_RUN; L.mode = MODE_PHOTON;
     init_photon(p, L, id);
     while (L.active) {
-      if (L.done == DONE_RUN) dda_step(p, L);
+      if (L.done == DONE_RUN) { dda_step(p, L); ray_after_steps(L); }
       else handle_event(p, L);
     }
   }
@@ -159,15 +159,17 @@ int hostsim_trace_rays(const HostSimArgs* a, int n, const float* pos, const floa
     locate_abs(p.ze, p.zRegular, p.nz, p.z0, p.zmax, p.dz, pos[3 * r + 2], 0, &L.cz, &L.fz);
     float dx = dir[3 * r], dy = dir[3 * r + 1], dz = dir[3 * r + 2];
     start_ray(p, L, dx, dy, dz, inv_abs(dx), inv_abs(dy), inv_abs(dz), tauLimit ? tauLimit[r] : INFINITY);
-    while (L.done == DONE_RUN) dda_step(p, L);
+    while (L.done == DONE_RUN) { dda_step(p, L); ray_after_steps(L); }
+    if (L.done == DONE_INSIDE) ray_stop_inside(p, L);
     tauOut[r] = L.done == DONE_BAD ? -2.0f : L.tau;
     ray_local(p, L, &L.fx, &L.fy, &L.fz);
+    const int ix = ray_ix(p, L), iy = ray_iy(p, L), iz = ray_iz(p, L);
     if (posOut) {
-      posOut[3 * r] = abs_x(p, L.ix, L.fx);
-      posOut[3 * r + 1] = abs_y(p, L.iy, L.fy);
-      posOut[3 * r + 2] = L.done == DONE_TOP ? p.zmax : (L.done == DONE_BOTTOM ? p.z0 : abs_z(p, L.iz, L.fz));
+      posOut[3 * r] = abs_x(p, ix, L.fx);
+      posOut[3 * r + 1] = abs_y(p, iy, L.fy);
+      posOut[3 * r + 2] = L.done == DONE_TOP ? p.zmax : (L.done == DONE_BOTTOM ? p.z0 : abs_z(p, iz, L.fz));
     }
-    if (idxOut) { idxOut[3 * r] = L.ix + 1; idxOut[3 * r + 1] = L.iy + 1; idxOut[3 * r + 2] = L.iz + 1; }
+    if (idxOut) { idxOut[3 * r] = ix + 1; idxOut[3 * r + 1] = iy + 1; idxOut[3 * r + 2] = iz + 1; }
   }
   return 0;
 }

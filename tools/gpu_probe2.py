@@ -40,6 +40,6 @@ if __name__ == "__main__":
     for wl in wls:
         nph = 2_000_000 if wl != "les" else 500_000
         for tune in ({"resident_blocks": 6}, {"resident_blocks": 6, "steps_per_event_phase": 6}, {"resident_blocks": 6, "steps_per_event_phase": 4},
-                     {"resident_blocks": 7}, {"resident_blocks": 5}, {"resident_blocks": 8}, {"resident_blocks": 7, "steps_per_event_phase": 6},
-                     {"event_threshold": 20}, {"event_threshold": 12}):
+                     {"resident_blocks": 5}, {"resident_blocks": 5, "steps_per_event_phase": 4}, {"resident_blocks": 4}, {"resident_blocks": 4, "steps_per_event_phase": 4},
+                     {"event_threshold": 8}, {"event_threshold": 24}, {"event_threshold": 30}):
             run(wl, nph, 2, tune)
