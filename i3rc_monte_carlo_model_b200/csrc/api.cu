@@ -104,7 +104,7 @@ struct i3rc_integrator {
   double traceMs = 0.0;
   long long traceLaunches = 0, otherLaunches = 0;
   // tuning
-  int blockSize = 128, blocksPerSM = 0, residentBlocks = 6, kSteps = 8, eventThreshold = 16;
+  int blockSize = 128, blocksPerSM = 0, residentBlocks = 5, poolShape = 0, kSteps = 8, eventThreshold = 16;
   // nccl
   void* nccl = nullptr;
   void* ncclLib = nullptr;
@@ -467,29 +467,33 @@ int launch_transport_t(i3rc_integrator* h, const Problem& p) {
 // MINB = resident blocks per SM the kernel is compiled for (register cap 65536 / (MINB * BLOCK));
 // STEPS = DDA crossings per bookkeeping round.  The tuning grid exists for the common configuration only (regular
 // grid + the FAST feature set, see ProblemT); everything else runs the general kernel at its default shape.
-template <int MINB, int NSLOT>
+template <int MINB, int NSLOT, int QCAP>
 int launch_transport_fast(i3rc_integrator* h, const Problem& p) {
   const int steps = h->kSteps <= 4 ? 4 : (h->kSteps <= 6 ? 6 : 8);
-  return steps == 4   ? launch_transport_t<128, true, true, MINB, 4, NSLOT, 128>(h, p)
-         : steps == 6 ? launch_transport_t<128, true, true, MINB, 6, NSLOT, 128>(h, p)
-                      : launch_transport_t<128, true, true, MINB, 8, NSLOT, 128>(h, p);
+  return steps == 4   ? launch_transport_t<128, true, true, MINB, 4, NSLOT, QCAP>(h, p)
+         : steps == 6 ? launch_transport_t<128, true, true, MINB, 6, NSLOT, QCAP>(h, p)
+                      : launch_transport_t<128, true, true, MINB, 8, NSLOT, QCAP>(h, p);
 }
 int launch_transport(i3rc_integrator* h, const Problem& p) {
   const bool reg = p.xyRegular && p.zRegular;
   const bool fast = p.useRayTracing && p.src.kind != 5 && p.src.kind != 6 && !p.useSurfaceBDRF && !p.useHybrid && !p.limitContrib &&
                     !p.trackByComponent;
   if (reg && fast) {
-    switch (h->residentBlocks) {
-      case 5:
-        return launch_transport_fast<5, 96>(h, p);
-      case 4:
-        return launch_transport_fast<4, 96>(h, p);
-      default:
-        return launch_transport_fast<6, 64>(h, p);
+    switch (h->residentBlocks * 10 + h->poolShape) {  // (blocks per SM, photon slots and ring entries per warp)
+      case 60:
+        return launch_transport_fast<6, 64, 64>(h, p);
+      case 40:
+        return launch_transport_fast<4, 64, 64>(h, p);
+      case 51:
+        return launch_transport_fast<5, 96, 128>(h, p);
+      case 52:
+        return launch_transport_fast<5, 48, 64>(h, p);
+      default:  // the shared-memory footprint is kept small on purpose: what is left of the 256 KB is L1 for the gathers
+        return launch_transport_fast<5, 64, 64>(h, p);
     }
   }
-  if (reg) return launch_transport_t<128, true, false, 6, 8, 64, 128>(h, p);
-  return fast ? launch_transport_t<128, false, true, 6, 8, 64, 128>(h, p) : launch_transport_t<128, false, false, 6, 8, 64, 128>(h, p);
+  if (reg) return launch_transport_t<128, true, false, 5, 8, 64, 64>(h, p);
+  return fast ? launch_transport_t<128, false, true, 5, 8, 64, 64>(h, p) : launch_transport_t<128, false, false, 5, 8, 64, 64>(h, p);
 }
 
 // zero tallies, trace one batch, post-process (MCRT:296-395); no host synchronisation
@@ -1184,6 +1188,7 @@ int i3rc_copy_Integrator(const i3rc_integrator* s, i3rc_integrator** out) {
   h->kSteps = s->kSteps;
   h->eventThreshold = s->eventThreshold;
   h->residentBlocks = s->residentBlocks;
+  h->poolShape = s->poolShape;
   h->message.clear();
   *out = h;
   return I3RC_SUCCESS;
@@ -1464,6 +1469,8 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->kSteps = value;
   else if (k == "resident_blocks" && value >= 4 && value <= 8)
     h->residentBlocks = value;
+  else if (k == "pool_shape" && value >= 0 && value <= 3)
+    h->poolShape = value;
   else if (k == "event_threshold" && value >= 1 && value <= 32)
     h->eventThreshold = value;
   else if (k == "track_by_component")

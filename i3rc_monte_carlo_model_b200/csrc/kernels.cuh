@@ -10,7 +10,7 @@ namespace i3rc {
 // ---- K1: persistent, warp-cooperative photon transport ---------------------------------------------------------
 // grid = (#SMs x resident blocks).  Lanes are NOT tied to photons.  Every warp owns, in shared memory,
 //   * a pool of NSLOT photon slots (position, direction, weight, Philox counter: 52 bytes each),
-//   * a ring of QCAP ray TASKS (36 bytes each): a photon's next path segment, or one local-estimate ray,
+//   * a ring of QCAP ray TASKS (40 bytes each): a photon's next path segment, or one local-estimate ray,
 //   * the list of slots whose path segment has ended and whose event (boundary / collision) is due,
 // and alternates, as a warp-uniform state machine, between
 //   TRACE rounds:  STEPS cell crossings for every lane that holds a ray; then, for all lanes at once, finished rays are
@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
       E.active = 0;
       E.comp = 0;
       E.pfi = 0;
+      E.eCell = 0.0f;
       float a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;  // deviates of the event's block still to be used
       float c2 = 0.0f, c3 = 0.0f;             // second half of the block shared by two local-estimate directions
       if (has) {
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
         c3 = __uint_as_float(sv[4 * 32]);
         E.comp = (int)(sv[5 * 32] >> 16);
         E.pfi = (int)(sv[5 * 32] & 0xffffu);
+        if (has && E.active) E.eCell = __ldg(p.ext + (E.cz * p.ny + E.cy) * p.nx + E.cx);
       }
       if (stage == 1) {  // local-estimate tasks, one direction at a time (MCRT:1473-1569)
         while (dcur < p.nDir && QCAP - (tail - head) >= 32) {
@@ -182,6 +184,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
             const long long id = (long long)base + __popc(mn & lt);
             if (id < p.src.n) {
               xiTau = init_photon_state(p, E, id);
+              E.eCell = __ldg(p.ext + (E.cz * p.ny + E.cy) * p.nx + E.cx);
               pool.id[eslot] = (uint32_t)id;
               go = true;
             }
@@ -201,6 +204,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
           t.cw = __int_as_float(eslot);
           t.cfix = 0.0f;
           t.tauFree = xiTau;
+          t.e0 = E.eCell;
           q[(tail + __popc(mg & lt)) & (QCAP - 1)] = t;
           pool.fx[eslot] = E.fx;
           pool.fy[eslot] = E.fy;
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
         const float ux = pool.ux[slot], uy = pool.uy[slot], uz = pool.uz[slot];
         if (FAST || p.useRayTracing) {
           start_ray_at(p, R, (int)(t.xy & 0xffffu), (int)(t.xy >> 16), (int)(t.zdmc & 0xffffu), t.fx, t.fy, t.fz, ux, uy,
-                       uz, inv_abs(ux), inv_abs(uy), inv_abs(uz), t.tauLimit);
+                       uz, inv_abs(ux), inv_abs(uy), inv_abs(uz), t.tauLimit, t.e0);
         } else {  // maximum cross-section: the whole flight at once; its end is handled by the next round
           R.cx = (int)(t.xy & 0xffffu);
           R.cy = (int)(t.xy >> 16);

@@ -145,6 +145,7 @@ struct Lane {
   int order;
   int mode;        // what the current ray is: MODE_PHOTON (own path segment) or a local-estimate stage
   int comp, pfi;   // photon: component (0 = surface) and phase-function entry of the last event
+  float eCell;     // photon: extinction of the cell of the event point
   int d;           // photon: next local-estimate direction to generate (per-lane scheduler only)
   float ev1, ev2, ev3, le2, le3;  // deviates of the current event kept between its stages (per-lane scheduler only)
   // local-estimate ray being traced (may belong to ANOTHER photon of the warp in the warp-cooperative kernel)
@@ -318,10 +319,11 @@ I3RC_HD void ray_begin(const P& p, Lane& L, float eCell) {
   if (!ray_advance(p, L)) L.e1 = I3RC_LDG(p.ext + L.idx);
 }
 
-// Start a ray in cell (ix,iy,iz) at offset (fx,fy,fz) inside it along direction (dx,dy,dz); ia* = 1/|cosine|.
+// Start a ray in cell (ix,iy,iz) at offset (fx,fy,fz) inside it along direction (dx,dy,dz); ia* = 1/|cosine|;
+// eCell = extinction of that cell (the caller has gathered it, ideally long before).
 template <class P>
 I3RC_HD void start_ray_at(const P& p, Lane& L, int ix, int iy, int iz, float fx, float fy, float fz, float dx, float dy,
-                          float dz, float iax, float iay, float iaz, float tauLimit) {
+                          float dz, float iax, float iay, float iaz, float tauLimit, float eCell) {
   const bool px = dx >= 0.0f, py = dy >= 0.0f, pz = dz >= 0.0f;
   const int sy = p.nx, sz = p.nx * p.ny;
   L.idx = iz * sz + iy * sy + ix;
@@ -346,14 +348,15 @@ I3RC_HD void start_ray_at(const P& p, Lane& L, int ix, int iy, int iz, float fx,
   L.tauLimit = tauLimit;
   L.nsteps = 0;
   L.done = DONE_RUN;
-  ray_begin(p, L, I3RC_LDG(p.ext + L.idx));
+  ray_begin(p, L, eCell);
 }
 
 // Start a ray at the event point (cx,cy,cz ; fx,fy,fz) of the lane along direction (dx,dy,dz).
 template <class P>
 I3RC_HD void start_ray(const P& p, Lane& L, float dx, float dy, float dz, float iax, float iay, float iaz,
                        float tauLimit) {
-  start_ray_at(p, L, L.cx, L.cy, L.cz, L.fx, L.fy, L.fz, dx, dy, dz, iax, iay, iaz, tauLimit);
+  start_ray_at(p, L, L.cx, L.cy, L.cz, L.fx, L.fy, L.fz, dx, dy, dz, iax, iay, iaz, tauLimit,
+               I3RC_LDG(p.ext + (L.cz * p.ny + L.cy) * p.nx + L.cx));
 }
 
 // ONE cell crossing (the body of accumulateExtinctionAlongPath's loop, MCRT:1690-1806), software-pipelined.
@@ -653,7 +656,7 @@ I3RC_HD float surface_reflectance(const Problem& p, float x, float y) {
   return I3RC_LDG(p.surf_albedo + j * p.surf_nx + i);
 }
 
-// One local-estimate ray as a self-contained task (36 bytes): origin, direction index, stage, and the two possible
+// One local-estimate ray as a self-contained task (40 bytes): origin, direction index, stage, and the two possible
 // contribution values, so that ANY lane of the warp can trace it (warp-cooperative kernel) .
 struct LeTask {
   uint32_t xy;    // ix | iy << 16
@@ -663,6 +666,7 @@ struct LeTask {
   float cw;       // weight * normalised phase function      (contribution = cw * exp(-tau), MCRT:1530,1574)
   float cfix;     // weight * zetaMin / pi                    (Iwabuchi roulette survivors, MCRT:1556,1584)
   float tauFree;  // second-stage optical path (MCRT:1576-1578)
+  float e0;       // extinction of the origin cell (gathered when the task was made, so the ray can start at once)
 };
 
 // Build the local-estimate task towards direction d from the lane's event point (MCRT:1473-1510, 1540-1569); xiTau and
@@ -707,6 +711,7 @@ I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, L
   t.cw = L.w * phat;
   t.cfix = L.w * p.zetaMin * (1.0f / F_PI);
   t.tauFree = tauFree;
+  t.e0 = L.eCell;
   return 1;
 }
 
@@ -722,7 +727,7 @@ I3RC_HD void start_le_task(const P& p, Lane& L, const LeTask& t) {
   L.tcfix = t.cfix;
   L.ttauFree = t.tauFree;
   start_ray_at(p, L, (int)(t.xy & 0xffff), (int)(t.xy >> 16), (int)(t.zdmc & 0xffff), t.fx, t.fy, t.fz, I3RC_LDG(dv + 0),
-               I3RC_LDG(dv + 1), I3RC_LDG(dv + 2), I3RC_LDG(dv + 3), I3RC_LDG(dv + 4), I3RC_LDG(dv + 5), t.tauLimit);
+               I3RC_LDG(dv + 1), I3RC_LDG(dv + 2), I3RC_LDG(dv + 3), I3RC_LDG(dv + 4), I3RC_LDG(dv + 5), t.tauLimit, t.e0);
 }
 
 template <class P>
@@ -836,11 +841,13 @@ I3RC_HD int photon_event(const P& p, Lane& L, float xi0, float xi1) {
     make_direction(mu, phi, &L.ux, &L.uy, &L.uz);
     L.comp = 0;
     L.pfi = 0;
+    L.eCell = I3RC_LDG(p.ext + L.cy * p.nx + L.cx);
   } else {  // collision, MCRT:581-668
     L.order++;
     I3RC_COUNT(L, CNT_COLL, 1);
     const size_t ncell = (size_t)p.nx * p.ny * p.nz;
     const size_t cell = ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx;
+    L.eCell = I3RC_LDG(p.ext + cell);  // for the rays that start here (local estimates, next segment)
     int comp = 1;
     if (p.nc > 1) {  // findIndex(xi, (/0, cumulativeExt(:)/)), MCRT:637-638
       const float xi = xi0;
