@@ -61,6 +61,7 @@ struct i3rc_integrator {
   std::vector<float> xe, ye, ze;
   float *d_xe = nullptr, *d_ye = nullptr, *d_ze = nullptr;
   float *d_ext = nullptr, *d_cum = nullptr, *d_ssa = nullptr;
+  float* d_extZ = nullptr;  // totalExt again, z-fastest: the copy the rays gather from (see Problem::ext)
   int* d_pf = nullptr;
   float maxExt = 0.0f;
   bool useSurfaceBDRF = false;
@@ -221,6 +222,13 @@ int finish_new_integrator(i3rc_integrator* h) {
   k_bump_and_max<<<(unsigned)((ncell + 255) / 256), 256, 0, h->stream>>>(ncell, h->d_cum + (size_t)(h->nc - 1) * ncell,
                                                                         h->d_ext, d_max);
   h->otherLaunches++;
+  dfree(h->d_extZ);
+  CUDA_OK(h, cudaMalloc(&h->d_extZ, sizeof(float) * ncell));
+  {
+    dim3 b(32, 8), g((unsigned)((nx + 31) / 32), (unsigned)((nz + 31) / 32), (unsigned)ny);
+    k_transpose_zfast<<<g, b, 0, h->stream>>>(nx, ny, nz, h->d_ext, h->d_extZ);
+    h->otherLaunches++;
+  }
   unsigned int bits = 0;
   CUDA_OK(h, cudaMemcpyAsync(&bits, d_max, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
@@ -329,7 +337,10 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
   p.xe = h->d_xe;
   p.ye = h->d_ye;
   p.ze = h->d_ze;
-  p.ext = h->d_ext;
+  p.ext = h->d_extZ;
+  p.esx = h->ny * h->nz;
+  p.esy = h->nz;
+  p.esz = 1;
   p.cumExt = h->d_cum;
   p.ssa = h->d_ssa;
   p.pfIdx = h->d_pf;
@@ -832,6 +843,7 @@ void i3rc_finalize_Integrator(i3rc_integrator* h) {
   dfree(h->d_ye);
   dfree(h->d_ze);
   dfree(h->d_ext);
+  dfree(h->d_extZ);
   dfree(h->d_cum);
   dfree(h->d_ssa);
   dfree(h->d_pf);

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
         c3 = __uint_as_float(sv[4 * 32]);
         E.comp = (int)(sv[5 * 32] >> 16);
         E.pfi = (int)(sv[5 * 32] & 0xffffu);
-        if (has && E.active) E.eCell = __ldg(p.ext + (E.cz * p.ny + E.cy) * p.nx + E.cx);
+        if (has && E.active) E.eCell = __ldg(p.ext + ext_index(p, E.cx, E.cy, E.cz));
       }
       if (stage == 1) {  // local-estimate tasks, one direction at a time (MCRT:1473-1569)
         while (dcur < p.nDir && QCAP - (tail - head) >= 32) {
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
             const long long id = (long long)base + __popc(mn & lt);
             if (id < p.src.n) {
               xiTau = init_photon_state(p, E, id);
-              E.eCell = __ldg(p.ext + (E.cz * p.ny + E.cy) * p.nx + E.cx);
+              E.eCell = __ldg(p.ext + ext_index(p, E.cx, E.cy, E.cz));
               pool.id[eslot] = (uint32_t)id;
               go = true;
             }
@@ -443,6 +443,22 @@ __global__ void k_bump_and_max(size_t ncell, float* __restrict__ lastCum, const 
   }
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(maxBits, __float_as_uint(m));
+}
+
+// totalExt[z][y][x] -> z-fastest copy out[x][y][z] (tiled through shared memory; one x-z plane per blockIdx.z)
+__global__ void k_transpose_zfast(int nx, int ny, int nz, const float* __restrict__ in, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int iy = blockIdx.z;
+  const int x0 = blockIdx.x * 32, z0 = blockIdx.y * 32;
+  for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+    const int ix = x0 + threadIdx.x, iz = z0 + k;
+    if (ix < nx && iz < nz) tile[k][threadIdx.x] = in[((size_t)iz * ny + iy) * nx + ix];
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+    const int ix = x0 + k, iz = z0 + threadIdx.x;
+    if (ix < nx && iz < nz) out[((size_t)ix * ny + iy) * nz + iz] = tile[threadIdx.x][k];
+  }
 }
 
 // ---- post-processing of one batch (MCRT:327-395) -------------------------------------------------------------

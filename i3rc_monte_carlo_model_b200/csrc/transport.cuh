@@ -86,7 +86,13 @@ struct Problem {
   float x0, y0, z0, xmax, ymax, zmax;
   float dx, dy, dz;
   const float *xe, *ye, *ze;
+  // Total extinction, the one field the rays gather from, with element strides (esx, esy, esz): cell (ix,iy,iz) is
+  // ext[ix*esx + iy*esy + iz*esz].  The library keeps it z-fastest (esz = 1): most crossings of a ray are through
+  // horizontal faces (layers are thinner than columns are wide, and solar / viewing directions are steep), so
+  // consecutive gathers of a ray then fall into the same 32-byte sector far more often than with the x-fastest order
+  // of the other fields.
   const float* ext;
+  int esx, esy, esz;
   const float* cumExt;
   const float* ssa;
   const int* pfIdx;
@@ -117,6 +123,8 @@ struct ProblemT : Problem {
   static constexpr bool kRegular = REG;
   static constexpr bool kFast = FAST;
 };
+
+I3RC_HD int ext_index(const Problem& p, int ix, int iy, int iz) { return ix * p.esx + iy * p.esy + iz * p.esz; }
 
 struct Lane {
   // current ray (regular or irregular grid): linear cell index, signed index strides per axis, and the number of
@@ -325,11 +333,10 @@ template <class P>
 I3RC_HD void start_ray_at(const P& p, Lane& L, int ix, int iy, int iz, float fx, float fy, float fz, float dx, float dy,
                           float dz, float iax, float iay, float iaz, float tauLimit, float eCell) {
   const bool px = dx >= 0.0f, py = dy >= 0.0f, pz = dz >= 0.0f;
-  const int sy = p.nx, sz = p.nx * p.ny;
-  L.idx = iz * sz + iy * sy + ix;
-  L.stx = px ? 1 : -1;
-  L.sty = py ? sy : -sy;
-  L.stz = pz ? sz : -sz;
+  L.idx = ext_index(p, ix, iy, iz);
+  L.stx = px ? p.esx : -p.esx;
+  L.sty = py ? p.esy : -p.esy;
+  L.stz = pz ? p.esz : -p.esz;
   L.cntx = px ? p.nx - ix : ix + 1;
   L.cnty = py ? p.ny - iy : iy + 1;
   L.cntz = pz ? p.nz - iz : iz + 1;
@@ -356,7 +363,7 @@ template <class P>
 I3RC_HD void start_ray(const P& p, Lane& L, float dx, float dy, float dz, float iax, float iay, float iaz,
                        float tauLimit) {
   start_ray_at(p, L, L.cx, L.cy, L.cz, L.fx, L.fy, L.fz, dx, dy, dz, iax, iay, iaz, tauLimit,
-               I3RC_LDG(p.ext + (L.cz * p.ny + L.cy) * p.nx + L.cx));
+               I3RC_LDG(p.ext + ext_index(p, L.cx, L.cy, L.cz)));
 }
 
 // ONE cell crossing (the body of accumulateExtinctionAlongPath's loop, MCRT:1690-1806), software-pipelined.
@@ -425,7 +432,7 @@ I3RC_HD void ray_stop_inside(const P& p, Lane& L) {
 }
 template <class P>
 I3RC_HD void ray_restart(const P& p, Lane& L) {
-  L.idx = (ray_iz(p, L) * p.ny + ray_iy(p, L)) * p.nx + ray_ix(p, L);
+  L.idx = ext_index(p, ray_ix(p, L), ray_iy(p, L), ray_iz(p, L));
   ray_begin(p, L, L.e);
 }
 
@@ -504,7 +511,7 @@ I3RC_HD void max_cross_section_flight(const P& p, Lane& L, float xiFirst) {
     locate_abs(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, p.dx, x, 0, &L.cx, &L.fx);
     locate_abs(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, p.dy, y, 0, &L.cy, &L.fy);
     locate_abs(p.ze, p.zRegular, p.nz, p.z0, p.zmax, p.dz, z, 0, &L.cz, &L.fz);
-    float e = I3RC_LDG(p.ext + (L.cz * p.ny + L.cy) * p.nx + L.cx);
+    float e = I3RC_LDG(p.ext + ext_index(p, L.cx, L.cy, L.cz));
     if (xiAcc < e / p.maxExt) {
       L.done = DONE_INSIDE;
       return;
@@ -841,13 +848,13 @@ I3RC_HD int photon_event(const P& p, Lane& L, float xi0, float xi1) {
     make_direction(mu, phi, &L.ux, &L.uy, &L.uz);
     L.comp = 0;
     L.pfi = 0;
-    L.eCell = I3RC_LDG(p.ext + L.cy * p.nx + L.cx);
+    L.eCell = I3RC_LDG(p.ext + ext_index(p, L.cx, L.cy, 0));
   } else {  // collision, MCRT:581-668
     L.order++;
     I3RC_COUNT(L, CNT_COLL, 1);
     const size_t ncell = (size_t)p.nx * p.ny * p.nz;
     const size_t cell = ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx;
-    L.eCell = I3RC_LDG(p.ext + cell);  // for the rays that start here (local estimates, next segment)
+    L.eCell = I3RC_LDG(p.ext + ext_index(p, L.cx, L.cy, L.cz));  // for the rays that start here (local estimates, next segment)
     int comp = 1;
     if (p.nc > 1) {  // findIndex(xi, (/0, cumulativeExt(:)/)), MCRT:637-638
       const float xi = xi0;

@@ -179,6 +179,15 @@ STAT_CASES = {
         maxIntensityContribution=0.5, useRussianRouletteForIntensity=False), dict(solarMu=0.6, solarAzimuth=20.0), 10000),
     "no-roulette-tabulated": (lambda: fields.plane_parallel(useMoments=False, SSA=0.9, nX=3, nY=2, nLayers=4), dict(
         surfaceAlbedo=0.5, useRussianRoulette=False), dict(solarMu=0.5, solarAzimuth=0.0), 4000),
+    # 16 directions: every event batch overfills the warp's task ring, so batches are suspended and resumed
+    "sixteen-directions-plain": (lambda: fields.step_cloud(0.99), dict(
+        surfaceAlbedo=0.2, intensityMus=[m for m in (1.0, 0.7, 0.4, -0.6) for _ in range(4)],
+        intensityPhis=[p for _ in range(4) for p in (0.0, 90.0, 180.0, 270.0)], useRussianRouletteForIntensity=False),
+        dict(solarMu=0.5, solarAzimuth=0.0), 6000),
+    "sixteen-directions-roulette": (lambda: fields.step_cloud(1.0), dict(
+        surfaceAlbedo=0.1, intensityMus=[m for m in (1.0, 0.8, 0.5, 0.3) for _ in range(4)],
+        intensityPhis=[p for _ in range(4) for p in (10.0, 100.0, 190.0, 280.0)], useRussianRouletteForIntensity=True,
+        zetaMin=0.5), dict(solarMu=0.8, solarAzimuth=40.0), 10000),
     "source-random-azimuth": (lambda: fields.step_cloud(0.99), dict(surfaceAlbedo=0.0), dict(solarMu=0.6), 3000),
     "source-flux": (lambda: fields.step_cloud(0.99), dict(surfaceAlbedo=0.0), dict(), 3000),
     "source-spotlight": (lambda: fields.step_cloud(0.99), dict(surfaceAlbedo=0.0),
