@@ -214,3 +214,132 @@ def read_namelists(path):
     n = sum(1 for v in rt["intensityMus"] if abs(v) > 0)  # numRadDir = count(abs(intensityMus) > 0), :151
     rt["intensityMus"], rt["intensityPhis"] = rt["intensityMus"][:n], (rt["intensityPhis"] + [0.0] * n)[:n]
     return out
+
+
+# ---- the whole program (Example-Drivers/monteCarloDriver.f95:137-419) ----------------------------------------------
+def monteCarloDriver(namelistFileName, backend=None, dist=None, verbose=True):
+    """What `monteCarloDriver namelist.nml` does, on the GPU: read the five namelists and the domain file, set the
+    integrator up exactly like the reference (:169-216), trace one photon to build the tables (:240-253), run this
+    rank's block of batches on the device (:264-326), sum the moments over ranks with ONE all-reduce (:333-348), and
+    have rank 0 write the ASCII / netCDF result files in the reference's formats (:382-419).  One process per GPU;
+    ``dist`` is an initialised torch.distributed (or None).  Returns name -> (mean, stderr) on every rank."""
+    import time
+
+    from . import fileIO
+    from ._lib import backend as cuda_backend
+    from .ErrorMessages import ErrorMessage, stateIsFailure, getCurrentMessage
+    from .monteCarloRadiativeTransfer import new_Integrator, specifyParameters
+
+    t0 = time.perf_counter()
+    rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    nml = read_namelists(namelistFileName)
+    cfg = {}
+    for g in nml.values():
+        cfg.update(g)
+    numRadDir = len(cfg["intensityMus"])
+    computeIntensity = numRadDir > 0 and bool(cfg["outputRadFile"] or cfg["outputNetcdfFile"])
+    if not computeIntensity:
+        cfg["outputRadFile"] = ""
+
+    status = ErrorMessage()
+
+    def check(what):  # printStatus: stop on failure (Code/userInterface_Unix.f95:21-54)
+        if stateIsFailure(status):
+            raise RuntimeError(f"{what}: {getCurrentMessage(status)}")
+
+    thisDomain = fileIO.read_Domain(cfg["domainFileName"], status)
+    check("read_Domain")
+    x, y, z = thisDomain.xPosition.copy(), thisDomain.yPosition.copy(), thisDomain.zPosition.copy()
+    I = new_Integrator(thisDomain, status=status, backend=backend or cuda_backend())
+    check("new_Integrator")
+    fileIO.finalize_Domain(thisDomain)
+    specifyParameters(I, surfaceAlbedo=cfg["surfaceAlbedo"], minInverseTableSize=cfg["nPhaseIntervals"], status=status)
+    check("specifyParameters")
+    if computeIntensity:
+        specifyParameters(I, minForwardTableSize=cfg["nPhaseIntervals"], intensityMus=cfg["intensityMus"],
+                          intensityPhis=cfg["intensityPhis"], computeIntensity=True, status=status)
+        check("specifyParameters")
+    specifyParameters(I, useRayTracing=cfg["useRayTracing"], useRussianRoulette=cfg["useRussianRoulette"], status=status)
+    check("specifyParameters")
+    if computeIntensity:
+        specifyParameters(I, useHybridPhaseFunsForIntenCalcs=cfg["useHybridPhaseFunsForIntenCalcs"],
+                          hybridPhaseFunWidth=cfg["hybridPhaseFunWidth"],
+                          numOrdersOrigPhaseFunIntenCalcs=cfg["numOrdersOrigPhaseFunIntenCalcs"],
+                          useRussianRouletteForIntensity=cfg["useRussianRouletteForIntensity"], zetaMin=cfg["zetaMin"],
+                          limitIntensityContributions=cfg["limitIntensityContributions"],
+                          maxIntensityContribution=cfg["maxIntensityContribution"], status=status)
+        check("specifyParameters")
+    source = dict(solarMu=cfg["solarMu"], solarAzimuth=cfg["solarAzimuth"])
+    # one photon with seed (/ iseed, 0 /): checks the set-up and builds the tables before the batches
+    ph = new_PhotonStream(numberOfPhotons=1, **source)
+    computeRadiativeTransfer(I, new_RandomNumberSequence([cfg["iseed"], 0]), ph, status=status)
+    check("computeRadiativeTransfer")
+    tSetup = time.perf_counter() - t0
+    numBatches, mine = partition_batches(cfg["numBatches"], world, rank)
+    cfg["numBatches"] = numBatches
+    if verbose and rank == 0:
+        print(f" Setup CPU time (secs, approx): {int(tSetup)}")
+        print(f" Doing {len(mine)} batches on each of {world} processors.")
+    withVolume = bool(cfg["reportVolumeAbsorption"] or cfg["outputAbsVolumeFile"])
+    if I.backend.stats_reset is not None:  # the product: the whole batch loop stays on the device
+        run_batches_device(I, source, cfg["numPhotonsPerBatch"], mine, iseed=cfg["iseed"], with_volume=withVolume)
+        allreduce_device_stats(I, dist)
+        stats = device_stats_report(I, cfg["solarFlux"], numBatches, with_volume=withVolume)
+    else:  # a backend without a device batch loop (the test-suite's checker): the reference's own host loop
+        want = (["meanFluxUp", "meanFluxDown", "meanFluxAbsorbed", "fluxUp", "fluxDown", "fluxAbsorbed", "absorbedProfile"]
+                + (["volumeAbsorption"] if withVolume else []) + (["intensity", "meanIntensity"] if computeIntensity else []))
+        hs = run_batches_host(I, source, cfg["numPhotonsPerBatch"], mine, iseed=cfg["iseed"], want=want)
+        hs.allreduce(dist)
+        names = {"intensity": "radiance", "meanIntensity": "meanRadiance", "volumeAbsorption": "absorbedVolume"}
+        stats = {names.get(k, k): v for k, v in hs.finish(cfg["solarFlux"], numBatches).items()}
+    tTotal = time.perf_counter() - t0
+    if rank == 0:
+        if verbose:
+            print(f" Total CPU time (secs, approx): {int(tTotal)}")
+        if any(cfg[k] for k in ("outputFluxFile", "outputAbsProfFile", "outputAbsVolumeFile", "outputRadFile")):
+            fileIO.writeResults_ASCII(cfg, x, y, z, stats)
+            if verbose:
+                print(" Wrote ASCII results")
+        if cfg["outputNetcdfFile"]:
+            out = dict(stats)
+            if not computeIntensity:
+                out.pop("radiance", None)
+            fileIO.writeResults_netcdf(cfg, x, y, z, out, cpuTimeTotal=tTotal, cpuTimeSetup=tSetup, numProcs=world)
+            if verbose:
+                print(" Wrote netcdf results")
+    return stats
+
+
+def main(argv=None):
+    """python -m i3rc_monte_carlo_model_b200.driver namelist.nml   (under torchrun: one rank per GPU)"""
+    import os
+    import sys
+    argv = sys.argv[1:] if argv is None else argv
+    if len(argv) != 1:
+        print("usage: python -m i3rc_monte_carlo_model_b200.driver <namelist file>", file=sys.stderr)
+        return 2
+    dist = None
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from ._lib import backend
+    be = backend()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if be.set_device(local) != 0:
+        print("monteCarloDriver: no CUDA device (the integrator has no CPU fallback)", file=sys.stderr)
+        return 1
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    try:
+        monteCarloDriver(argv[0], backend=be, dist=dist)
+    finally:
+        if dist is not None:
+            dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
