@@ -29,7 +29,7 @@ struct SlotPool {  // structure of arrays: lane i touches slot[k] of every array
   uint32_t xy[NSLOT];   // cx | cy << 16
   uint32_t zs[NSLOT];   // cz | segDone << 16
   float fx[NSLOT], fy[NSLOT], fz[NSLOT];
-  float ux[NSLOT], uy[NSLOT], uz[NSLOT];
+  float ux[NSLOT + MAX_DIRS], uy[NSLOT + MAX_DIRS], uz[NSLOT + MAX_DIRS];  // [NSLOT + d]: radiance direction d
   float w[NSLOT];
   int order[NSLOT];
   uint32_t id[NSLOT];     // photon number inside this launch
@@ -62,6 +62,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
     pool.zs[k] = (uint32_t)DONE_NEW << 16;
   }
   if (lane < CNT_N) s_cnt[warp][lane] = 0;
+  if (lane < p.nDir) {  // (at most MAX_DIRS = 32 directions)
+    pool.ux[NSLOT + lane] = __ldg(p.dirs + lane * DIR_STRIDE + 0);
+    pool.uy[NSLOT + lane] = __ldg(p.dirs + lane * DIR_STRIDE + 1);
+    pool.uz[NSLOT + lane] = __ldg(p.dirs + lane * DIR_STRIDE + 2);
+  }
   __syncwarp();
 
   Lane R;  // the ray this lane is tracing
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
       uint32_t* rv = s_ray[warp][0] + lane;  // what the ray is for waits in shared memory while it is traced
       if (R.mode == MODE_PHOTON) {
         const int done = R.done;
-        R.slot = (int)rv[0];
+        R.slot = (int)rv[1 * 32];
         I3RC_COUNT(R, CNT_CROSS_PH, R.nsteps);
         float fx = 0.0f, fy = 0.0f, fz = 0.0f;
         int cx, cy, cz;
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
         R.done = DONE_IDLE;
       } else {
         I3RC_COUNT(R, CNT_CROSS_LE, R.nsteps);
-        R.td = (int)(rv[0] & 0xffu);
+        R.td = (int)(rv[0] & 31u);
         R.tcomp = (int)(rv[0] >> 8);
         R.tcw = __uint_as_float(rv[1 * 32]);
         R.tcfix = __uint_as_float(rv[2 * 32]);
@@ -299,7 +304,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
       }
     }
     const unsigned ms = __ballot_sync(full, segEnd);
-    if (segEnd) pend[npend + __popc(ms & lt)] = (uint8_t)s_ray[warp][0][lane];
+    if (segEnd) pend[npend + __popc(ms & lt)] = (uint8_t)s_ray[warp][1][lane];
     npend += __popc(ms);
     // idle lanes take the next tasks
     const bool idle = R.done == DONE_IDLE;
@@ -307,38 +312,35 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
     const int avail = tail - head;
     const int rank = __popc(mi & lt);
     if (idle && rank < avail) {
+      // One path for both kinds of task: a path segment finds its direction in its photon slot, a local-estimate ray
+      // in the copy of the direction table behind the slots; what the ray is for is parked in shared memory.
       const LeTask t = q[(head + rank) & (QCAP - 1)];
       const int mode = (int)((t.zdmc >> 21) & 7u);
+      const int j = mode == MODE_PHOTON ? __float_as_int(t.cw) : NSLOT + (int)((t.zdmc >> 16) & 31u);
+      const float ux = pool.ux[j], uy = pool.uy[j], uz = pool.uz[j];
       uint32_t* rv = s_ray[warp][0] + lane;
-      if (mode == MODE_PHOTON) {
-        const int slot = __float_as_int(t.cw);
-        rv[0] = (uint32_t)slot;
-        R.mode = MODE_PHOTON;
-        const float ux = pool.ux[slot], uy = pool.uy[slot], uz = pool.uz[slot];
-        if (FAST || p.useRayTracing) {
-          start_ray_at(p, R, (int)(t.xy & 0xffffu), (int)(t.xy >> 16), (int)(t.zdmc & 0xffffu), t.fx, t.fy, t.fz, ux, uy,
-                       uz, inv_abs(ux), inv_abs(uy), inv_abs(uz), t.tauLimit, t.e0);
-        } else {  // maximum cross-section: the whole flight at once; its end is handled by the next round
-          R.cx = (int)(t.xy & 0xffffu);
-          R.cy = (int)(t.xy >> 16);
-          R.cz = (int)(t.zdmc & 0xffffu);
-          R.fx = t.fx;
-          R.fy = t.fy;
-          R.fz = t.fz;
-          R.ux = ux;
-          R.uy = uy;
-          R.uz = uz;
-          R.rng.init((uint64_t)(p.firstPhoton + (long long)pool.id[slot]));
-          R.rng.block = pool.block[slot];
-          R.nsteps = 0;
-          max_cross_section_flight(p, R, t.tauFree);
-        }
-      } else {
-        start_le_task(p, R, t);
-        rv[0] = (uint32_t)R.td | ((uint32_t)R.tcomp << 8);
-        rv[1 * 32] = __float_as_uint(R.tcw);
-        rv[2 * 32] = __float_as_uint(R.tcfix);
-        rv[3 * 32] = __float_as_uint(R.ttauFree);
+      rv[0] = t.zdmc >> 16;  // d | mode << 5 | comp << 8
+      rv[1 * 32] = __float_as_uint(t.cw);  // (a path segment: the slot number)
+      rv[2 * 32] = __float_as_uint(t.cfix);
+      rv[3 * 32] = __float_as_uint(t.tauFree);
+      R.mode = mode;
+      if (FAST || p.useRayTracing || mode != MODE_PHOTON) {
+        start_ray_at(p, R, (int)(t.xy & 0xffffu), (int)(t.xy >> 16), (int)(t.zdmc & 0xffffu), t.fx, t.fy, t.fz, ux, uy, uz,
+                     inv_abs(ux), inv_abs(uy), inv_abs(uz), t.tauLimit, t.e0);
+      } else {  // maximum cross-section: the whole flight at once; its end is handled by the next round
+        R.cx = (int)(t.xy & 0xffffu);
+        R.cy = (int)(t.xy >> 16);
+        R.cz = (int)(t.zdmc & 0xffffu);
+        R.fx = t.fx;
+        R.fy = t.fy;
+        R.fz = t.fz;
+        R.ux = ux;
+        R.uy = uy;
+        R.uz = uz;
+        R.rng.init((uint64_t)(p.firstPhoton + (long long)pool.id[j]));
+        R.rng.block = pool.block[j];
+        R.nsteps = 0;
+        max_cross_section_flight(p, R, t.tauFree);
       }
     }
     head += min(__popc(mi), avail);
