@@ -105,7 +105,7 @@ struct i3rc_integrator {
   double traceMs = 0.0;
   long long traceLaunches = 0, otherLaunches = 0;
   // tuning
-  int blockSize = 128, blocksPerSM = 0, residentBlocks = 5, poolShape = 0, kSteps = 8, eventThreshold = 16;
+  int blockSize = 128, blocksPerSM = 0, residentBlocks = 5, poolShape = 0, minRunning = 16, kSteps = 16, eventThreshold = 16;
   // nccl
   void* nccl = nullptr;
   void* ncclLib = nullptr;
@@ -472,7 +472,7 @@ int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   if (grid < 1) grid = 1;
   ProblemT<REG, FAST> pt;
   static_cast<Problem&>(pt) = p;
-  k_transport<BLOCK, REG, FAST, MINB, STEPS, NSLOT, QCAP><<<(unsigned)grid, BLOCK, 0, h->stream>>>(pt, h->eventThreshold);
+  k_transport<BLOCK, REG, FAST, MINB, STEPS, NSLOT, QCAP><<<(unsigned)grid, BLOCK, 0, h->stream>>>(pt, h->eventThreshold, h->minRunning);
   return I3RC_SUCCESS;
 }
 // MINB = resident blocks per SM the kernel is compiled for (register cap 65536 / (MINB * BLOCK));
@@ -480,10 +480,10 @@ int launch_transport_t(i3rc_integrator* h, const Problem& p) {
 // grid + the FAST feature set, see ProblemT); everything else runs the general kernel at its default shape.
 template <int MINB, int NSLOT, int QCAP>
 int launch_transport_fast(i3rc_integrator* h, const Problem& p) {
-  const int steps = h->kSteps <= 4 ? 4 : (h->kSteps <= 6 ? 6 : 8);
-  return steps == 4   ? launch_transport_t<128, true, true, MINB, 4, NSLOT, QCAP>(h, p)
-         : steps == 6 ? launch_transport_t<128, true, true, MINB, 6, NSLOT, QCAP>(h, p)
-                      : launch_transport_t<128, true, true, MINB, 8, NSLOT, QCAP>(h, p);
+  const int steps = h->kSteps <= 8 ? 8 : (h->kSteps <= 16 ? 16 : 32);
+  return steps == 8    ? launch_transport_t<128, true, true, MINB, 8, NSLOT, QCAP>(h, p)
+         : steps == 16 ? launch_transport_t<128, true, true, MINB, 16, NSLOT, QCAP>(h, p)
+                       : launch_transport_t<128, true, true, MINB, 32, NSLOT, QCAP>(h, p);
 }
 int launch_transport(i3rc_integrator* h, const Problem& p) {
   const bool reg = p.xyRegular && p.zRegular;
@@ -495,16 +495,14 @@ int launch_transport(i3rc_integrator* h, const Problem& p) {
         return launch_transport_fast<6, 64, 64>(h, p);
       case 40:
         return launch_transport_fast<4, 64, 64>(h, p);
-      case 51:
-        return launch_transport_fast<5, 96, 128>(h, p);
       case 52:
         return launch_transport_fast<5, 48, 64>(h, p);
       default:  // the shared-memory footprint is kept small on purpose: what is left of the 256 KB is L1 for the gathers
         return launch_transport_fast<5, 64, 64>(h, p);
     }
   }
-  if (reg) return launch_transport_t<128, true, false, 5, 8, 64, 64>(h, p);
-  return fast ? launch_transport_t<128, false, true, 5, 8, 64, 64>(h, p) : launch_transport_t<128, false, false, 5, 8, 64, 64>(h, p);
+  if (reg) return launch_transport_t<128, true, false, 5, 16, 64, 64>(h, p);
+  return fast ? launch_transport_t<128, false, true, 5, 16, 64, 64>(h, p) : launch_transport_t<128, false, false, 5, 16, 64, 64>(h, p);
 }
 
 // zero tallies, trace one batch, post-process (MCRT:296-395); no host synchronisation
@@ -1201,6 +1199,7 @@ int i3rc_copy_Integrator(const i3rc_integrator* s, i3rc_integrator** out) {
   h->eventThreshold = s->eventThreshold;
   h->residentBlocks = s->residentBlocks;
   h->poolShape = s->poolShape;
+  h->minRunning = s->minRunning;
   h->message.clear();
   *out = h;
   return I3RC_SUCCESS;
@@ -1481,6 +1480,8 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->kSteps = value;
   else if (k == "resident_blocks" && value >= 4 && value <= 8)
     h->residentBlocks = value;
+  else if (k == "min_running" && value >= 0 && value <= 32)
+    h->minRunning = value;
   else if (k == "pool_shape" && value >= 0 && value <= 3)
     h->poolShape = value;
   else if (k == "event_threshold" && value >= 1 && value <= 32)

@@ -34,10 +34,16 @@ struct SlotPool {  // structure of arrays: lane i touches slot[k] of every array
   int order[NSLOT];
   uint32_t id[NSLOT];     // photon number inside this launch
   uint32_t block[NSLOT];  // Philox blocks consumed so far
+  // A path segment that has ended leaves its ray here as it is (zs bit 24): fx/fy/fz = path lengths left to the next
+  // faces, xy/zs = the per-axis cell counters + how it ended + the faces last crossed, sp/spd = length of the pending
+  // cell and the distance into it at which the segment ends.  The event batch turns that into the event point, with
+  // all its lanes, instead of the one or two lanes that close a segment in any given trace round.
+  float sp[NSLOT], spd[NSLOT];
 };
+constexpr uint32_t SLOT_RAW = 1u << 24;
 
 template <int BLOCK, bool REG, bool FAST, int MINB, int STEPS, int NSLOT, int QCAP>
-__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, FAST> p, const int lowWater) {
+__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, FAST> p, const int lowWater, const int minRunning) {
   constexpr int NW = BLOCK / 32;
   static_assert((QCAP & (QCAP - 1)) == 0 && QCAP >= 64, "ring size: power of two, room for one push of 32");
   static_assert(NSLOT >= 32 && NSLOT <= 255, "slot ids are bytes");
@@ -117,18 +123,41 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
       float c2 = 0.0f, c3 = 0.0f;             // second half of the block shared by two local-estimate directions
       if (has) {
         const uint32_t zs = pool.zs[eslot];
-        E.segDone = (int)(zs >> 16);
+        E.segDone = (int)((zs >> 16) & 15u);
         if (E.segDone != DONE_NEW) {
           const uint32_t xy = pool.xy[eslot];
-          E.cx = (int)(xy & 0xffffu);
-          E.cy = (int)(xy >> 16);
-          E.cz = (int)(int16_t)(zs & 0xffffu);
           E.fx = pool.fx[eslot];
           E.fy = pool.fy[eslot];
           E.fz = pool.fz[eslot];
           E.ux = pool.ux[eslot];
           E.uy = pool.uy[eslot];
           E.uz = pool.uz[eslot];
+          if (zs & SLOT_RAW) {  // the segment's ray as it stopped -> the event point (MCRT:1721-1731, 1793-1804)
+            Lane T;
+            T.stx = E.ux >= 0.0f ? 1 : -1;  // (only the signs matter here)
+            T.sty = E.uy >= 0.0f ? 1 : -1;
+            T.stz = E.uz >= 0.0f ? 1 : -1;
+            T.iax = inv_abs(E.ux) * (REG ? p.dx : 1.0f);
+            T.iay = inv_abs(E.uy) * (REG ? p.dy : 1.0f);
+            T.iaz = inv_abs(E.uz) * (REG ? p.dz : 1.0f);
+            T.rx = E.fx;
+            T.ry = E.fy;
+            T.rz = E.fz;
+            T.cntx = (int)(xy & 0xffffu);
+            T.cnty = (int)(xy >> 16);
+            T.cntz = (int)(zs & 0xffffu);
+            T.sp = pool.sp[eslot];
+            T.mk = (int)((zs >> 20) & 7u);
+            ray_undo_to(p, T, pool.spd[eslot]);
+            ray_local(p, T, &E.fx, &E.fy, &E.fz);
+            E.cx = ray_ix(p, T);
+            E.cy = ray_iy(p, T);
+            E.cz = ray_iz(p, T);
+          } else {
+            E.cx = (int)(xy & 0xffffu);
+            E.cy = (int)(xy >> 16);
+            E.cz = (int)(int16_t)(zs & 0xffffu);
+          }
           E.w = pool.w[eslot];
           E.order = pool.order[eslot];
           E.rng.init((uint64_t)(p.firstPhoton + (long long)pool.id[eslot]));
@@ -252,10 +281,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
 
     // ================= TRACE round =================
     // (pairs of steps: the two extinction registers of a ray swap roles on every step, see dda_step)
+    // The round ends after STEPS crossings, or earlier when fewer than minRunning lanes still have a running ray: then
+    // enough lanes wait for the (divergent, per-ray) bookkeeping below to make it worth its price.
 #pragma unroll 1
     for (int k = 0; k < STEPS / 2; k++) {
       if (R.done == DONE_RUN) dda_step<0>(p, R);
       if (R.done == DONE_RUN) dda_step<1>(p, R);
+      if (__popc(__ballot_sync(full, R.done == DONE_RUN)) < minRunning) break;
     }
     ray_after_steps(R);
     // close finished rays
@@ -266,31 +298,23 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
         const int done = R.done;
         R.slot = (int)rv[1 * 32];
         I3RC_COUNT(R, CNT_CROSS_PH, R.nsteps);
-        float fx = 0.0f, fy = 0.0f, fz = 0.0f;
-        int cx, cy, cz;
         if (FAST || p.useRayTracing) {
-          if (done == DONE_INSIDE) ray_stop_inside(p, R);
-          fx = pool.fx[R.slot];  // offsets stay where the ray does not move along an axis
-          fy = pool.fy[R.slot];
-          fz = pool.fz[R.slot];
-          ray_local(p, R, &fx, &fy, &fz);
-          cx = ray_ix(p, R);
-          cy = ray_iy(p, R);
-          cz = ray_iz(p, R);
+          const bool inside = done == DONE_INSIDE;
+          if (!isinf(R.iax)) pool.fx[R.slot] = R.rx;  // (an axis the ray does not move along keeps its offset)
+          if (!isinf(R.iay)) pool.fy[R.slot] = R.ry;
+          if (!isinf(R.iaz)) pool.fz[R.slot] = R.rz;
+          pool.xy[R.slot] = (uint32_t)R.cntx | ((uint32_t)R.cnty << 16);
+          pool.zs[R.slot] = (uint32_t)R.cntz | ((uint32_t)done << 16) | ((uint32_t)(inside ? R.mk & 7 : 0) << 20) | SLOT_RAW;
+          pool.sp[R.slot] = inside ? R.sp : 0.0f;
+          pool.spd[R.slot] = inside ? ray_stop_offset(R) : 0.0f;
         } else {  // maximum cross-section flight: the event point is already in the photon registers
-          fx = R.fx;
-          fy = R.fy;
-          fz = R.fz;
-          cx = R.cx;
-          cy = R.cy;
-          cz = R.cz;
+          pool.fx[R.slot] = R.fx;
+          pool.fy[R.slot] = R.fy;
+          pool.fz[R.slot] = R.fz;
+          pool.xy[R.slot] = (uint32_t)R.cx | ((uint32_t)R.cy << 16);
+          pool.zs[R.slot] = ((uint32_t)R.cz & 0xffffu) | ((uint32_t)done << 16);
           pool.block[R.slot] = R.rng.block;
         }
-        pool.fx[R.slot] = fx;
-        pool.fy[R.slot] = fy;
-        pool.fz[R.slot] = fz;
-        pool.xy[R.slot] = (uint32_t)cx | ((uint32_t)cy << 16);
-        pool.zs[R.slot] = ((uint32_t)cz & 0xffffu) | ((uint32_t)done << 16);
         segEnd = true;
         R.done = DONE_IDLE;
       } else {

@@ -418,9 +418,8 @@ I3RC_HD void ray_after_steps(Lane& L) {
 // point where the target optical path is reached (MCRT:1721-1731).  Afterwards the geometry is no longer ahead:
 // L.e is the extinction of the cell it is in, and ray_restart() puts a ray that goes on back into step.
 template <class P>
-I3RC_HD void ray_stop_inside(const P& p, Lane& L) {
+I3RC_HD void ray_undo_to(const P& p, Lane& L, float spd) {  // spd: path length from the entry of the pending cell
   const int m = L.mk;
-  const float spd = I3RC_FDIV(L.tauLimit - L.tau, L.e);
   L.rx = ((m & 1) ? L.sp : L.rx + L.sp) - spd;
   L.ry = ((m & 2) ? L.sp : L.ry + L.sp) - spd;
   L.rz = ((m & 4) ? L.sp : L.rz + L.sp) - spd;
@@ -428,6 +427,11 @@ I3RC_HD void ray_stop_inside(const P& p, Lane& L) {
   if (m & 2) L.cnty = L.cnty == p.ny ? 1 : L.cnty + 1;
   if (m & 4) L.cntz += 1;
   L.mk = 0;
+}
+I3RC_HD float ray_stop_offset(const Lane& L) { return I3RC_FDIV(L.tauLimit - L.tau, L.e); }
+template <class P>
+I3RC_HD void ray_stop_inside(const P& p, Lane& L) {
+  ray_undo_to(p, L, ray_stop_offset(L));
   L.tau = L.tauLimit;
 }
 template <class P>
