@@ -105,7 +105,7 @@ struct i3rc_integrator {
   double traceMs = 0.0;
   long long traceLaunches = 0, otherLaunches = 0;
   // tuning
-  int blockSize = 128, blocksPerSM = 0, residentBlocks = 5, poolShape = 0, minRunning = 16, kSteps = 16, eventThreshold = 16;
+  int blockSize = 128, blocksPerSM = 0, residentBlocks = 0, poolShape = 0, minRunning = 16, kSteps = 16, eventThreshold = 16;
   // nccl
   void* nccl = nullptr;
   void* ncclLib = nullptr;
@@ -490,7 +490,11 @@ int launch_transport(i3rc_integrator* h, const Problem& p) {
   const bool fast = p.useRayTracing && p.src.kind != 5 && p.src.kind != 6 && !p.useSurfaceBDRF && !p.useHybrid && !p.limitContrib &&
                     !p.trackByComponent;
   if (reg && fast) {
-    switch (h->residentBlocks * 10 + h->poolShape) {  // (blocks per SM, photon slots and ring entries per warp)
+    // resident blocks per SM, 0 = automatic: 6 while the extinction field is L2-resident; 5 (more of the 256 KB left as
+    // L1) when the gathers go to HBM
+    const size_t ncell = (size_t)p.nx * p.ny * p.nz;
+    const int blocks = h->residentBlocks ? h->residentBlocks : (ncell * sizeof(float) <= (size_t)48 << 20 ? 6 : 5);
+    switch (blocks * 10 + h->poolShape) {  // (blocks per SM, photon slots and ring entries per warp)
       case 60:
         return launch_transport_fast<6, 64, 64>(h, p);
       case 40:
@@ -1478,7 +1482,7 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->blocksPerSM = value;
   else if (k == "steps_per_event_phase" && value >= 1)
     h->kSteps = value;
-  else if (k == "resident_blocks" && value >= 4 && value <= 8)
+  else if (k == "resident_blocks" && (value == 0 || (value >= 4 && value <= 6)))
     h->residentBlocks = value;
   else if (k == "min_running" && value >= 0 && value <= 32)
     h->minRunning = value;

@@ -35,7 +35,7 @@ struct SlotPool {  // structure of arrays: lane i touches slot[k] of every array
   uint32_t id[NSLOT];     // photon number inside this launch
   uint32_t block[NSLOT];  // Philox blocks consumed so far
   // A path segment that has ended leaves its ray here as it is (zs bit 24): fx/fy/fz = path lengths left to the next
-  // faces, xy/zs = the per-axis cell counters + how it ended + the faces last crossed, sp/spd = length of the pending
+  // faces (signed, see Lane), xy/zs = the per-axis cell counters + how it ended, sp/spd = length of the pending
   // cell and the distance into it at which the segment ends.  The event batch turns that into the event point, with
   // all its lanes, instead of the one or two lanes that close a segment in any given trace round.
   float sp[NSLOT], spd[NSLOT];
@@ -147,8 +147,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
             T.cnty = (int)(xy >> 16);
             T.cntz = (int)(zs & 0xffffu);
             T.sp = pool.sp[eslot];
-            T.mk = (int)((zs >> 20) & 7u);
-            ray_undo_to(p, T, pool.spd[eslot]);
+            if (E.segDone == DONE_INSIDE) ray_undo_to(p, T, pool.spd[eslot]);
             ray_local(p, T, &E.fx, &E.fy, &E.fz);
             E.cx = ray_ix(p, T);
             E.cy = ray_iy(p, T);
@@ -304,9 +303,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
           if (!isinf(R.iay)) pool.fy[R.slot] = R.ry;
           if (!isinf(R.iaz)) pool.fz[R.slot] = R.rz;
           pool.xy[R.slot] = (uint32_t)R.cntx | ((uint32_t)R.cnty << 16);
-          pool.zs[R.slot] = (uint32_t)R.cntz | ((uint32_t)done << 16) | ((uint32_t)(inside ? R.mk & 7 : 0) << 20) | SLOT_RAW;
-          pool.sp[R.slot] = inside ? R.sp : 0.0f;
-          pool.spd[R.slot] = inside ? ray_stop_offset(R) : 0.0f;
+          pool.zs[R.slot] = (uint32_t)R.cntz | ((uint32_t)done << 16) | SLOT_RAW;
+          if (inside) {
+            pool.sp[R.slot] = R.sp;
+            pool.spd[R.slot] = ray_stop_offset(R);
+          }
         } else {  // maximum cross-section flight: the event point is already in the photon registers
           pool.fx[R.slot] = R.fx;
           pool.fy[R.slot] = R.fy;

@@ -132,14 +132,15 @@ struct Lane {
   int idx;
   int stx, sty, stz;
   int cntx, cnty, cntz;
-  float rx, ry, rz, tau, tauLimit;  // path length left to the next x/y/z cell face; optical path so far / target
+  float rx, ry, rz, tau, tauLimit;  // |r|: path length left to the next x/y/z cell face; optical path so far / target
   // The geometry (idx, cnt*, r*) runs ONE CELL AHEAD of the optical path: the cell whose optical path is still to be
-  // added ("pending") has path length sp; mk = faces crossed when the geometry left it (1, 2, 4 = x, y, z; 8 = that
-  // crossing left the domain).  The extinctions of the pending cell and of the cell the geometry is in live in
-  // e0 / e1, which swap roles on every step (dda_step<PAR>), so that a gather is issued a whole step before its value
-  // is needed and no register move ever waits for it.  e = extinction of the pending cell of a ray that has stopped.
+  // added ("pending") has path length sp.  The SIGN of rx / ry / rz records whether that face was crossed when the
+  // geometry left the pending cell (negative: crossed, |r| = full path length of the new cell), which is what is
+  // needed to step back when the ray turns out to end inside the pending cell; cntz == 0 says the crossing left the
+  // domain.  The extinctions of the pending cell and of the cell the geometry is in live in e0 / e1, which swap
+  // roles on every step (dda_step<PAR>), so that a gather is issued a whole step before its value is needed and no
+  // register move ever waits for it.  e = extinction of the pending cell of a ray that has stopped.
   float sp, e0, e1, e;
-  int mk;
   int par;  // which of e0 / e1 holds the pending cell (run-time copy for callers that step one lane at a time)
   float iax, iay, iaz;  // kRegular: path length per cell along the ray (cell width / |direction cosine|); else 1/|cosine|
   int done;
@@ -300,22 +301,26 @@ I3RC_HD int ray_iz(const P& p, const Lane& L) { return L.stz > 0 ? p.nz - L.cntz
 // domain (no next cell to gather).  Face crossing with selects, not branches: a warp's lanes cross different faces.
 template <class P>
 I3RC_HD bool ray_advance(const P& p, Lane& L) {
-  const float s = fminf(L.rx, fminf(L.ry, L.rz));
-  const bool cx = L.rx <= s, cy = L.ry <= s, cz = L.rz <= s;
-  const int nx_ = L.cntx - (cx ? 1 : 0), ny_ = L.cnty - (cy ? 1 : 0), nz_ = L.cntz - (cz ? 1 : 0);
+  const float ax = fabsf(L.rx), ay = fabsf(L.ry), az = fabsf(L.rz);
+  const float s = fminf(ax, fminf(ay, az));
+  const bool cx = ax <= s, cy = ay <= s, cz = az <= s;
+  int nx_ = L.cntx, ny_ = L.cnty, nz_ = L.cntz, idx = L.idx;
+  if (cx) nx_--, idx += L.stx;
+  if (cy) ny_--, idx += L.sty;
+  if (cz) nz_--, idx += L.stz;
   const bool wx = nx_ == 0, wy = ny_ == 0, out = nz_ == 0;  // periodic in x and y (MCRT:1774-1788); z: MCRT:1793-1804
-  int idx = L.idx + (cx ? L.stx : 0) + (cy ? L.sty : 0) + (cz ? L.stz : 0);
-  idx -= (wx ? L.stx * p.nx : 0) + (wy ? L.sty * p.ny : 0);
+  if (wx) idx -= L.stx * p.nx, nx_ = p.nx;
+  if (wy) idx -= L.sty * p.ny, ny_ = p.ny;
   L.idx = idx;
-  L.cntx = wx ? p.nx : nx_;
-  L.cnty = wy ? p.ny : ny_;
+  L.cntx = nx_;
+  L.cnty = ny_;
   L.cntz = nz_;
-  const float qx = L.rx - s, qy = L.ry - s, qz = L.rz - s;
-  L.rx = cx ? ray_dt(p, L.iax, p.xe, p.xyRegular, p.dx, ray_ix(p, L)) : qx;
-  L.ry = cy ? ray_dt(p, L.iay, p.ye, p.xyRegular, p.dy, ray_iy(p, L)) : qy;
-  L.rz = (cz && (P::kRegular || !out)) ? ray_dt(p, L.iaz, p.ze, p.zRegular, p.dz, ray_iz(p, L)) : qz;
+  const float qx = ax - s, qy = ay - s, qz = az - s;
+  L.rx = cx ? -ray_dt(p, L.iax, p.xe, p.xyRegular, p.dx, ray_ix(p, L)) : qx;
+  L.ry = cy ? -ray_dt(p, L.iay, p.ye, p.xyRegular, p.dy, ray_iy(p, L)) : qy;
+  // (outside the domain there is no cell width to look up: any negative value records the crossing)
+  L.rz = cz ? ((P::kRegular || !out) ? -ray_dt(p, L.iaz, p.ze, p.zRegular, p.dz, ray_iz(p, L)) : -1.0f) : qz;
   L.sp = s;
-  L.mk = (cx ? 1 : 0) | (cy ? 2 : 0) | (cz ? 4 : 0) | (out ? 8 : 0);
   return out;
 }
 // (Re)start the pipeline from the cell the geometry is in, whose extinction is eCell: it becomes the pending cell
@@ -381,7 +386,7 @@ I3RC_HD void dda_step(const P& p, Lane& L) {
   float& ePending = PAR ? L.e1 : L.e0;
   const float t = fmaf(L.sp, ePending, L.tau);
   L.nsteps++;
-  if (t > L.tauLimit || (L.mk & 8)) {
+  if (t > L.tauLimit || L.cntz == 0) {
     L.e = ePending;
     L.done = DONE_STOP;
     return;
@@ -404,7 +409,7 @@ I3RC_HD void dda_step(const P& p, Lane& L) {
 I3RC_HD void ray_after_steps(Lane& L) {
   if (L.done == DONE_STOP) {
     const float t = fmaf(L.sp, L.e, L.tau);
-    if ((L.mk & 8) && !(t > L.tauLimit)) {
+    if (L.cntz == 0 && !(t > L.tauLimit)) {
       L.tau = t;
       L.done = L.stz > 0 ? DONE_TOP : DONE_BOTTOM;
     } else {
@@ -419,14 +424,13 @@ I3RC_HD void ray_after_steps(Lane& L) {
 // L.e is the extinction of the cell it is in, and ray_restart() puts a ray that goes on back into step.
 template <class P>
 I3RC_HD void ray_undo_to(const P& p, Lane& L, float spd) {  // spd: path length from the entry of the pending cell
-  const int m = L.mk;
-  L.rx = ((m & 1) ? L.sp : L.rx + L.sp) - spd;
-  L.ry = ((m & 2) ? L.sp : L.ry + L.sp) - spd;
-  L.rz = ((m & 4) ? L.sp : L.rz + L.sp) - spd;
-  if (m & 1) L.cntx = L.cntx == p.nx ? 1 : L.cntx + 1;
-  if (m & 2) L.cnty = L.cnty == p.ny ? 1 : L.cnty + 1;
-  if (m & 4) L.cntz += 1;
-  L.mk = 0;
+  const bool mx = L.rx < 0.0f, my = L.ry < 0.0f, mz = L.rz < 0.0f;  // faces crossed when leaving the pending cell
+  L.rx = (mx ? L.sp : L.rx + L.sp) - spd;
+  L.ry = (my ? L.sp : L.ry + L.sp) - spd;
+  L.rz = (mz ? L.sp : L.rz + L.sp) - spd;
+  if (mx) L.cntx = L.cntx == p.nx ? 1 : L.cntx + 1;
+  if (my) L.cnty = L.cnty == p.ny ? 1 : L.cnty + 1;
+  if (mz) L.cntz += 1;
 }
 I3RC_HD float ray_stop_offset(const Lane& L) { return I3RC_FDIV(L.tauLimit - L.tau, L.e); }
 template <class P>
@@ -444,17 +448,17 @@ I3RC_HD void ray_restart(const P& p, Lane& L) {
 template <class P>
 I3RC_HD void ray_local(const P& p, const Lane& L, float* fx, float* fy, float* fz) {
   if (!isinf(L.iax)) {
-    float rem = I3RC_FDIV(L.rx, ray_dt(p, L.iax, p.xe, p.xyRegular, p.dx, ray_ix(p, L)));
+    float rem = I3RC_FDIV(fabsf(L.rx), ray_dt(p, L.iax, p.xe, p.xyRegular, p.dx, ray_ix(p, L)));
     rem = fminf(fmaxf(rem, 0.0f), 1.0f);
     *fx = L.stx > 0 ? 1.0f - rem : rem;
   }
   if (!isinf(L.iay)) {
-    float rem = I3RC_FDIV(L.ry, ray_dt(p, L.iay, p.ye, p.xyRegular, p.dy, ray_iy(p, L)));
+    float rem = I3RC_FDIV(fabsf(L.ry), ray_dt(p, L.iay, p.ye, p.xyRegular, p.dy, ray_iy(p, L)));
     rem = fminf(fmaxf(rem, 0.0f), 1.0f);
     *fy = L.sty > 0 ? 1.0f - rem : rem;
   }
   if (L.cntz != 0 && !isinf(L.iaz)) {
-    float rem = I3RC_FDIV(L.rz, ray_dt(p, L.iaz, p.ze, p.zRegular, p.dz, ray_iz(p, L)));
+    float rem = I3RC_FDIV(fabsf(L.rz), ray_dt(p, L.iaz, p.ze, p.zRegular, p.dz, ray_iz(p, L)));
     rem = fminf(fmaxf(rem, 0.0f), 1.0f);
     *fz = L.stz > 0 ? 1.0f - rem : rem;
   }
