@@ -105,7 +105,7 @@ struct i3rc_integrator {
   double traceMs = 0.0;
   long long traceLaunches = 0, otherLaunches = 0;
   // tuning
-  int blockSize = 128, blocksPerSM = 0, residentBlocks = 0, poolShape = 0, minRunning = 16, kSteps = 16, eventThreshold = 16;
+  int blockSize = 128, blocksPerSM = 0, residentBlocks = 0, poolShape = 0, minRunning = 16, padSmem = 0, kSteps = 16, eventThreshold = 16;
   // nccl
   void* nccl = nullptr;
   void* ncclLib = nullptr;
@@ -475,7 +475,7 @@ int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   if (grid < 1) grid = 1;
   ProblemT<REG, FAST> pt;
   static_cast<Problem&>(pt) = p;
-  k_transport<BLOCK, REG, FAST, MINB, STEPS, NSLOT, QCAP><<<(unsigned)grid, BLOCK, 0, h->stream>>>(pt, h->eventThreshold, h->minRunning);
+  k_transport<BLOCK, REG, FAST, MINB, STEPS, NSLOT, QCAP><<<(unsigned)grid, BLOCK, (size_t)h->padSmem, h->stream>>>(pt, h->eventThreshold, h->minRunning);
   return I3RC_SUCCESS;
 }
 // MINB = resident blocks per SM the kernel is compiled for (register cap 65536 / (MINB * BLOCK));
@@ -1487,6 +1487,8 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->kSteps = value;
   else if (k == "resident_blocks" && (value == 0 || (value >= 4 && value <= 6)))
     h->residentBlocks = value;
+  else if (k == "pad_smem" && value >= 0 && value <= 16384)
+    h->padSmem = value;  // experiment: unused dynamic shared memory (shrinks the L1 share of the SM)
   else if (k == "min_running" && value >= 0 && value <= 32)
     h->minRunning = value;
   else if (k == "pool_shape" && value >= 0 && value <= 3)
