@@ -243,7 +243,7 @@ def _F(v, w, d):
 
 def _header(fh, title, cfg, out_type, radiance=False):
     fh.write(f"!   I3RC Monte Carlo 3D Solar Radiative Transfer: {title}\n")
-    fh.write("!  Property_File=" + f"{cfg['domainFileName'][:60]:>60s}" + "\n")
+    fh.write("!  Property_File=" + f"{cfg['domainFileName'][:60]:<60s}" + "\n")  # A60 of a blank-padded character(256)
     fh.write("!  Num_Photons=" + f"{cfg['numPhotonsPerBatch'] * cfg['numBatches']:10d}" + "\n")
     fh.write(f"!  PhotonTracing={_L(cfg['useRayTracing'])}    Russian_Roulette={_L(cfg['useRussianRoulette'])}\n")
     fh.write(f"!  Hybrid_Phase_Func_for_Radiance={_L(cfg['useHybridPhaseFunsForIntenCalcs'])}"

@@ -25,3 +25,11 @@ def cuda():
     be = backend()
     assert be.device_count() > 0, "no CUDA device visible"
     return be
+
+
+@pytest.fixture
+def cuda_absent():
+    """Skips the test on a box that has a GPU (it checks the behaviour without one)."""
+    from i3rc_monte_carlo_model_b200._lib import backend
+    if backend().device_count() > 0:
+        pytest.skip("a CUDA device is present")

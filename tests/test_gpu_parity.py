@@ -319,7 +319,7 @@ def test_properties_at_landsat_benchmark_size(cuda):
     assert np.allclose(again["fluxUp"][0], r["fluxUp"][0], rtol=2e-4, atol=1e-5)
     # ... independently of the launch shape (per-photon counter-based streams)
     I2 = copy_Integrator(I)
-    assert cuda.set_tuning(I2.handle, b"resident_blocks", 7) == 0 and cuda.set_tuning(I2.handle, b"steps_per_event_phase", 3) == 0
+    assert cuda.set_tuning(I2.handle, b"resident_blocks", 4) == 0 and cuda.set_tuning(I2.handle, b"steps_per_event_phase", 8) == 0 and cuda.set_tuning(I2.handle, b"min_running", 24) == 0
     other = run_batches(I2, nph, 1, want=["meanFluxUp", "fluxUp", "meanIntensity"])
     assert abs(other["meanFluxUp"][0] - r["meanFluxUp"][0]) < 2e-6
     assert np.allclose(other["meanIntensity"][0], r["meanIntensity"][0], rtol=1e-4)
