@@ -165,7 +165,7 @@ def cpu_port_rate(wl, seconds, threads=0, nbatches=None):
     return nph * nbatches / el, cores, f"{nbatches} batches x {nph} photons of the same workload", el
 
 
-def run_reference(args, wl):
+def run_reference(args, wl, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -190,7 +190,7 @@ def run_reference(args, wl):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -207,9 +207,17 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tune", default="", help="key=value,... passed to i3rc_set_tuning")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: anything libraries print there (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     wl = make_workload(args.workload)
     if args.impl == "reference":
-        return run_reference(args, wl)
+        return run_reference(args, wl, emit)
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -398,7 +406,7 @@ def main():
                     "meanRadiance": [[float(m), float(e)] for m, e in zip(np.ravel(stats["meanRadiance"][0]), np.ravel(stats["meanRadiance"][1]))]
                     if "meanRadiance" in stats else None},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
