@@ -284,8 +284,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
     // enough lanes wait for the (divergent, per-ray) bookkeeping below to make it worth its price.
 #pragma unroll 1
     for (int k = 0; k < STEPS / 2; k++) {
-      if (R.done == DONE_RUN) dda_step<0>(p, R);
-      if (R.done == DONE_RUN) dda_step<1>(p, R);
+      if (R.done == DONE_RUN) dda_step_pair(p, R);
       if (__popc(__ballot_sync(full, R.done == DONE_RUN)) < minRunning) break;
     }
     ray_after_steps(R);

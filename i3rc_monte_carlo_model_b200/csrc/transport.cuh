@@ -394,6 +394,29 @@ I3RC_HD void dda_step(const P& p, Lane& L) {
   L.tau = t;
   if (!ray_advance(p, L)) ePending = I3RC_LDG(p.ext + L.idx);  // (the register is free now: it becomes the look-ahead)
 }
+// Two crossings in a row, the form the kernel's trace round uses: the second step is nested in the first one's
+// "goes on" branch, so a running ray pays one test per step and nothing has to be re-examined in between.
+template <class P>
+I3RC_HD void dda_step_pair(const P& p, Lane& L) {
+  const float tA = fmaf(L.sp, L.e0, L.tau);
+  if (tA > L.tauLimit || L.cntz == 0) {
+    L.nsteps += 1;
+    L.e = L.e0;
+    L.done = DONE_STOP;
+    return;
+  }
+  L.tau = tA;
+  if (!ray_advance(p, L)) L.e0 = I3RC_LDG(p.ext + L.idx);
+  const float tB = fmaf(L.sp, L.e1, L.tau);
+  L.nsteps += 2;
+  if (tB > L.tauLimit || L.cntz == 0) {
+    L.e = L.e1;
+    L.done = DONE_STOP;
+    return;
+  }
+  L.tau = tB;
+  if (!ray_advance(p, L)) L.e1 = I3RC_LDG(p.ext + L.idx);
+}
 // one lane at a time (CPU harness, probes): the parity is kept in the lane
 template <class P>
 I3RC_HD void dda_step(const P& p, Lane& L) {
