@@ -62,6 +62,8 @@ struct i3rc_integrator {
   float *d_xe = nullptr, *d_ye = nullptr, *d_ze = nullptr;
   float *d_ext = nullptr, *d_cum = nullptr, *d_ssa = nullptr;
   float* d_extZ = nullptr;  // totalExt again, z-fastest: the copy the rays gather from (see Problem::ext)
+  int2* d_zlut = nullptr;   // layer table when only the horizontally varying layers are stored (Problem::zlut)
+  int nzc = 0;
   int* d_pf = nullptr;
   float maxExt = 0.0f;
   bool useSurfaceBDRF = false;
@@ -105,7 +107,9 @@ struct i3rc_integrator {
   double traceMs = 0.0;
   long long traceLaunches = 0, otherLaunches = 0;
   // tuning
-  int blockSize = 128, blocksPerSM = 0, residentBlocks = 0, poolShape = 0, minRunning = 16, padSmem = 0, kSteps = 16, eventThreshold = 16;
+  int blockSize = 128, blocksPerSM = 0, residentBlocks = 0, poolShape = 0, minRunning = 16, padSmem = 0, kSteps = 16;
+  int eventThreshold = 16;
+  int splitLayers = 1;  // (0 never, 1 large fields, 2 always) store only the horizontally varying layers of totalExt in 3-D when that pays (Problem::zlut)
   // nccl
   void* nccl = nullptr;
   void* ncclLib = nullptr;
@@ -226,11 +230,50 @@ int finish_new_integrator(i3rc_integrator* h) {
                                                                         h->d_ext, d_max);
   h->otherLaunches++;
   dfree(h->d_extZ);
-  CUDA_OK(h, cudaMalloc(&h->d_extZ, sizeof(float) * ncell));
+  dfree(h->d_zlut);
+  h->nzc = 0;
   {
-    dim3 b(32, 8), g((unsigned)((nx + 31) / 32), (unsigned)((nz + 31) / 32), (unsigned)ny);
-    k_transpose_zfast<<<g, b, 0, h->stream>>>(nx, ny, nz, h->d_ext, h->d_extZ);
+    // which layers are horizontally uniform?  If enough are, only the others are stored in 3-D (Problem::zlut)
+    if (const char* e = getenv("I3RC_SPLIT_LAYERS")) h->splitLayers = atoi(e);  // (development switch: 0 never, 2 always)
+    const size_t ncol = (size_t)nx * ny;
+    unsigned int* d_mm = nullptr;
+    CUDA_OK(h, cudaMalloc(&d_mm, sizeof(unsigned int) * 2 * nz));
+    k_layer_minmax<<<nz, 256, 0, h->stream>>>(h->d_ext, ncol, d_mm);
     h->otherLaunches++;
+    std::vector<unsigned int> mm(2 * (size_t)nz);
+    CUDA_OK(h, cudaMemcpyAsync(mm.data(), d_mm, sizeof(unsigned int) * mm.size(), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d_mm);
+    std::vector<int2> lut(nz);
+    std::vector<int> layers;
+    for (int k = 0; k < nz; k++) {
+      if (mm[2 * k] == mm[2 * k + 1]) {
+        lut[k] = make_int2(-1, (int)mm[2 * k]);
+      } else {
+        lut[k] = make_int2((int)layers.size(), 0);
+        layers.push_back(k);
+      }
+    }
+    const int nzc = (int)layers.size();
+    // worth it for a field that does not stay in L2 and of which at least a quarter of the layers is uniform
+    const bool big = ncell * sizeof(float) > ((size_t)48 << 20) || h->splitLayers == 2;
+    if (ncol > 1 && nzc > 0 && nzc * 4 <= nz * 3 && h->splitLayers && big) {
+      int* d_layers = nullptr;
+      CUDA_OK(h, upload(&d_layers, layers.data(), layers.size(), h->stream));
+      CUDA_OK(h, upload(&h->d_zlut, lut.data(), lut.size(), h->stream));
+      CUDA_OK(h, cudaMalloc(&h->d_extZ, sizeof(float) * ncol * nzc));
+      dim3 b(32, 8), g((unsigned)((nx + 31) / 32), (unsigned)((nzc + 31) / 32), (unsigned)ny);
+      k_compact_zfast<<<g, b, 0, h->stream>>>(nx, ny, nzc, d_layers, h->d_ext, h->d_extZ);
+      h->otherLaunches++;
+      CUDA_OK(h, cudaStreamSynchronize(h->stream));
+      cudaFree(d_layers);
+      h->nzc = nzc;
+    } else {
+      CUDA_OK(h, cudaMalloc(&h->d_extZ, sizeof(float) * ncell));
+      dim3 b(32, 8), g((unsigned)((nx + 31) / 32), (unsigned)((nz + 31) / 32), (unsigned)ny);
+      k_transpose_zfast<<<g, b, 0, h->stream>>>(nx, ny, nz, h->d_ext, h->d_extZ);
+      h->otherLaunches++;
+    }
   }
   unsigned int bits = 0;
   CUDA_OK(h, cudaMemcpyAsync(&bits, d_max, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
@@ -341,8 +384,10 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
   p.ye = h->d_ye;
   p.ze = h->d_ze;
   p.ext = h->d_extZ;
-  p.esx = h->ny * h->nz;
-  p.esy = h->nz;
+  p.zlut = h->d_zlut;
+  p.nzc = h->nzc;
+  p.esx = h->ny * (h->nzc ? h->nzc : h->nz);
+  p.esy = h->nzc ? h->nzc : h->nz;
   p.esz = 1;
   p.cumExt = h->d_cum;
   p.ssa = h->d_ssa;
@@ -462,20 +507,20 @@ int fill_source(i3rc_integrator* h, const i3rc_photon_source* s, SourceDev& d) {
   return I3RC_SUCCESS;
 }
 
-template <int BLOCK, bool REG, bool FAST, int MINB, int STEPS, int NSLOT, int QCAP>
+template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP>
 int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   int perSM = h->blocksPerSM;
   if (perSM <= 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_transport<BLOCK, REG, FAST, MINB, STEPS, NSLOT, QCAP>, BLOCK, 0) != cudaSuccess || perSM <= 0)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_transport<BLOCK, REG, FAST, SPLIT, MINB, STEPS, NSLOT, QCAP>, BLOCK, 0) != cudaSuccess || perSM <= 0)
       perSM = 1;
   }
   long long want = (p.src.n + BLOCK - 1) / BLOCK;
   long long grid = (long long)h->numSMs * perSM;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  ProblemT<REG, FAST> pt;
+  ProblemT<REG, FAST, SPLIT> pt;
   static_cast<Problem&>(pt) = p;
-  k_transport<BLOCK, REG, FAST, MINB, STEPS, NSLOT, QCAP><<<(unsigned)grid, BLOCK, (size_t)h->padSmem, h->stream>>>(pt, h->eventThreshold, h->minRunning);
+  k_transport<BLOCK, REG, FAST, SPLIT, MINB, STEPS, NSLOT, QCAP><<<(unsigned)grid, BLOCK, (size_t)h->padSmem, h->stream>>>(pt, h->eventThreshold, h->minRunning);
   return I3RC_SUCCESS;
 }
 // MINB = resident blocks per SM the kernel is compiled for (register cap 65536 / (MINB * BLOCK));
@@ -484,14 +529,19 @@ int launch_transport_t(i3rc_integrator* h, const Problem& p) {
 template <int MINB, int NSLOT, int QCAP>
 int launch_transport_fast(i3rc_integrator* h, const Problem& p) {
   const int steps = h->kSteps <= 8 ? 8 : (h->kSteps <= 16 ? 16 : 32);
-  return steps == 8    ? launch_transport_t<128, true, true, MINB, 8, NSLOT, QCAP>(h, p)
-         : steps == 16 ? launch_transport_t<128, true, true, MINB, 16, NSLOT, QCAP>(h, p)
-                       : launch_transport_t<128, true, true, MINB, 32, NSLOT, QCAP>(h, p);
+  return steps == 8    ? launch_transport_t<128, true, true, false, MINB, 8, NSLOT, QCAP>(h, p)
+         : steps == 16 ? launch_transport_t<128, true, true, false, MINB, 16, NSLOT, QCAP>(h, p)
+                       : launch_transport_t<128, true, true, false, MINB, 32, NSLOT, QCAP>(h, p);
 }
 int launch_transport(i3rc_integrator* h, const Problem& p) {
   const bool reg = p.xyRegular && p.zRegular;
   const bool fast = p.useRayTracing && p.src.kind != 5 && p.src.kind != 6 && !p.useSurfaceBDRF && !p.useHybrid && !p.limitContrib &&
                     !p.trackByComponent;
+  if (p.nzc) {  // only the horizontally varying layers are stored (large fields): the gathers look the layer up first
+    if (reg && fast) return launch_transport_t<128, true, true, true, 5, 16, 64, 64>(h, p);
+    if (reg) return launch_transport_t<128, true, false, true, 5, 16, 64, 64>(h, p);
+    return launch_transport_t<128, false, false, true, 5, 16, 64, 64>(h, p);
+  }
   if (reg && fast) {
     // resident blocks per SM, 0 = automatic: 6 while the extinction field is L2-resident; 5 (more of the 256 KB left as
     // L1) when the gathers go to HBM
@@ -508,8 +558,8 @@ int launch_transport(i3rc_integrator* h, const Problem& p) {
         return launch_transport_fast<5, 64, 64>(h, p);
     }
   }
-  if (reg) return launch_transport_t<128, true, false, 5, 16, 64, 64>(h, p);
-  return fast ? launch_transport_t<128, false, true, 5, 16, 64, 64>(h, p) : launch_transport_t<128, false, false, 5, 16, 64, 64>(h, p);
+  if (reg) return launch_transport_t<128, true, false, false, 5, 16, 64, 64>(h, p);
+  return fast ? launch_transport_t<128, false, true, false, 5, 16, 64, 64>(h, p) : launch_transport_t<128, false, false, false, 5, 16, 64, 64>(h, p);
 }
 
 // zero tallies, trace one batch, post-process (MCRT:296-395); no host synchronisation
@@ -849,6 +899,7 @@ void i3rc_finalize_Integrator(i3rc_integrator* h) {
   dfree(h->d_ze);
   dfree(h->d_ext);
   dfree(h->d_extZ);
+  dfree(h->d_zlut);
   dfree(h->d_cum);
   dfree(h->d_ssa);
   dfree(h->d_pf);
@@ -1207,6 +1258,7 @@ int i3rc_copy_Integrator(const i3rc_integrator* s, i3rc_integrator** out) {
   h->residentBlocks = s->residentBlocks;
   h->poolShape = s->poolShape;
   h->minRunning = s->minRunning;
+  h->splitLayers = s->splitLayers;
   h->message.clear();
   *out = h;
   return I3RC_SUCCESS;
@@ -1226,7 +1278,7 @@ int i3rc_trace_rays(i3rc_integrator* h, int n, const float* pos, const float* di
     CUDA_OK(h, cudaMalloc(&d_tau, sizeof(float) * n));
     CUDA_OK(h, cudaMalloc(&d_po, sizeof(float) * 3 * n));
     CUDA_OK(h, cudaMalloc(&d_idx, sizeof(int) * 3 * n));
-    ProblemT<false> p;
+    ProblemDyn p;
     fill_problem(h, p);
     k_trace_rays<<<(n + 127) / 128, 128, 0, h->stream>>>(p, n, d_pos, d_dir, d_lim, d_tau, d_po, d_idx);
     h->otherLaunches++;
@@ -1487,6 +1539,8 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->kSteps = value;
   else if (k == "resident_blocks" && (value == 0 || (value >= 4 && value <= 6)))
     h->residentBlocks = value;
+  else if (k == "split_layers")
+    h->splitLayers = value;  // takes effect at the next new_Integrator / copy_Integrator
   else if (k == "pad_smem" && value >= 0 && value <= 16384)
     h->padSmem = value;  // experiment: unused dynamic shared memory (shrinks the L1 share of the SM)
   else if (k == "min_running" && value >= 0 && value <= 32)

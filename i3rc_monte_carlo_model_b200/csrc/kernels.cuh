@@ -42,8 +42,8 @@ struct SlotPool {  // structure of arrays: lane i touches slot[k] of every array
 };
 constexpr uint32_t SLOT_RAW = 1u << 24;
 
-template <int BLOCK, bool REG, bool FAST, int MINB, int STEPS, int NSLOT, int QCAP>
-__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, FAST> p, const int lowWater, const int minRunning) {
+template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP>
+__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, FAST, SPLIT> p, const int lowWater, const int minRunning) {
   constexpr int NW = BLOCK / 32;
   static_assert((QCAP & (QCAP - 1)) == 0 && QCAP >= 64, "ring size: power of two, room for one push of 32");
   static_assert(NSLOT >= 32 && NSLOT <= 255, "slot ids are bytes");
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
         c3 = __uint_as_float(sv[4 * 32]);
         E.comp = (int)(sv[5 * 32] >> 16);
         E.pfi = (int)(sv[5 * 32] & 0xffffu);
-        if (has && E.active) E.eCell = __ldg(p.ext + ext_index(p, E.cx, E.cy, E.cz));
+        if (has && E.active) E.eCell = ext_at(p, E.cx, E.cy, E.cz);
       }
       if (stage == 1) {  // local-estimate tasks, one direction at a time (MCRT:1473-1569)
         while (dcur < p.nDir && QCAP - (tail - head) >= 32) {
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
             const long long id = (long long)base + __popc(mn & lt);
             if (id < p.src.n) {
               xiTau = init_photon_state(p, E, id);
-              E.eCell = __ldg(p.ext + ext_index(p, E.cx, E.cy, E.cz));
+              E.eCell = ext_at(p, E.cx, E.cy, E.cz);
               pool.id[eslot] = (uint32_t)id;
               go = true;
             }
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
 }
 
 // ---- probes: accumulateExtinctionAlongPath for explicit rays (deterministic sub-path parity) ---------------
-__global__ void k_trace_rays(const ProblemT<false> p, int n, const float* __restrict__ pos, const float* __restrict__ dir,
+__global__ void k_trace_rays(const ProblemDyn p, int n, const float* __restrict__ pos, const float* __restrict__ dir,
                              const float* __restrict__ tauLimit, float* __restrict__ tauOut,
                              float* __restrict__ posOut, int* __restrict__ idxOut) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -484,6 +484,48 @@ __global__ void k_transpose_zfast(int nx, int ny, int nz, const float* __restric
   for (int k = threadIdx.y; k < 32; k += blockDim.y) {
     const int ix = x0 + k, iz = z0 + threadIdx.x;
     if (ix < nx && iz < nz) out[((size_t)ix * ny + iy) * nz + iz] = tile[threadIdx.x][k];
+  }
+}
+
+// per layer: are all cells of the layer equal?  out[iz] = {min bits, max bits} (extinctions are >= 0: bits order = value order)
+__global__ void k_layer_minmax(const float* __restrict__ in, size_t ncol, unsigned int* __restrict__ out) {
+  __shared__ unsigned int lo[256], hi[256];
+  const float* row = in + (size_t)blockIdx.x * ncol;
+  unsigned int a = 0xffffffffu, b = 0u;
+  for (size_t i = threadIdx.x; i < ncol; i += blockDim.x) {
+    const unsigned int v = __float_as_uint(row[i]);
+    a = min(a, v);
+    b = max(b, v);
+  }
+  lo[threadIdx.x] = a;
+  hi[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      lo[threadIdx.x] = min(lo[threadIdx.x], lo[threadIdx.x + o]);
+      hi[threadIdx.x] = max(hi[threadIdx.x], hi[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[2 * blockIdx.x] = lo[0];
+    out[2 * blockIdx.x + 1] = hi[0];
+  }
+}
+// the layers that vary horizontally, z-fastest: out[(ix*ny + iy)*nzc + k] = in[layer[k]][iy][ix]
+__global__ void k_compact_zfast(int nx, int ny, int nzc, const int* __restrict__ layer, const float* __restrict__ in,
+                                float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int iy = blockIdx.z;
+  const int x0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+    const int ix = x0 + threadIdx.x, kk = k0 + k;
+    if (ix < nx && kk < nzc) tile[k][threadIdx.x] = in[((size_t)layer[kk] * ny + iy) * nx + ix];
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+    const int ix = x0 + k, kk = k0 + threadIdx.x;
+    if (ix < nx && kk < nzc) out[((size_t)ix * ny + iy) * nzc + kk] = tile[threadIdx.x][k];
   }
 }
 

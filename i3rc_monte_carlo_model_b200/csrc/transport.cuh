@@ -22,6 +22,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "philox.cuh"
 
@@ -43,6 +44,12 @@
 #define I3RC_COS(x) cosf(x)
 #define I3RC_SINCOS(x, s, c) (*(s) = sinf(x), *(c) = cosf(x))
 #define I3RC_FDIV(a, b) ((a) / (b))
+#endif
+
+#ifndef __CUDACC__
+struct int2 {  // (the CUDA vector type, for the CPU build of this header)
+  int x, y;
+};
 #endif
 
 namespace i3rc {
@@ -93,6 +100,13 @@ struct Problem {
   // of the other fields.
   const float* ext;
   int esx, esy, esz;
+  // Horizontally uniform layers (clear air or gas only, above and below the clouds of a typical domain) need no 3-D
+  // storage: when nzc > 0 the field holds only the nzc layers that vary horizontally, ext[(ix*ny + iy)*nzc + k], and
+  // zlut[iz] = { k, or -1 for a uniform layer ; bits of the uniform layer's extinction }; esz stays 1, so the cell index
+  // of a ray is its column's base + iz.  A 512x512x256 field with 80 cloudy layers shrinks from 268 MB to 84 MB and
+  // fits the L2 cache.
+  const int2* zlut;
+  int nzc;
   const float* cumExt;
   const float* ssa;
   const int* pfIdx;
@@ -118,13 +132,43 @@ struct Problem {
 // FAST = the common configuration (ray tracing, a top-of-domain source, constant Lambertian albedo, original phase
 // functions, no contribution limiting): the rarely used code paths are compiled out, which keeps the kernel's
 // instruction footprint small (the SM's instruction cache holds ~32 KB).
-template <bool REG, bool FAST = false>
+// SPLIT = the field stores only the horizontally varying layers (Problem::zlut): the gather first looks the layer up.
+template <bool REG, bool FAST = false, bool SPLIT = false>
 struct ProblemT : Problem {
   static constexpr bool kRegular = REG;
   static constexpr bool kFast = FAST;
+  static constexpr bool kSplit = SPLIT;
+};
+// the general-purpose instantiation (probes, CPU harness): the layer table is honoured at run time
+struct ProblemDyn : Problem {
+  static constexpr bool kRegular = false;
+  static constexpr bool kFast = false;
+  static constexpr bool kSplit = true;
 };
 
 I3RC_HD int ext_index(const Problem& p, int ix, int iy, int iz) { return ix * p.esx + iy * p.esy + iz * p.esz; }
+// extinction of layer iz of the column whose index (ext_index) is idx
+template <class P>
+I3RC_HD float ext_gather(const P& p, int idx, int iz) {
+  if (!P::kSplit || p.nzc == 0) return I3RC_LDG(p.ext + idx);
+#ifdef __CUDA_ARCH__
+  const int2 t = __ldg(p.zlut + iz);
+#else
+  const int2 t = p.zlut[iz];
+#endif
+  if (t.x < 0) {
+#ifdef __CUDA_ARCH__
+    return __int_as_float(t.y);
+#else
+    float f;
+    memcpy(&f, &t.y, sizeof f);
+    return f;
+#endif
+  }
+  return I3RC_LDG(p.ext + (idx - iz) + t.x);  // (idx counts the layer with stride 1, see Problem::zlut)
+}
+template <class P>
+I3RC_HD float ext_at(const P& p, int ix, int iy, int iz) { return ext_gather(p, ext_index(p, ix, iy, iz), iz); }
 
 struct Lane {
   // current ray (regular or irregular grid): linear cell index, signed index strides per axis, and the number of
@@ -329,7 +373,7 @@ template <class P>
 I3RC_HD void ray_begin(const P& p, Lane& L, float eCell) {
   L.e0 = eCell;
   L.par = 0;
-  if (!ray_advance(p, L)) L.e1 = I3RC_LDG(p.ext + L.idx);
+  if (!ray_advance(p, L)) L.e1 = ext_gather(p, L.idx, ray_iz(p, L));
 }
 
 // Start a ray in cell (ix,iy,iz) at offset (fx,fy,fz) inside it along direction (dx,dy,dz); ia* = 1/|cosine|;
@@ -368,7 +412,7 @@ template <class P>
 I3RC_HD void start_ray(const P& p, Lane& L, float dx, float dy, float dz, float iax, float iay, float iaz,
                        float tauLimit) {
   start_ray_at(p, L, L.cx, L.cy, L.cz, L.fx, L.fy, L.fz, dx, dy, dz, iax, iay, iaz, tauLimit,
-               I3RC_LDG(p.ext + ext_index(p, L.cx, L.cy, L.cz)));
+               ext_at(p, L.cx, L.cy, L.cz));
 }
 
 // ONE cell crossing (the body of accumulateExtinctionAlongPath's loop, MCRT:1690-1806), software-pipelined.
@@ -392,7 +436,7 @@ I3RC_HD void dda_step(const P& p, Lane& L) {
     return;
   }
   L.tau = t;
-  if (!ray_advance(p, L)) ePending = I3RC_LDG(p.ext + L.idx);  // (the register is free now: it becomes the look-ahead)
+  if (!ray_advance(p, L)) ePending = ext_gather(p, L.idx, ray_iz(p, L));  // (the register is free now: it becomes the look-ahead)
 }
 // Two crossings in a row, the form the kernel's trace round uses: the second step is nested in the first one's
 // "goes on" branch, so a running ray pays one test per step and nothing has to be re-examined in between.
@@ -406,7 +450,7 @@ I3RC_HD void dda_step_pair(const P& p, Lane& L) {
     return;
   }
   L.tau = tA;
-  if (!ray_advance(p, L)) L.e0 = I3RC_LDG(p.ext + L.idx);
+  if (!ray_advance(p, L)) L.e0 = ext_gather(p, L.idx, ray_iz(p, L));
   const float tB = fmaf(L.sp, L.e1, L.tau);
   L.nsteps += 2;
   if (tB > L.tauLimit || L.cntz == 0) {
@@ -415,7 +459,7 @@ I3RC_HD void dda_step_pair(const P& p, Lane& L) {
     return;
   }
   L.tau = tB;
-  if (!ray_advance(p, L)) L.e1 = I3RC_LDG(p.ext + L.idx);
+  if (!ray_advance(p, L)) L.e1 = ext_gather(p, L.idx, ray_iz(p, L));
 }
 // one lane at a time (CPU harness, probes): the parity is kept in the lane
 template <class P>
@@ -542,7 +586,7 @@ I3RC_HD void max_cross_section_flight(const P& p, Lane& L, float xiFirst) {
     locate_abs(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, p.dx, x, 0, &L.cx, &L.fx);
     locate_abs(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, p.dy, y, 0, &L.cy, &L.fy);
     locate_abs(p.ze, p.zRegular, p.nz, p.z0, p.zmax, p.dz, z, 0, &L.cz, &L.fz);
-    float e = I3RC_LDG(p.ext + ext_index(p, L.cx, L.cy, L.cz));
+    float e = ext_at(p, L.cx, L.cy, L.cz);
     if (xiAcc < e / p.maxExt) {
       L.done = DONE_INSIDE;
       return;
@@ -879,13 +923,13 @@ I3RC_HD int photon_event(const P& p, Lane& L, float xi0, float xi1) {
     make_direction(mu, phi, &L.ux, &L.uy, &L.uz);
     L.comp = 0;
     L.pfi = 0;
-    L.eCell = I3RC_LDG(p.ext + ext_index(p, L.cx, L.cy, 0));
+    L.eCell = ext_at(p, L.cx, L.cy, 0);
   } else {  // collision, MCRT:581-668
     L.order++;
     I3RC_COUNT(L, CNT_COLL, 1);
     const size_t ncell = (size_t)p.nx * p.ny * p.nz;
     const size_t cell = ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx;
-    L.eCell = I3RC_LDG(p.ext + ext_index(p, L.cx, L.cy, L.cz));  // for the rays that start here (local estimates, next segment)
+    L.eCell = ext_at(p, L.cx, L.cy, L.cz);  // for the rays that start here (local estimates, next segment)
     int comp = 1;
     if (p.nc > 1) {  // findIndex(xi, (/0, cumulativeExt(:)/)), MCRT:637-638
       const float xi = xi0;

@@ -97,7 +97,7 @@ def test_scattering_angle_and_phase_lookup_probes(cuda, oracle):
     assert np.max(np.abs(pg - po) / np.abs(po)) < 1e-5
 
 
-@pytest.mark.parametrize("field", ["stepCloud", "landsat", "irregular"])
+@pytest.mark.parametrize("field", ["stepCloud", "landsat", "irregular", "uniformLayers"])
 def test_optical_path_along_fixed_rays(cuda, oracle, field):
     """accumulateExtinctionAlongPath on the device vs exact float64 integration (1e-5) and vs the oracle."""
     from tests.hostsim.binding import dense_from_domain
@@ -106,6 +106,8 @@ def test_optical_path_along_fixed_rays(cuda, oracle, field):
         d = fields.step_cloud(1.0)
     elif field == "landsat":
         d = fields.landsat_cloud(1.0, nLegendreCoefficients=8)
+    elif field == "uniformLayers":  # cloud in 20 of 64 layers + gas everywhere: only the cloudy layers are stored in 3-D
+        d = fields.synthetic_les(nx=24, ny=16, nz=64, n_entries=3, seed=7, nLegendreCoefficients=8)
     else:
         d = _irregular_domain()
     tot = dense_from_domain(d)[0].astype(np.float64)
