@@ -93,9 +93,13 @@ struct i3rc_integrator {
   size_t scratchN = 0;
   float* d_fscratch = nullptr;
   size_t fscratchN = 0;
-  // source arrays (I3RC_SRC_ARRAYS)
+  // source arrays (I3RC_SRC_ARRAYS): uploaded in two pieces on a second stream so that all but the first tenth of the
+  // copy runs under the transport kernel of the first piece
   float* d_srcArrays = nullptr;
   size_t srcArraysN = 0;
+  const float* hostArrays[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t copyStream = nullptr;
+  cudaEvent_t copyDone[2] = {nullptr, nullptr}, computeDone = nullptr;
   // batch moments
   double* d_stats = nullptr;
   size_t statsN = 0;
@@ -496,8 +500,12 @@ int fill_source(i3rc_integrator* h, const i3rc_photon_source* s, SourceDev& d) {
       h->srcArraysN = 5 * n;
     }
     const float* srcs[5] = {s->xPosition, s->yPosition, s->zPosition, s->initialMu, s->initialPhi};
-    for (int k = 0; k < 5; k++)
-      CUDA_OK(h, cudaMemcpyAsync(h->d_srcArrays + k * n, srcs[k], sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    for (int k = 0; k < 5; k++) h->hostArrays[k] = srcs[k];  // (copied by run_one_batch, piecewise)
+    if (!h->copyStream) {
+      CUDA_OK(h, cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+      for (auto& e : h->copyDone) CUDA_OK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      CUDA_OK(h, cudaEventCreateWithFlags(&h->computeDone, cudaEventDisableTiming));
+    }
     d.ax = h->d_srcArrays;
     d.ay = h->d_srcArrays + n;
     d.az = h->d_srcArrays + 2 * n;
@@ -592,12 +600,45 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
     h->ev.push_back(b);
   }
   CUDA_OK(h, cudaEventRecord(h->ev[h->evUsed], h->stream));
-  int rc = launch_transport(h, p);
+  int rc = I3RC_SUCCESS;
+  if (src.kind == I3RC_SRC_ARRAYS) {
+    // hand-filled photon arrays: piece 0 (a tenth) is copied, then traced while piece 1 is being copied
+    const long long n = src.n;
+    const long long n0 = n >= (1 << 20) ? ((n / 10 + 127) / 128) * 128 : n;
+    const long long offs[3] = {0, n0, n};
+    CUDA_OK(h, cudaEventRecord(h->computeDone, h->stream));  // the previous batch may still be reading the arrays
+    CUDA_OK(h, cudaStreamWaitEvent(h->copyStream, h->computeDone, 0));
+    for (int c = 0; c < 2; c++) {
+      const long long len = offs[c + 1] - offs[c];
+      if (len <= 0) continue;
+      for (int k = 0; k < 5; k++)
+        CUDA_OK(h, cudaMemcpyAsync(h->d_srcArrays + k * n + offs[c], h->hostArrays[k] + offs[c], sizeof(float) * len,
+                                   cudaMemcpyHostToDevice, h->copyStream));
+      CUDA_OK(h, cudaEventRecord(h->copyDone[c], h->copyStream));
+    }
+    for (int c = 0; c < 2 && rc == I3RC_SUCCESS; c++) {
+      const long long len = offs[c + 1] - offs[c];
+      if (len <= 0) continue;
+      CUDA_OK(h, cudaStreamWaitEvent(h->stream, h->copyDone[c], 0));
+      if (c) CUDA_OK(h, cudaMemsetAsync(h->d_next, 0, sizeof(unsigned long long), h->stream));
+      p.src.n = len;
+      p.src.ax = src.ax + offs[c];
+      p.src.ay = src.ay + offs[c];
+      p.src.az = src.az + offs[c];
+      p.src.amu = src.amu + offs[c];
+      p.src.aphi = src.aphi + offs[c];
+      p.firstPhoton = offs[c];
+      rc = launch_transport(h, p);
+      h->traceLaunches++;
+    }
+  } else {
+    rc = launch_transport(h, p);
+    h->traceLaunches++;
+  }
   if (rc != I3RC_SUCCESS) return rc;
   CUDA_OK(h, cudaGetLastError());
   CUDA_OK(h, cudaEventRecord(h->ev[h->evUsed + 1], h->stream));
   h->evUsed += 2;
-  h->traceLaunches++;
 
   if (nD && h->limitContrib) {  // MCRT:327-347
     int rows = (h->nc + 1) * nD;
@@ -920,6 +961,12 @@ void i3rc_finalize_Integrator(i3rc_integrator* h) {
   dfree(h->d_intByComp);
   dfree(h->d_excess);
   dfree(h->d_counters);
+  if (h->copyStream) {
+    cudaStreamDestroy(h->copyStream);
+    for (auto& e : h->copyDone) cudaEventDestroy(e);
+    cudaEventDestroy(h->computeDone);
+    h->copyStream = nullptr;
+  }
   dfree(h->d_next);
   dfree(h->d_scratch);
   dfree(h->d_fscratch);
