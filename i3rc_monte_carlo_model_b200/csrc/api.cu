@@ -89,6 +89,8 @@ struct i3rc_integrator {
   float *d_fluxUp = nullptr, *d_fluxDown = nullptr, *d_fluxAbs = nullptr, *d_volAbs = nullptr;
   float *d_intensity = nullptr, *d_intByComp = nullptr, *d_excess = nullptr;
   unsigned long long *d_counters = nullptr, *d_next = nullptr;
+  double* d_fold = nullptr;  // float64 sums of the tallies of a batch that is traced in pieces (run_one_batch)
+  size_t foldN = 0;
   double* d_scratch = nullptr;  // slab sums
   size_t scratchN = 0;
   float* d_fscratch = nullptr;
@@ -601,39 +603,77 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
   }
   CUDA_OK(h, cudaEventRecord(h->ev[h->evUsed], h->stream));
   int rc = I3RC_SUCCESS;
-  if (src.kind == I3RC_SRC_ARRAYS) {
-    // hand-filled photon arrays: piece 0 (a tenth) is copied, then traced while piece 1 is being copied
-    const long long n = src.n;
-    const long long n0 = n >= (1 << 20) ? ((n / 10 + 127) / 128) * 128 : n;
-    const long long offs[3] = {0, n0, n};
+  // The batch is traced in pieces (photon ids [off, off + len), one launch each) for two reasons:
+  //  * float32 tallies: an element that receives more than ~2^24 increments stops growing (a 1-column plane-parallel
+  //    domain with 1e8 photons), and small increments are lost long before that.  Pieces are kept below 2^20 photons per
+  //    column and folded into float64 sums in between;
+  //  * hand-filled photon arrays: the first tenth is copied, then traced while the rest is being copied.
+  const long long n = src.n;
+  const long long perPiece = std::max<long long>(1 << 19, (long long)ncol << 20);
+  const bool arrays = src.kind == I3RC_SRC_ARRAYS;
+  std::vector<long long> cuts{0};
+  if (arrays && n >= (1 << 20)) cuts.push_back(std::min<long long>(((n / 10 + 127) / 128) * 128, perPiece));
+  while (n - cuts.back() > perPiece) cuts.push_back(cuts.back() + perPiece);
+  cuts.push_back(n);
+  const int nPieces = (int)cuts.size() - 1;
+  const bool fold = n > perPiece;  // some element may see too many increments for float32
+  struct Tally {
+    float* f;
+    size_t n;
+  };
+  std::vector<Tally> tallies{{h->d_fluxUp, ncol}, {h->d_fluxDown, ncol}, {h->d_fluxAbs, ncol}, {h->d_volAbs, ncell}};
+  if (h->d_intensity) tallies.push_back({h->d_intensity, ncol * h->nDir});
+  if (h->d_intByComp && byComp) tallies.push_back({h->d_intByComp, ncol * h->nDir * (h->nc + 1)});
+  if (h->d_excess) tallies.push_back({h->d_excess, (size_t)(h->nc + 1) * h->nDir});
+  size_t nTally = 0;
+  for (auto& t : tallies) nTally += t.n;
+  if (fold) {
+    if (h->foldN < nTally) {
+      dfree(h->d_fold);
+      CUDA_OK(h, cudaMalloc(&h->d_fold, sizeof(double) * nTally));
+      h->foldN = nTally;
+    }
+    CUDA_OK(h, cudaMemsetAsync(h->d_fold, 0, sizeof(double) * nTally, h->stream));
+  }
+  if (arrays) {
     CUDA_OK(h, cudaEventRecord(h->computeDone, h->stream));  // the previous batch may still be reading the arrays
     CUDA_OK(h, cudaStreamWaitEvent(h->copyStream, h->computeDone, 0));
+    // two copies: [0, cuts[1]) and the rest (when the batch has a first tenth), each followed by an event
+    const long long c1 = (n >= (1 << 20)) ? cuts[1] : n;
+    const long long copyCuts[3] = {0, c1, n};
     for (int c = 0; c < 2; c++) {
-      const long long len = offs[c + 1] - offs[c];
+      const long long len = copyCuts[c + 1] - copyCuts[c];
       if (len <= 0) continue;
       for (int k = 0; k < 5; k++)
-        CUDA_OK(h, cudaMemcpyAsync(h->d_srcArrays + k * n + offs[c], h->hostArrays[k] + offs[c], sizeof(float) * len,
+        CUDA_OK(h, cudaMemcpyAsync(h->d_srcArrays + k * n + copyCuts[c], h->hostArrays[k] + copyCuts[c], sizeof(float) * len,
                                    cudaMemcpyHostToDevice, h->copyStream));
       CUDA_OK(h, cudaEventRecord(h->copyDone[c], h->copyStream));
     }
-    for (int c = 0; c < 2 && rc == I3RC_SUCCESS; c++) {
-      const long long len = offs[c + 1] - offs[c];
-      if (len <= 0) continue;
-      CUDA_OK(h, cudaStreamWaitEvent(h->stream, h->copyDone[c], 0));
-      if (c) CUDA_OK(h, cudaMemsetAsync(h->d_next, 0, sizeof(unsigned long long), h->stream));
-      p.src.n = len;
-      p.src.ax = src.ax + offs[c];
-      p.src.ay = src.ay + offs[c];
-      p.src.az = src.az + offs[c];
-      p.src.amu = src.amu + offs[c];
-      p.src.aphi = src.aphi + offs[c];
-      p.firstPhoton = offs[c];
-      rc = launch_transport(h, p);
-      h->traceLaunches++;
+  }
+  for (int c = 0; c < nPieces && rc == I3RC_SUCCESS; c++) {
+    const long long off = cuts[c], len = cuts[c + 1] - cuts[c];
+    if (len <= 0) continue;
+    if (arrays && c < 2) CUDA_OK(h, cudaStreamWaitEvent(h->stream, h->copyDone[(c == 0 || n < (1 << 20)) ? 0 : 1], 0));
+    if (c) CUDA_OK(h, cudaMemsetAsync(h->d_next, 0, sizeof(unsigned long long), h->stream));
+    p.src.n = len;
+    if (arrays) {
+      p.src.ax = src.ax + off;
+      p.src.ay = src.ay + off;
+      p.src.az = src.az + off;
+      p.src.amu = src.amu + off;
+      p.src.aphi = src.aphi + off;
     }
-  } else {
+    p.firstPhoton = off;
     rc = launch_transport(h, p);
     h->traceLaunches++;
+    if (fold && rc == I3RC_SUCCESS) {
+      size_t o = 0;
+      for (auto& t : tallies) {
+        k_fold_tally<<<(unsigned)((t.n + 255) / 256), 256, 0, h->stream>>>(t.f, h->d_fold + o, t.n, c == nPieces - 1);
+        o += t.n;
+        h->otherLaunches++;
+      }
+    }
   }
   if (rc != I3RC_SUCCESS) return rc;
   CUDA_OK(h, cudaGetLastError());
@@ -961,6 +1001,7 @@ void i3rc_finalize_Integrator(i3rc_integrator* h) {
   dfree(h->d_intByComp);
   dfree(h->d_excess);
   dfree(h->d_counters);
+  dfree(h->d_fold);
   if (h->copyStream) {
     cudaStreamDestroy(h->copyStream);
     for (auto& e : h->copyDone) cudaEventDestroy(e);

@@ -544,6 +544,15 @@ __global__ void k_slab_sums(const float* __restrict__ in, size_t ncol, double* _
   }
   if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
 }
+// A batch traced in pieces: acc += tally; the tally restarts from zero, or -- after the last piece -- gets the total
+__global__ void k_fold_tally(float* __restrict__ tally, double* __restrict__ acc, size_t n, int last) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double s = acc[i] + (double)tally[i];
+    acc[i] = s;
+    tally[i] = last ? (float)s : 0.0f;
+  }
+}
 // redistribute the clipped local-estimate excess in proportion to intensityByComponent (MCRT:327-347)
 __global__ void k_redistribute_excess(int nDir, int ncomp1, size_t ncol, const float* __restrict__ excess,
                                       const double* __restrict__ slabSum, float* __restrict__ intensity,

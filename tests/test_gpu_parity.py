@@ -363,6 +363,21 @@ def test_dense_and_component_constructors_agree(cuda):
 
 
 # ---- edge cases and status behaviour on the CUDA library ------------------------------------------------------
+def test_float32_tallies_do_not_saturate_on_a_single_column(cuda):
+    """64 M photons into ONE column: float32 tallies alone would stop growing at 2^24 increments (closure 0.43); the
+    batch is traced in pieces that are folded into float64 sums."""
+    I = make_integrator(cuda, fields.plane_parallel(SSA=0.9), surfaceAlbedo=0.3, intensityMus=[1.0, 0.5], intensityPhis=[0.0, 180.0],
+                        useRussianRouletteForIntensity=False)
+    small = run_batches(I, 1_000_000, 4, want=["meanFluxUp", "meanFluxDown", "meanFluxAbsorbed", "meanIntensity", "absorbedProfile"])
+    big = run_batches(I, 64_000_000, 1, want=["meanFluxUp", "meanFluxDown", "meanFluxAbsorbed", "meanIntensity", "absorbedProfile"])
+    closure = big["meanFluxUp"][0] + big["meanFluxAbsorbed"][0] + 0.7 * big["meanFluxDown"][0]
+    assert abs(closure - 1.0) < 5e-4
+    assert big["counters"]["photons"] == 64_000_000
+    for k in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed", "meanIntensity", "absorbedProfile"):
+        m, s = mean_se(small[k])
+        assert np.all(np.abs(big[k][0] - m) < 5.0 * s + 2e-4), (k, big[k][0], m, s)
+
+
 @pytest.mark.parametrize("nph", [1, 31, 33, 1000])
 def test_ragged_photon_counts(cuda, nph):
     I = make_integrator(cuda, fields.plane_parallel(), surfaceAlbedo=0.0)
