@@ -209,6 +209,7 @@ int finish_new_integrator(i3rc_integrator* h) {
   // limits of this implementation: cell indices travel as 16-bit fields, cells are addressed with 32-bit indices
   if (nx > 32767 || ny > 32767 || nz > 32767 || (size_t)nx * ny * nz > (size_t)0x7fffffff)
     return fail(h, "new_Integrator: domain too large for this implementation (at most 32767 cells per axis, 2^31-1 cells).");
+  if (h->nc > 255) return fail(h, "new_Integrator: at most 255 optical components in this implementation.");
   const std::vector<float>&x = h->xe, &y = h->ye, &z = h->ze;
   float dX = x[1] - x[0], dY = y[1] - y[0], dZ = z[1] - z[0];
   bool xyReg = true, zReg = true;
