@@ -379,7 +379,9 @@ def main():
                 "kernel": "k_transport", "kernel_ms_per_launch": trace_ms / launches, "kernel_share_of_step": trace_ms / max(sum(step_ms), 1e-9),
                 "algorithmic_bytes_per_launch": abytes / launches, "cell_crossings_per_s": crossings / (trace_ms * 1e-3),
                 "bytes_per_crossing_model": "4 B/crossing + (4nC+16) B/collision + 32 B/absorption + 24 B/contribution + 8 B/exit",
-                "note": "fields are L2-resident on this workload (7.8 MB per field): the kernel is latency/issue bound, not HBM bound"}
+                "note": ("fields are L2-resident on this workload (7.8 MB per field): the kernel is issue bound, not HBM bound"
+                         if args.workload != "les" else
+                         "268 MB extinction field of which only the 80 horizontally varying layers (84 MB) are stored in 3-D")}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
