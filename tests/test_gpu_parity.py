@@ -97,8 +97,26 @@ def test_scattering_angle_and_phase_lookup_probes(cuda, oracle):
     assert np.max(np.abs(pg - po) / np.abs(po)) < 1e-5
 
 
-@pytest.mark.parametrize("field", ["stepCloud", "landsat", "irregular", "uniformLayers"])
-def test_optical_path_along_fixed_rays(cuda, oracle, field):
+@pytest.fixture
+def force_layer_split(monkeypatch):
+    """Store only the horizontally varying layers of totalExt in 3-D whatever the size of the field (the library does
+    it on its own for fields that do not fit L2)."""
+    monkeypatch.setenv("I3RC_SPLIT_LAYERS", "2")
+
+
+def _irregular_domain_with_uniform_layers():
+    d = _irregular_domain()
+    c = d.components[0]
+    ext, ssa, pfi = c.extinction.copy(), c.singleScatteringAlbedo.copy(), c.phaseFunctionIndex.copy()
+    for k, v in ((0, 0.004), (1, 0.0), (6, 0.0), (12, 0.002), (13, 0.0)):  # clear or hazy layers, horizontally uniform
+        ext[:, :, k], ssa[:, :, k], pfi[:, :, k] = v, (0.95 if v > 0 else 0.0), (1 if v > 0 else 0)
+    from i3rc_monte_carlo_model_b200.opticalProperties import replaceOpticalComponent
+    replaceOpticalComponent(d, 1, c.name, ext, ssa, pfi, c.table)
+    return d
+
+
+@pytest.mark.parametrize("field", ["stepCloud", "landsat", "irregular", "uniformLayers", "irregularUniformLayers"])
+def test_optical_path_along_fixed_rays(cuda, oracle, field, force_layer_split):
     """accumulateExtinctionAlongPath on the device vs exact float64 integration (1e-5) and vs the oracle."""
     from tests.hostsim.binding import dense_from_domain
     from tests.test_oracle_pins import _f64_optical_path
@@ -108,6 +126,8 @@ def test_optical_path_along_fixed_rays(cuda, oracle, field):
         d = fields.landsat_cloud(1.0, nLegendreCoefficients=8)
     elif field == "uniformLayers":  # cloud in 20 of 64 layers + gas everywhere: only the cloudy layers are stored in 3-D
         d = fields.synthetic_les(nx=24, ny=16, nz=64, n_entries=3, seed=7, nLegendreCoefficients=8)
+    elif field == "irregularUniformLayers":
+        d = _irregular_domain_with_uniform_layers()
     else:
         d = _irregular_domain()
     tot = dense_from_domain(d)[0].astype(np.float64)
@@ -190,6 +210,9 @@ STAT_CASES = {
         surfaceAlbedo=0.1, intensityMus=[m for m in (1.0, 0.8, 0.5, 0.3) for _ in range(4)],
         intensityPhis=[p for _ in range(4) for p in (10.0, 100.0, 190.0, 280.0)], useRussianRouletteForIntensity=True,
         zetaMin=0.5), dict(solarMu=0.8, solarAzimuth=40.0), 10000),
+    "irregular-grid-uniform-layers": (_irregular_domain_with_uniform_layers, dict(
+        surfaceAlbedo=0.4, intensityMus=[0.8, -0.6], intensityPhis=[45.0, 200.0], useRussianRouletteForIntensity=False),
+        dict(solarMu=0.7, solarAzimuth=200.0), 20000),
     "source-random-azimuth": (lambda: fields.step_cloud(0.99), dict(surfaceAlbedo=0.0), dict(solarMu=0.6), 3000),
     "source-flux": (lambda: fields.step_cloud(0.99), dict(surfaceAlbedo=0.0), dict(), 3000),
     "source-spotlight": (lambda: fields.step_cloud(0.99), dict(surfaceAlbedo=0.0),
@@ -199,6 +222,11 @@ STAT_CASES = {
     "source-internal-intensity": (lambda: fields.step_cloud(0.99), dict(surfaceAlbedo=0.3),
                                   dict(detectorX=0.3, detectorY=0.5, detectorZ=0.6, detectorMu=0.7, detectorPhi=1.0), 3000),
 }
+
+
+@pytest.mark.parametrize("name", ["irregular-grid-uniform-layers", "two-components-hybrid-limited", "sixteen-directions-roulette"])
+def test_statistical_parity_with_layer_split(cuda, oracle, name, force_layer_split):
+    test_statistical_parity_with_oracle(cuda, oracle, name)
 
 
 @pytest.mark.parametrize("name", list(STAT_CASES))
