@@ -204,6 +204,7 @@ class Backend:
             "lookup_phase_function": (ci, [vp, ci, ci, ci, ci, c_float_p, c_float_p]),
         }
         self._optional = {
+            "set_component_profile": (ci, [vp, ci, c_float_p]),
             "set_inverse_table": (ci, [vp, ci, ci, ci, c_float_p]),
             "set_forward_table": (ci, [vp, ci, ci, ci, c_float_p, c_float_p]),
             "stats_reset": (ci, [vp, ci]),

@@ -204,31 +204,11 @@ int ensure_fscratch(i3rc_integrator* h, size_t n) {
 }
 
 // common part of the two new_Integrator forms once the dense arrays are on the device (MCRT:193-254)
-int finish_new_integrator(i3rc_integrator* h) {
+// From the dense totalExt / cumulativeExt on the device: the last cumulative fraction nudged to 1 + epsilon and the
+// domain maximum of totalExt (MCRT:233-234), and the copy of totalExt the rays gather from (z-fastest; only the
+// horizontally varying layers when that pays, see Problem::zlut).  Also run after a component profile is replaced.
+int build_gather_field(i3rc_integrator* h) {
   const int nx = h->nx, ny = h->ny, nz = h->nz;
-  // limits of this implementation: cell indices travel as 16-bit fields, cells are addressed with 32-bit indices
-  if (nx > 32767 || ny > 32767 || nz > 32767 || (size_t)nx * ny * nz > (size_t)0x7fffffff)
-    return fail(h, "new_Integrator: domain too large for this implementation (at most 32767 cells per axis, 2^31-1 cells).");
-  if (h->nc > 255) return fail(h, "new_Integrator: at most 255 optical components in this implementation.");
-  const std::vector<float>&x = h->xe, &y = h->ye, &z = h->ze;
-  float dX = x[1] - x[0], dY = y[1] - y[0], dZ = z[1] - z[0];
-  bool xyReg = true, zReg = true;
-  for (int i = 0; i < nx; i++)
-    if (!(fabsf((x[i + 1] - x[i]) - dX) <= 2.0f * h_spacing(x[i + 1]))) xyReg = false;
-  for (int i = 0; i < ny; i++)
-    if (!(fabsf((y[i + 1] - y[i]) - dY) <= 2.0f * h_spacing(y[i + 1]))) xyReg = false;
-  for (int i = 0; i < nz; i++)
-    if (!(fabsf((z[i + 1] - z[i]) - dZ) <= h_spacing(z[i + 1]))) zReg = false;
-  h->xyRegular = xyReg;
-  h->zRegular = zReg;
-  if (xyReg) {
-    h->deltaX = dX;
-    h->deltaY = dY;
-  }
-  if (zReg) h->deltaZ = dZ;
-  CUDA_OK(h, upload(&h->d_xe, x.data(), x.size(), h->stream));
-  CUDA_OK(h, upload(&h->d_ye, y.data(), y.size(), h->stream));
-  CUDA_OK(h, upload(&h->d_ze, z.data(), z.size(), h->stream));
   size_t ncell = (size_t)nx * ny * nz;
   unsigned int* d_max = nullptr;
   CUDA_OK(h, cudaMalloc(&d_max, sizeof(unsigned int)));
@@ -287,6 +267,36 @@ int finish_new_integrator(i3rc_integrator* h) {
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
   cudaFree(d_max);
   memcpy(&h->maxExt, &bits, sizeof(float));
+  return I3RC_SUCCESS;
+}
+
+int finish_new_integrator(i3rc_integrator* h) {
+  const int nx = h->nx, ny = h->ny, nz = h->nz;
+  // limits of this implementation: cell indices travel as 16-bit fields, cells are addressed with 32-bit indices
+  if (nx > 32767 || ny > 32767 || nz > 32767 || (size_t)nx * ny * nz > (size_t)0x7fffffff)
+    return fail(h, "new_Integrator: domain too large for this implementation (at most 32767 cells per axis, 2^31-1 cells).");
+  if (h->nc > 255) return fail(h, "new_Integrator: at most 255 optical components in this implementation.");
+  const std::vector<float>&x = h->xe, &y = h->ye, &z = h->ze;
+  float dX = x[1] - x[0], dY = y[1] - y[0], dZ = z[1] - z[0];
+  bool xyReg = true, zReg = true;
+  for (int i = 0; i < nx; i++)
+    if (!(fabsf((x[i + 1] - x[i]) - dX) <= 2.0f * h_spacing(x[i + 1]))) xyReg = false;
+  for (int i = 0; i < ny; i++)
+    if (!(fabsf((y[i + 1] - y[i]) - dY) <= 2.0f * h_spacing(y[i + 1]))) xyReg = false;
+  for (int i = 0; i < nz; i++)
+    if (!(fabsf((z[i + 1] - z[i]) - dZ) <= h_spacing(z[i + 1]))) zReg = false;
+  h->xyRegular = xyReg;
+  h->zRegular = zReg;
+  if (xyReg) {
+    h->deltaX = dX;
+    h->deltaY = dY;
+  }
+  if (zReg) h->deltaZ = dZ;
+  CUDA_OK(h, upload(&h->d_xe, x.data(), x.size(), h->stream));
+  CUDA_OK(h, upload(&h->d_ye, y.data(), y.size(), h->stream));
+  CUDA_OK(h, upload(&h->d_ze, z.data(), z.size(), h->stream));
+  int rcg = build_gather_field(h);
+  if (rcg != I3RC_SUCCESS) return rcg;
   h->tables.resize(h->nc);
   h->inv.resize(h->nc);
   h->fwd.resize(h->nc);
@@ -1202,6 +1212,25 @@ int i3rc_set_forward_table(i3rc_integrator* h, int comp, int nSteps, int nEntrie
   h->fwd[comp].nEntries = h->fwdOrig[comp].nEntries = nEntries;
   if (nSteps > h->minForwardTableSize) h->minForwardTableSize = nSteps;
   h->tableDescDirty = true;
+  return I3RC_SUCCESS;
+}
+
+int i3rc_set_component_profile(i3rc_integrator* h, int comp, const float* extinction) {
+  if (!h || !h->readyToCompute) return I3RC_FAILURE;
+  if (comp < 0 || comp >= h->nc || !extinction) return fail(h, "set_component_profile: no such component.");
+  for (int k = 0; k < h->nz; k++)
+    if (!(extinction[k] >= 0.0f)) return fail(h, "set_component_profile: extinction must be >= 0.");
+  CUDA_OK(h, cudaSetDevice(h->device));
+  float* d_prof = nullptr;
+  CUDA_OK(h, upload(&d_prof, extinction, (size_t)h->nz, h->stream));
+  const size_t ncell = (size_t)h->nx * h->ny * h->nz;
+  k_replace_profile<<<(unsigned)((ncell + 255) / 256), 256, 0, h->stream>>>(h->nx, h->ny, h->nz, h->nc, comp, d_prof, h->d_ext, h->d_cum);
+  h->otherLaunches++;
+  CUDA_OK(h, cudaGetLastError());
+  int rc = build_gather_field(h);  // maximum extinction, 1 + epsilon nudge, the copy of totalExt the rays gather from
+  cudaFree(d_prof);
+  if (rc != I3RC_SUCCESS) return rc;
+  h->message.clear();
   return I3RC_SUCCESS;
 }
 

@@ -470,6 +470,29 @@ __global__ void k_expand_components(int nx, int ny, int nz, int nc, const Compon
   if (run > F_TINY)
     for (int c = 0; c < nc; c++) cumExt[(size_t)c * ncell + cell] = cumExt[(size_t)c * ncell + cell] / run;
 }
+// One component's extinction replaced by a horizontally uniform profile (a k-distribution term of a gas component): the
+// per-component extinctions are recovered from the cumulative fractions, the component swapped, totals and fractions
+// rebuilt like getOpticalPropertiesByComponent does (Code/opticalProperties.f95:524-537).
+__global__ void k_replace_profile(int nx, int ny, int nz, int nc, int comp, const float* __restrict__ profile,
+                                  float* __restrict__ totalExt, float* __restrict__ cumExt) {
+  const size_t ncell = (size_t)nx * ny * nz;
+  const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ncell) return;
+  const int iz = (int)(cell / ((size_t)nx * ny));
+  const float tot = totalExt[cell];
+  float prev = 0.0f, run = 0.0f;
+  for (int c = 0; c < nc; c++) {
+    float frac = cumExt[(size_t)c * ncell + cell];
+    if (c == nc - 1 && tot > F_TINY) frac = 1.0f;  // (undo the 1 + epsilon nudge)
+    const float a = c == comp ? profile[iz] : (tot > F_TINY ? (frac - prev) * tot : frac - prev);
+    prev = frac;
+    run += a;
+    cumExt[(size_t)c * ncell + cell] = run;
+  }
+  totalExt[cell] = run;
+  if (run > F_TINY)
+    for (int c = 0; c < nc; c++) cumExt[(size_t)c * ncell + cell] = cumExt[(size_t)c * ncell + cell] / run;
+}
 // MCRT:233-234: nudge the last cumulative fraction to 1 + epsilon; also the domain maximum of totalExt
 __global__ void k_bump_and_max(size_t ncell, float* __restrict__ lastCum, const float* __restrict__ totalExt,
                                unsigned int* __restrict__ maxBits) {

@@ -165,6 +165,33 @@ def device_stats_report(integ, solarFlux, numBatches, with_volume=False):
     return res
 
 
+# ---- spectral loop -------------------------------------------------------------------------------
+def run_spectral_bands(integ, source, numPhotonsPerBatch, numBatches, gasComponent, bands, iseed=10, solarFlux=1.0, dist=None):
+    """A k-distribution / band loop over ONE integrator: for every term ``(weight, extinctionProfile[nZ])`` the gas
+    component's extinction is swapped on the device (``setComponentProfile``, no field rebuild), the usual batches are
+    traced, and the per-term means are combined: mean = sum_k w_k mean_k, stderr = sqrt(sum_k w_k^2 stderr_k^2) (terms are
+    independent).  The reference has no such loop (Code/kDistribution.f95 is an unfinished stub); its only mechanism for
+    gas absorption is an extra ssa = 0 component (Tools/PhysicalPropertiesToDomain.f95:330-347), which is what is
+    swapped here.  Returns name -> (mean, stderr)."""
+    from .monteCarloRadiativeTransfer import setComponentProfile
+    rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    nB, mine = partition_batches(numBatches, world, rank)
+    total = None
+    for k, (weight, profile) in enumerate(bands):
+        setComponentProfile(integ, gasComponent, profile)
+        # every term gets its own seeds: batches (k * nB + 1) ... of the same iseed
+        run_batches_device(integ, source, numPhotonsPerBatch, [b + k * nB for b in mine], iseed=iseed)
+        allreduce_device_stats(integ, dist)
+        st = device_stats_report(integ, solarFlux, nB)
+        if total is None:
+            total = {name: (np.zeros_like(np.asarray(m, np.float64)), np.zeros_like(np.asarray(e, np.float64))) for name, (m, e) in st.items()}
+        for name, (m, e) in st.items():
+            total[name][0][...] += weight * np.asarray(m)
+            total[name][1][...] += (weight * np.asarray(e)) ** 2
+    return {name: (m, np.sqrt(v)) for name, (m, v) in total.items()}
+
+
 # ---- namelists (monteCarloDriver.f95:90-103) ------------------------------------------------------------------
 _DEFAULTS = {
     "radiativetransfer": dict(solarFlux=1.0, solarMu=1.0, solarAzimuth=0.0, surfaceAlbedo=0.0, intensityMus=[], intensityPhis=[]),

@@ -208,6 +208,23 @@ def reportResults(thisIntegrator, *want, status=None, out=None):
 
 
 # ---- helpers that are not part of the reference module but of the C ABI -------------------------
+def setComponentProfile(thisIntegrator, componentNumber, extinction, status=None):
+    """Replace the extinction of component ``componentNumber`` (1-based) by a horizontally uniform profile
+    extinction[nZ] on the device -- one k-distribution term of a gas component (i3rc_set_component_profile)."""
+    be = thisIntegrator.backend
+    if be.set_component_profile is None:
+        setStateToFailure(status, "setComponentProfile: not available on this backend.")
+        return
+    e = _abi.f32(np.asarray(extinction).ravel())
+    if e.size != thisIntegrator.nz:
+        setStateToFailure(status, "setComponentProfile: extinction must have one value per layer.")
+        return
+    rc = be.set_component_profile(thisIntegrator.handle, int(componentNumber) - 1, _abi.fptr(e))
+    from_return_code(status, rc, thisIntegrator._msg())
+    if status is None and rc == _abi.FAILURE:
+        raise RuntimeError(thisIntegrator._msg())
+
+
 def getCounters(thisIntegrator):
     c = _abi.Counters()
     thisIntegrator.backend.get_counters(thisIntegrator.handle, C.byref(c))

@@ -141,6 +141,12 @@ int i3rc_new_Integrator(int nx, int ny, int nz, int nc, const float* xPos, const
 /* new_Integrator(domain): getOpticalPropertiesByComponent (opticalProperties.f95:429-539) runs on the device. */
 int i3rc_new_Integrator_components(int nx, int ny, int nz, const float* xPos, const float* yPos, const float* zPos,
                                    int nc, const i3rc_component* comps, i3rc_integrator** out);
+/* Spectral loops (the reference's own kDistribution.f95 is an unfinished stub): replace the extinction
+ * of component `comp` (0-based) by a horizontally uniform profile extinction[nz] -- one k-distribution term of a gas
+ * component -- without rebuilding or re-uploading the other fields.  Single-scattering albedo and phase-function index of
+ * the component stay as they are.  Equivalent to replaceOpticalComponent (Code/opticalProperties.f95:232-309) followed
+ * by new_Integrator. */
+int i3rc_set_component_profile(i3rc_integrator* h, int comp, const float* extinction);
 /* forwardTables(comp) (MCRT:92-93): the table tabulate{Inverse,Forward}PhaseFunctions work from. comp is 0-based. */
 int i3rc_set_phase_table(i3rc_integrator* h, int comp, const i3rc_phase_table* t);
 int i3rc_copy_Integrator(const i3rc_integrator* src, i3rc_integrator** out); /* MCRT:1082 */

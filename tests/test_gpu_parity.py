@@ -429,3 +429,63 @@ def test_compute_status_cuda(cuda):
     status = ErrorMessage()
     r = reportResults(I, "intensity", status=status)
     assert stateIsFailure(status) and "intensity information not available" in getCurrentMessage(status)
+
+
+# ---- spectral loop: a gas component's extinction profile swapped on the device ------------------
+@pytest.mark.gpu
+def test_component_profile_swap_equals_a_fresh_integrator(cuda, oracle, force_layer_split):
+    from i3rc_monte_carlo_model_b200.monteCarloRadiativeTransfer import setComponentProfile
+    from i3rc_monte_carlo_model_b200.opticalProperties import replaceOpticalComponent
+    params = dict(surfaceAlbedo=0.1, intensityMus=[1.0, 0.6], intensityPhis=[0.0, 90.0], useRussianRouletteForIntensity=True, zetaMin=0.3)
+    d1 = fields.synthetic_les(nx=16, ny=12, nz=32, n_entries=3, seed=3, nLegendreCoefficients=16)
+    gas = d1.components[1]
+    prof2 = (gas.extinction[0, 0, :] * np.linspace(3.0, 0.5, 32)).astype(np.float32)  # another k-term
+    d2 = fields.synthetic_les(nx=16, ny=12, nz=32, n_entries=3, seed=3, nLegendreCoefficients=16)
+    replaceOpticalComponent(d2, 2, gas.name, prof2, gas.singleScatteringAlbedo[0, 0, :], gas.phaseFunctionIndex[0, 0, :], gas.table)
+    A = make_integrator(cuda, d1, **params)
+    setComponentProfile(A, 2, prof2)          # swapped on the device
+    B = make_integrator(cuda, d2, **params)   # built from the modified domain
+    rng = np.random.default_rng(5)
+    n = 200
+    hi = np.array([d1.xPosition[-1], d1.yPosition[-1], d1.zPosition[-1]], np.float64)
+    pos = ((0.02 + 0.96 * rng.random((n, 3))) * hi).astype(np.float32)
+    mu = rng.uniform(0.2, 1.0, n) * rng.choice([-1, 1], n)
+    phi = rng.uniform(0, 2 * np.pi, n)
+    u = np.column_stack([np.sqrt(1 - mu**2) * np.cos(phi), np.sqrt(1 - mu**2) * np.sin(phi), mu]).astype(np.float32)
+    ta, _, _ = traceRays(A, pos, u)
+    tb, _, _ = traceRays(B, pos, u)
+    assert np.allclose(ta, tb, rtol=2e-6, atol=1e-7)
+    ra, rb = run_batches(A, 20000, 8), run_batches(B, 20000, 8)  # same seeds, same photons up to float rounding of the field
+    for k in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed", "meanIntensity"):
+        assert np.allclose(ra[k].mean(0), rb[k].mean(0), rtol=5e-3, atol=2e-4), k
+    assert abs(ra["counters"]["collisions"] - rb["counters"]["collisions"]) < 0.01 * rb["counters"]["collisions"]
+    ref = oracle_summary(make_integrator(oracle, d2, **params), 20000, 16)
+    got = run_batches(A, 20000, 16)
+    assert_statistical_parity(got, ref, keys=["meanFluxUp", "meanFluxDown", "meanFluxAbsorbed", "meanIntensity"], label="swapped profile: ")
+    st = ErrorMessage()
+    setComponentProfile(A, 5, prof2, status=st)
+    assert stateIsFailure(st) and "no such component" in getCurrentMessage(st)
+
+
+@pytest.mark.gpu
+def test_spectral_band_loop(cuda):
+    from i3rc_monte_carlo_model_b200.driver import run_batches_device, device_stats_report, run_spectral_bands
+    d = fields.synthetic_les(nx=16, ny=12, nz=32, n_entries=3, seed=3, nLegendreCoefficients=16)
+    gas = d.components[1].extinction[0, 0, :].copy()
+    I = make_integrator(cuda, d, surfaceAlbedo=0.1, intensityMus=[1.0], intensityPhis=[0.0])
+    src = dict(solarMu=0.6, solarAzimuth=10.0)
+    bands = [(0.5, gas * 0.2), (0.3, gas * 1.0), (0.2, gas * 6.0)]
+    tot = run_spectral_bands(I, src, 40000, 8, 2, bands, iseed=3)
+    # the same three terms one by one, combined by hand
+    want = 0.0
+    absorbed = []
+    for k, (w, prof) in enumerate(bands):
+        from i3rc_monte_carlo_model_b200.monteCarloRadiativeTransfer import setComponentProfile
+        setComponentProfile(I, 2, prof)
+        run_batches_device(I, src, 40000, range(1 + 8 * k, 9 + 8 * k), iseed=3)
+        st = device_stats_report(I, 1.0, 8)
+        want = want + w * st["meanFluxUp"][0]
+        absorbed.append(float(st["meanFluxAbsorbed"][0]))
+    assert float(tot["meanFluxUp"][0]) == pytest.approx(float(want), rel=1e-6)
+    assert absorbed[0] < absorbed[1] < absorbed[2]  # more gas, more absorption
+    assert 0 < float(tot["meanFluxUp"][1]) < 5e-3
