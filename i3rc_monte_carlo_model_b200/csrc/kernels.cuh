@@ -13,15 +13,16 @@ namespace i3rc {
 
 // ---- K1: persistent, warp-cooperative photon transport ---------------------------------------------------------
 // grid = (#SMs x resident blocks).  Lanes are NOT tied to photons.  Every warp owns, in shared memory,
-//   * a pool of NSLOT photon slots (position, direction, weight, Philox counter: 52 bytes each),
+//   * a pool of NSLOT photon slots (position, direction, weight, Philox counter, raw end of the last segment: 56 bytes),
 //   * a ring of QCAP ray TASKS (40 bytes each): a photon's next path segment, or one local-estimate ray,
 //   * the list of slots whose path segment has ended and whose event (boundary / collision) is due,
 // and alternates, as a warp-uniform state machine, between
-//   TRACE rounds:  STEPS cell crossings for every lane that holds a ray; then, for all lanes at once, finished rays are
-//                  closed (a segment's end point goes back to its slot, which joins the event list; a local-estimate
-//                  ray is tallied) and idle lanes pop the next tasks from the ring;
-//   EVENT batches: when 32 events are due (or the ring has run dry) lane i takes the i-th due slot: boundary or
-//                  collision handling, then a warp-uniform loop over the radiance directions in which every lane
+//   TRACE rounds:  up to STEPS cell crossings for every lane that holds a ray (the round ends early when fewer than
+//                  minRunning lanes still run); then, for all lanes at once, finished rays are closed (a segment's raw
+//                  ray goes back to its slot, which joins the event list; a local-estimate ray is tallied) and idle
+//                  lanes pop the next tasks from the ring;
+//   EVENT batches: when 32 events are due (or the ring has run dry and at most lowWater lanes trace) lane i takes the
+//                  i-th due slot: the raw ray becomes the event point, boundary or collision handling, then a warp-uniform loop over the radiance directions in which every lane
 //                  turns its local-estimate ray into a task, then roulette + scattering, refill of dead slots from the
 //                  device photon counter (one warp-aggregated atomicAdd), and the task of the next path segment.
 // So both the cell-crossing loop and the event code run with (nearly) full warps, whatever the individual photons do.
@@ -31,7 +32,7 @@ namespace i3rc {
 template <int NSLOT>
 struct SlotPool {  // structure of arrays: lane i touches slot[k] of every array
   uint32_t xy[NSLOT];   // cx | cy << 16
-  uint32_t zs[NSLOT];   // cz | segDone << 16
+  uint32_t zs[NSLOT];   // cz | segDone << 16 (| SLOT_RAW: xy / zs / f* hold the raw ray, see below)
   float fx[NSLOT], fy[NSLOT], fz[NSLOT];
   float ux[NSLOT + MAX_DIRS], uy[NSLOT + MAX_DIRS], uz[NSLOT + MAX_DIRS];  // [NSLOT + d]: radiance direction d
   float w[NSLOT];
