@@ -406,6 +406,7 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
   p.esx = h->ny * (h->nzc ? h->nzc : h->nz);
   p.esy = h->nzc ? h->nzc : h->nz;
   p.esz = 1;
+  p.extN = (long long)h->nx * h->ny * (h->nzc ? h->nzc : h->nz);
   p.cumExt = h->d_cum;
   p.ssa = h->d_ssa;
   p.pfIdx = h->d_pf;

@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
     const unsigned ms = __ballot_sync(full, segEnd);
     if (segEnd) pend[npend + __popc(ms & lt)] = (uint8_t)s_ray[warp][1][lane];
     npend += __popc(ms);
+    I3RC_ASSERT(R, npend <= NSLOT && tail - head <= QCAP && tail - head >= 0);
     // idle lanes take the next tasks
     const bool idle = R.done == DONE_IDLE;
     const unsigned mi = __ballot_sync(full, idle);
@@ -356,6 +357,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
       const LeTask t = q[(head + rank) & (QCAP - 1)];
       const int mode = (int)((t.zdmc >> 21) & 7u);
       const int j = mode == MODE_PHOTON ? __float_as_int(t.cw) : NSLOT + (int)((t.zdmc >> 16) & 31u);
+      I3RC_ASSERT(R, j >= 0 && j < NSLOT + MAX_DIRS && (int)(t.xy & 0xffffu) < p.nx && (int)(t.xy >> 16) < p.ny &&
+                         (int)(t.zdmc & 0xffffu) < p.nz);
       const float ux = pool.ux[j], uy = pool.uy[j], uz = pool.uz[j];
       uint32_t* rv = s_ray[warp][0] + lane;
       rv[0] = t.zdmc >> 16;  // d | mode << 5 | comp << 8

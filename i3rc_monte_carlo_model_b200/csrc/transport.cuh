@@ -52,6 +52,14 @@ struct int2 {  // (the CUDA vector type, for the CPU build of this header)
 };
 #endif
 
+// Build with -DI3RC_CHECK to turn the index invariants of the transport code into run-time checks: a violated check
+// counts as a "bad" photon (counter CNT_BAD, which the test-suite requires to be zero) instead of touching memory.
+#ifdef I3RC_CHECK
+#define I3RC_ASSERT(L, cond) (!(cond) ? (void)I3RC_COUNT(L, CNT_BAD, 1) : (void)0)
+#else
+#define I3RC_ASSERT(L, cond) ((void)0)
+#endif
+
 namespace i3rc {
 
 constexpr int MAX_DIRS = 32;
@@ -100,6 +108,7 @@ struct Problem {
   // of the other fields.
   const float* ext;
   int esx, esy, esz;
+  long long extN;  // number of elements of ext (checked builds)
   // Horizontally uniform layers (clear air or gas only, above and below the clouds of a typical domain) need no 3-D
   // storage: when nzc > 0 the field holds only the nzc layers that vary horizontally, ext[(ix*ny + iy)*nzc + k], and
   // zlut[iz] = { k, or -1 for a uniform layer ; bits of the uniform layer's extinction }; esz stays 1, so the cell index
@@ -150,6 +159,15 @@ I3RC_HD int ext_index(const Problem& p, int ix, int iy, int iz) { return ix * p.
 // extinction of layer iz of the column whose index (ext_index) is idx
 template <class P>
 I3RC_HD float ext_gather(const P& p, int idx, int iz) {
+#ifdef I3RC_CHECK
+  {
+    const long long at = (!P::kSplit || p.nzc == 0) ? idx : (long long)(idx - iz) + (iz >= 0 && iz < p.nz ? (p.zlut[iz].x >= 0 ? p.zlut[iz].x : 0) : -1);
+    if (iz < 0 || iz >= p.nz || at < 0 || at >= p.extN) {
+      atomicAdd(p.counters + CNT_BAD, 1ull);
+      return 0.0f;
+    }
+  }
+#endif
   if (!P::kSplit || p.nzc == 0) return I3RC_LDG(p.ext + idx);
 #ifdef __CUDA_ARCH__
   const int2 t = __ldg(p.zlut + iz);

@@ -68,7 +68,7 @@ static void fill(const HostSimArgs* a, Problem& p, std::vector<TableDesc>& td, s
   p.x0 = a->xe[0]; p.y0 = a->ye[0]; p.z0 = a->ze[0];
   p.xmax = a->xe[a->nx]; p.ymax = a->ye[a->ny]; p.zmax = a->ze[a->nz];
   p.dx = a->xe[1] - a->xe[0]; p.dy = a->ye[1] - a->ye[0]; p.dz = a->ze[1] - a->ze[0];
-  p.ext = a->ext; p.esx = 1; p.esy = a->nx; p.esz = a->nx * a->ny; p.zlut = nullptr; p.nzc = 0; p.cumExt = a->cum; p.ssa = a->ssa; p.pfIdx = a->pf;
+  p.ext = a->ext; p.esx = 1; p.esy = a->nx; p.esz = a->nx * a->ny; p.zlut = nullptr; p.nzc = 0; p.extN = (long long)a->nx * a->ny * a->nz; p.cumExt = a->cum; p.ssa = a->ssa; p.pfIdx = a->pf;
   size_t ncell = (size_t)a->nx * a->ny * a->nz;
   float mx = 0.0f;
   for (size_t i = 0; i < ncell; i++) mx = a->ext[i] > mx ? a->ext[i] : mx;
