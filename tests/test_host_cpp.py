@@ -163,3 +163,44 @@ def test_cpp_planeParallel_matches_the_python_mirror(tmp_path, hostbin, cuda, di
         for col, key in ((4, "fluxUp"), (5, "fluxDown"), (8, "fluxAbsorbed")):
             assert float(vals[col]) == pytest.approx(np.mean([pb[key] for pb in per_batch]), abs=1.5e-5), key
         assert abs(float(vals[4]) + float(vals[5]) + float(vals[8]) - 1.0) < 0.01
+
+
+@pytest.mark.gpu
+def test_cpp_monteCarloDriver_two_components_with_volume_absorption(tmp_path, hostbin, cuda):
+    """A cloud component that does not fill the column (zLevelBase > 1) plus a horizontally uniform gas component, volume
+    absorption reported: the C++ driver and the Python driver write the same files."""
+    from i3rc_monte_carlo_model_b200.driver import monteCarloDriver
+    dom = str(tmp_path / "les.dom")
+    fileIO.write_Domain(fields.synthetic_les(nx=12, ny=8, nz=24, n_entries=3, seed=4, nLegendreCoefficients=16), dom)
+    nml_text = NML.replace("reportVolumeAbsorption = .false.", "reportVolumeAbsorption = .true.").replace(
+        'outputAbsProfFile = "{out}/prof.txt",', 'outputAbsProfFile = "{out}/prof.txt", outputAbsVolumeFile = "{out}/vol.txt",')
+    outs = {}
+    for who in ("py", "cpp"):
+        out = tmp_path / who
+        out.mkdir()
+        nml = tmp_path / f"{who}.nml"
+        nml.write_text(nml_text.format(dom=dom, out=str(out)))
+        if who == "py":
+            monteCarloDriver(str(nml), backend=cuda, verbose=False)
+        else:
+            r = subprocess.run([hostbin("monteCarloDriver"), str(nml)], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+        outs[who] = out
+    for name in ("flux.txt", "rad.txt", "prof.txt", "vol.txt"):
+        a, b = open(outs["py"] / name).read().splitlines(), open(outs["cpp"] / name).read().splitlines()
+        assert len(a) == len(b) and a[:8] == b[:8], name
+        # numbers: float32 atomic tallies of two runs agree to summation order, i.e. to the last printed digit or so
+        for la, lb in zip(a[12:], b[12:]):
+            if la.startswith("!"):
+                assert la == lb
+                continue
+            import re  # the F9.4 values (coordinates are F7.3 and written without separators)
+            va, vb = (np.array(re.findall(r"-?\d+\.\d{4}(?!\d)", t), float) for t in (la, lb))
+            assert va.size == vb.size and va.size >= 2 and np.allclose(va, vb, atol=2.1e-4), (name, la, lb)
+    vol = open(outs["cpp"] / "vol.txt").read().splitlines()
+    assert len(vol) == 10 + 12 * 8 * 24 and vol[7] == "!  Output_Type= Volume Absorption "
+    fb = netcdf_file(str(outs["cpp"] / "results.nc"), "r", mmap=False)
+    assert fb.variables["absorbedVolume"].dimensions == ("z", "y", "x") and fb.variables["absorbedVolume"].shape == (24, 8, 12)
+    fa = netcdf_file(str(outs["py"] / "results.nc"), "r", mmap=False)
+    assert np.allclose(np.array(fa.variables["absorbedVolume"][:]), np.array(fb.variables["absorbedVolume"][:]), rtol=1e-3, atol=1e-7)
+    fa.close(), fb.close()
