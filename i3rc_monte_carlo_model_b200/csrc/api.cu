@@ -448,6 +448,8 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
 int validate_source(i3rc_integrator* h, const i3rc_photon_source* s) {
   if (!s) return fail(h, "getNextPhoton: photons have not been initialized.");
   if (s->numberOfPhotons <= 0) return fail(h, "setIllumination: must ask for non-negative number of photons.");
+  if (s->numberOfPhotons > 0x7fffffffLL)  // numberOfPhotons is a default integer in the reference; photon ids travel as 32 bits
+    return fail(h, "setIllumination: at most 2^31-1 photons per batch (use more batches).");
   switch (s->kind) {
     case I3RC_SRC_DIRECTIONAL:
     case I3RC_SRC_SPOTLIGHT:
