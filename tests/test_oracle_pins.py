@@ -271,3 +271,58 @@ def test_roulette_zeroes_downward_radiance_quirk_Q4(oracle):
                         useRussianRouletteForIntensity=True, zetaMin=0.3)
     r = run_batches(I, 5000, 2)
     assert np.all(r["meanIntensity"] == 0)
+
+
+def _independent_slab_mc(tau, ssa, g, mu0, albedo, n, seed):
+    """An independent plane-parallel Monte Carlo (numpy, float64, analytic Henyey-Greenstein sampling, textbook
+    rotation of the direction) with the reference's tally definitions: fluxUp = weight leaving the top, fluxDown =
+    weight arriving at the surface (every arrival), fluxAbsorbed = weight lost at collisions; no roulette."""
+    rng = np.random.default_rng(seed)
+    z = np.full(n, tau)                      # optical height above the surface
+    mu = np.full(n, -mu0)
+    phi = np.zeros(n)
+    w = np.ones(n)
+    alive = np.ones(n, bool)
+    up = down = absorbed = 0.0
+    while alive.any():
+        i = np.flatnonzero(alive)
+        s = -np.log(1.0 - rng.random(i.size))
+        znew = z[i] + mu[i] * s
+        out_top = znew >= tau
+        hit = znew <= 0.0
+        up += w[i[out_top]].sum()
+        alive[i[out_top]] = False
+        j = i[hit]                           # Lambertian reflection
+        down += w[j].sum()
+        w[j] *= albedo
+        z[j] = 0.0
+        mu[j] = np.sqrt(rng.random(j.size))
+        phi[j] = 2 * np.pi * rng.random(j.size)
+        alive[j[w[j] <= 0]] = False
+        k = i[~out_top & ~hit]               # collisions
+        z[k] = znew[~out_top & ~hit]
+        absorbed += (w[k] * (1 - ssa)).sum()
+        w[k] *= ssa
+        xi = rng.random(k.size)
+        cost = (1 + g * g - ((1 - g * g) / (1 - g + 2 * g * xi)) ** 2) / (2 * g)
+        psi = 2 * np.pi * rng.random(k.size)
+        sint, mu_k = np.sqrt(np.maximum(0, 1 - cost**2)), mu[k]
+        sin0 = np.sqrt(np.maximum(1e-300, 1 - mu_k**2))
+        mu[k] = np.clip(mu_k * cost + sin0 * sint * np.cos(psi), -1, 1)  # (azimuth is irrelevant in a slab)
+        alive[k[w[k] < 1e-12]] = False
+    return up / n, down / n, absorbed / n
+
+
+@pytest.mark.parametrize("tau,ssa,albedo", [(1.0, 1.0, 0.0), (4.0, 0.9, 0.3)])
+def test_multiple_scattering_slab_against_an_independent_monte_carlo(oracle, tau, ssa, albedo):
+    """The whole chain of the oracle (inverse-table sampling, Marchuk rotation, ray tracing, surface reflection, implicit
+    capture, roulette) against an independent textbook Monte Carlo of the same slab."""
+    from tests.cases import make_integrator, run_batches, mean_se
+    d = fields.plane_parallel(opticalDepth=tau, SSA=ssa, nLayers=3)
+    I = make_integrator(oracle, d, surfaceAlbedo=albedo)
+    r = run_batches(I, 20000, 12, source=dict(solarMu=0.5, solarAzimuth=0.0), want=["meanFluxUp", "meanFluxDown", "meanFluxAbsorbed"])
+    ind = np.array([_independent_slab_mc(tau, ssa, 0.85, 0.5, albedo, 40000, 100 + b) for b in range(6)])
+    for col, key in enumerate(("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed")):
+        m, s = mean_se(r[key])
+        mi, si = ind[:, col].mean(), ind[:, col].std(ddof=1) / np.sqrt(ind.shape[0])
+        assert abs(m - mi) <= 3.5 * np.hypot(s, si) + 1e-6, (key, m, mi, s, si)
