@@ -284,6 +284,7 @@ def _independent_slab_mc(tau, ssa, g, mu0, albedo, n, seed):
     w = np.ones(n)
     alive = np.ones(n, bool)
     up = down = absorbed = 0.0
+    nadir = 0.0  # weight leaving the top within the cone mu > 0.95
     while alive.any():
         i = np.flatnonzero(alive)
         s = -np.log(1.0 - rng.random(i.size))
@@ -291,6 +292,7 @@ def _independent_slab_mc(tau, ssa, g, mu0, albedo, n, seed):
         out_top = znew >= tau
         hit = znew <= 0.0
         up += w[i[out_top]].sum()
+        nadir += w[i[out_top]][mu[i[out_top]] > 0.95].sum()
         alive[i[out_top]] = False
         j = i[hit]                           # Lambertian reflection
         down += w[j].sum()
@@ -310,7 +312,7 @@ def _independent_slab_mc(tau, ssa, g, mu0, albedo, n, seed):
         sin0 = np.sqrt(np.maximum(1e-300, 1 - mu_k**2))
         mu[k] = np.clip(mu_k * cost + sin0 * sint * np.cos(psi), -1, 1)  # (azimuth is irrelevant in a slab)
         alive[k[w[k] < 1e-12]] = False
-    return up / n, down / n, absorbed / n
+    return up / n, down / n, absorbed / n, nadir / n
 
 
 @pytest.mark.parametrize("tau,ssa,albedo", [(1.0, 1.0, 0.0), (4.0, 0.9, 0.3)])
@@ -326,3 +328,21 @@ def test_multiple_scattering_slab_against_an_independent_monte_carlo(oracle, tau
         m, s = mean_se(r[key])
         mi, si = ind[:, col].mean(), ind[:, col].std(ddof=1) / np.sqrt(ind.shape[0])
         assert abs(m - mi) <= 3.5 * np.hypot(s, si) + 1e-6, (key, m, mi, s, si)
+
+
+def test_nadir_radiance_normalisation_against_photon_binning(oracle):
+    """The local estimate's normalisation (P/(4 pi |mu|), MCRT:1509; radiance per unit incident flux on the horizontal) against
+    plain binning of the photons that leave an independent slab Monte Carlo within 18 degrees of the zenith:
+    <I> ~ weight / (N * <mu> * solid angle), compared with the azimuthal mean of the oracle's radiances in the middle of that
+    cone (the radiance varies by some 20 % across the cone, so the match is to a few percent)."""
+    from tests.cases import make_integrator, run_batches, mean_se
+    d = fields.plane_parallel(opticalDepth=2.0, SSA=1.0, nLayers=2)
+    phis = [0.0, 60.0, 120.0, 180.0, 240.0, 300.0]
+    I = make_integrator(oracle, d, surfaceAlbedo=0.0, intensityMus=[0.975] * 6, intensityPhis=phis, useRussianRouletteForIntensity=False)
+    r = run_batches(I, 20000, 8, source=dict(solarMu=0.5, solarAzimuth=0.0), want=["meanIntensity"])
+    per_batch = r["meanIntensity"].mean(axis=1)  # azimuthal mean, per batch
+    m, s = per_batch.mean(), per_batch.std(ddof=1) / np.sqrt(per_batch.size)
+    ind = np.array([_independent_slab_mc(2.0, 1.0, 0.85, 0.5, 0.0, 150000, 200 + b)[3] for b in range(4)])
+    binned = ind / (0.975 * 2 * np.pi * 0.05)  # <mu> = 0.975 over mu in (0.95, 1]; solid angle 2 pi * 0.05
+    bm, bs = binned.mean(), binned.std(ddof=1) / 2.0
+    assert abs(m - bm) <= 0.03 * bm + 3 * np.hypot(s, bs), (m, s, bm, bs)
