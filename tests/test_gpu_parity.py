@@ -489,3 +489,17 @@ def test_spectral_band_loop(cuda):
     assert float(tot["meanFluxUp"][0]) == pytest.approx(float(want), rel=1e-6)
     assert absorbed[0] < absorbed[1] < absorbed[2]  # more gas, more absorption
     assert 0 < float(tot["meanFluxUp"][1]) < 5e-3
+
+
+@pytest.mark.parametrize("case", ["stepCloud", "lesTwoComponents"])
+def test_translation_invariance_of_the_periodic_domain(cuda, case):
+    """Shifting a periodic domain shifts the per-column fluxes and radiances (indexing, wrap-around, exit columns)."""
+    from tests.cases import assert_translation_invariance
+    if case == "stepCloud":
+        d, k = fields.step_cloud(0.99), (5, 0)
+    else:
+        d, k = fields.synthetic_les(nx=16, ny=12, nz=24, n_entries=3, seed=9, nLegendreCoefficients=16), (7, 5)
+    assert_translation_invariance(cuda, d, k[0], k[1],
+                                  dict(surfaceAlbedo=0.2, intensityMus=[1.0, 0.5, -0.7], intensityPhis=[0.0, 200.0, 90.0],
+                                       useRussianRouletteForIntensity=False),
+                                  100000, 16, source=dict(solarMu=0.5, solarAzimuth=30.0))

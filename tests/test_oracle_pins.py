@@ -346,3 +346,10 @@ def test_nadir_radiance_normalisation_against_photon_binning(oracle):
     binned = ind / (0.975 * 2 * np.pi * 0.05)  # <mu> = 0.975 over mu in (0.95, 1]; solid angle 2 pi * 0.05
     bm, bs = binned.mean(), binned.std(ddof=1) / 2.0
     assert abs(m - bm) <= 0.03 * bm + 3 * np.hypot(s, bs), (m, s, bm, bs)
+
+
+def test_translation_invariance_of_the_periodic_domain(oracle):
+    from tests.cases import assert_translation_invariance
+    assert_translation_invariance(oracle, fields.step_cloud(0.99), 5, 0,
+                                  dict(surfaceAlbedo=0.2, intensityMus=[1.0, 0.5], intensityPhis=[0.0, 180.0], useRussianRouletteForIntensity=False),
+                                  6000, 12, source=dict(solarMu=0.5, solarAzimuth=0.0))
