@@ -10,6 +10,15 @@ quoted on), including normalisation and the batch-moment update.  Ranks are inde
 Example-Drivers/monteCarloDriver.f95:264-274, weak scaling); the only collective is ONE all-reduce of the packed
 moment buffer after the last step.
 
+    python bench.py --scaling strong --gpus N ...            (fixed total work: --total-batches batches shared by the
+                                                              ranks; domain setup and the all-reduce inside the clock)
+
+Roofline: the gathers of the cell-crossing loop come out of L2 on C1-C4 (fields <= 40 MB), so the
+ceiling is the L2 random-gather rate MEASURED in this run (i3rc_measure_gather_rate over 8 MB), HBM only when the gather
+field does not fit L2; the issue-slot ceiling (i3rc_measure_issue_rate) is reported beside it, and one launch of the
+transport kernel is re-run under `ncu` by this script (a separate short process, after the timed region) for the DRAM
+traffic, executed instructions and hit rates of the very build that was timed.
+
 Timing: every step is bracketed by CUDA events on the stream the kernels are launched on; L2 is flushed (256 MiB
 memset) between steps outside the brackets; a barrier + synchronize surrounds the K steps; the slowest rank counts.
 One JSON line is printed by rank 0.
@@ -137,15 +146,17 @@ def timing_of(be, I):
 
 
 # ---- the CPU arm ------------------------------------------------------------------------------------------------
-def cpu_port_rate(wl, seconds, threads=0, nbatches=None):
+def cpu_port_rate(wl, seconds, threads=0, nbatches=None, fast=True):
     """Photons/s of the oracle port (OpenMP threads stand in for MPI ranks, one batch per thread at a time) on a
-    bounded sample of the workload; returns (rate, cores, description, elapsed)."""
-    from oracle.binding import oracle_backend, run_batches
+    bounded sample of the workload; returns (rate, cores, description, elapsed).  fast: the -O3 -march=native build of
+    the same source, compiled on this machine (BASELINE.md section 3's flags for the CPU arm); else the parity build
+    (-O2 -ffp-contract=off)."""
+    from oracle.binding import fast_oracle_backend, oracle_backend, run_batches
     from i3rc_monte_carlo_model_b200.monteCarloIllumination import new_PhotonStream
     from i3rc_monte_carlo_model_b200.monteCarloRadiativeTransfer import (computeRadiativeTransfer, new_Integrator,
                                                                         specifyParameters)
     from i3rc_monte_carlo_model_b200.RandomNumbers import new_RandomNumberSequence
-    be = oracle_backend()
+    be = fast_oracle_backend() if fast else oracle_backend()
     cores = threads or os.cpu_count() or 1
     I = new_Integrator(wl["domain"](), backend=be)
     specifyParameters(I, **wl["params"])
@@ -187,12 +198,78 @@ def run_reference(args, wl, emit):
         "config": {"workload": wl["workload"], "note": "the reference is Fortran 95 and cannot be compiled in this image (no "
                    "Fortran compiler, MPI or netCDF): this arm times the C restatement of its algorithm (oracle/, OpenMP "
                    "threads standing in for MPI ranks) on all host threads"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + " per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + " per step",
+                         "build": "gcc -O3 -march=native -fopenmp, compiled on this machine (oracle/Makefile target `fast`)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
     return 0
+
+
+# ---- one transport launch under ncu (a separate short process, after the timed region) -----------------------------
+NCU_METRICS = ["dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "smsp__inst_executed.sum",
+               "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+               "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "lts__t_sectors.sum",
+               "lts__t_sectors_srcunit_tex_op_read.sum"]
+NCU_EXTRA = ["l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
+             "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"]
+
+
+def probe_launch(args, wl):
+    """`bench.py --probe-launch`: set the workload up and trace two batches (the second one is what ncu captures)."""
+    from i3rc_monte_carlo_model_b200._lib import backend
+    from i3rc_monte_carlo_model_b200.monteCarloIllumination import new_PhotonStream
+    from i3rc_monte_carlo_model_b200.monteCarloRadiativeTransfer import new_Integrator, specifyParameters
+    be = backend()
+    assert be.set_device(0) == 0
+    I = new_Integrator(wl["domain"](), backend=be)
+    specifyParameters(I, **wl["params"])
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        assert be.set_tuning(I.handle, k.encode(), int(v)) == 0, kv
+    src = new_PhotonStream(numberOfPhotons=args.photons or wl["photons"], **wl["source"]).as_c()
+    assert be.stats_reset(I.handle, 0) == 0
+    for b in range(2):
+        assert be.run_batches(I.handle, C.byref(src), 10, 0, 1_000_000 + b, 1) == 0, I._msg()
+    be.synchronize(I.handle)
+    return 0
+
+
+def ncu_one_launch(args, nph, timeout=240):
+    """Metrics of ONE k_transport launch of this workload at this size, measured now with ncu on this GPU.  Returns a
+    dict (metric -> value, plus 'command') or None when ncu is not available / not permitted here."""
+    import csv
+    import shutil
+    if shutil.which("ncu") is None:
+        return None
+    cmd_tail = [sys.executable, os.path.abspath(__file__), "--probe-launch", "--workload", args.workload, "--photons", str(nph)]
+    if args.tune:
+        cmd_tail += ["--tune", args.tune]
+    for metrics in (NCU_METRICS + NCU_EXTRA, NCU_METRICS):
+        with tempfile.NamedTemporaryFile("r", suffix=".csv") as f:
+            cmd = ["ncu", "--metrics", ",".join(metrics), "--clock-control", "none", "-k", "regex:k_transport", "-s", "2", "-c", "1",
+                   "--csv", "--log-file", f.name] + cmd_tail  # (-s 2: the table-building photon and the warm-up batch)
+            try:
+                r = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout,
+                                   env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0")))
+            except Exception:
+                return None
+            out = {}
+            try:
+                rows = [ln for ln in open(f.name) if ln.startswith('"')]
+                for row in csv.DictReader(rows):
+                    try:
+                        out[row["Metric Name"]] = float(row["Metric Value"].replace(",", ""))
+                    except (KeyError, ValueError):
+                        pass
+                    out["kernel"] = row.get("Kernel Name", "")
+            except Exception:
+                out = {}
+            if r.returncode == 0 and "dram__bytes_read.sum" in out:
+                out["command"] = " ".join(cmd[:cmd.index("--log-file")] + cmd_tail[1:])
+                return out
+    return None
 
 
 # ---- the CUDA arm -------------------------------------------------------------------------------------------------
@@ -204,8 +281,15 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="landsat")
     ap.add_argument("--photons", type=int, default=0, help="photons per step (batch) and GPU")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: --steps batches IN TOTAL are shared by the ranks (monteCarloDriver.f95:264-274); domain setup, "
+                         "table building and the all-reduce are inside the clock")
+    ap.add_argument("--report-volume", action="store_true", help="keep batch moments of volumeAbsorption too "
+                    "(reportVolumeAbsorption: the all-reduce payload grows by 2 x 8 B per cell)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ncu", action="store_true", help="skip the ncu pass over one transport launch")
+    ap.add_argument("--probe-launch", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--tune", default="", help="key=value,... passed to i3rc_set_tuning")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON: anything libraries print there (e.g. NCCL's version banner) goes to stderr
@@ -217,6 +301,8 @@ def main():
         os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     wl = make_workload(args.workload)
+    if args.probe_launch:
+        return probe_launch(args, wl)
     if args.impl == "reference":
         return run_reference(args, wl, emit)
     args.warmup = max(args.warmup, 3)
@@ -243,31 +329,44 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        warm = torch.zeros(1, device="cuda", dtype=torch.float64)
+        dist.all_reduce(warm)  # communicator set-up (connections, buffers) is not part of any timed all-reduce below
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    strong = args.scaling == "strong"
     nph = args.photons or wl["photons"]
     K, W = args.steps, args.warmup
-    I = new_Integrator(wl["domain"](), backend=be)
+    domain = wl["domain"]()  # (building the synthetic field on the host is input preparation, outside every clock)
+    barrier()
+    t_setup0 = time.perf_counter()
+    I = new_Integrator(domain, backend=be)
     assert I.handle, "new_Integrator failed"
     specifyParameters(I, **wl["params"])
     for kv in filter(None, args.tune.split(",")):
         k, v = kv.split("=")
         assert be.set_tuning(I.handle, k.encode(), int(v)) == 0, kv
+    assert be.tabulate(I.handle) == 0, I._msg()
+    be.synchronize(I.handle)
+    setup_ms = (time.perf_counter() - t_setup0) * 1e3  # upload of the domain, gather field, phase-function tables
     src = new_PhotonStream(numberOfPhotons=nph, **wl["source"]).as_c()
     stream = torch.cuda.ExternalStream(be.stream(I.handle), device=torch.device("cuda", local))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    nB_total, mine = partition_batches(K * world, world, rank)  # rank r: batches r*K+1 .. (r+1)*K
+    with_volume = 1 if args.report_volume else 0
+    if strong:   # K batches in total, rank r takes its block of them
+        nB_total, mine = partition_batches(K, world, rank)
+    else:        # K batches per rank
+        nB_total, mine = partition_batches(K * world, world, rank)
     mine = list(mine)
 
     # ---- device-resident arm: photons generated, traced, normalised and folded into the moments on the GPU ----
-    assert be.stats_reset(I.handle, 0) == 0
+    assert be.stats_reset(I.handle, with_volume) == 0
     for w in range(W):
         assert be.run_batches(I.handle, C.byref(src), 10, 0, 1_000_000 + w, 1) == 0, I._msg()
-    assert be.stats_reset(I.handle, 0) == 0
+    assert be.stats_reset(I.handle, with_volume) == 0
     be.reset_timing(I.handle)
     sampler = ClockSampler(local)
     barrier()
@@ -288,43 +387,72 @@ def main():
         step_ms.append(e0.elapsed_time(e1))
         for k, v in getCounters(I).items():
             counters[k] += v
-    t_ar0 = time.perf_counter()
-    allreduce_device_stats(I, dist if world > 1 else None)  # the ONE collective of the job
+    # the ONE collective of the job, timed with CUDA events on torch's stream (where NCCL runs it)
     be.synchronize(I.handle)
-    allreduce_ms = (time.perf_counter() - t_ar0) * 1e3
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    allreduce_device_stats(I, dist if world > 1 else None)
+    a1.record()
+    a1.synchronize()
+    allreduce_ms = a0.elapsed_time(a1) if world > 1 else 0.0
+    stats_bytes = 0
+    if world > 1:
+        ptr, n = C.c_void_p(), C.c_int64()
+        be.stats_device_buffer(I.handle, C.byref(ptr), C.byref(n))
+        stats_bytes = 8 * n.value
     barrier()
     wall_ms = (time.perf_counter() - wall0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
     trace_ms, trace_launches, other_launches = timing_of(be, I)
-    dev_ms = float(sum(step_ms)) + allreduce_ms
+    dev_ms = float(sum(step_ms)) + allreduce_ms + (setup_ms if strong else 0.0)
     if world > 1:
-        t = torch.tensor([dev_ms, wall_ms, trace_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([dev_ms, wall_ms, trace_ms, setup_ms, allreduce_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall_ms, trace_ms_max = t.tolist()
+        dev_ms, wall_ms, trace_ms_max, setup_ms, allreduce_ms = t.tolist()
         cs = torch.tensor([counters[k] for k in _abi.COUNTER_FIELDS], device="cuda", dtype=torch.int64)
         dist.all_reduce(cs)
         counters_all = dict(zip(_abi.COUNTER_FIELDS, cs.tolist()))
     else:
         counters_all = counters
-    total_photons = nph * K * world
+    total_batches = nB_total if strong else K * world
+    total_photons = nph * total_batches
     value = total_photons / (dev_ms * 1e-3)
     stats = device_stats_report(I, 1.0, nB_total)
 
     # ---- end-to-end arm: the reference's own call sequence per batch with HOST buffers ----
+    # Every batch: the photon arrays of type(photonStream) are FILLED ON THE HOST (2 N uniform deviates, what the reference's
+    # new_PhotonStream does per batch, monteCarloDriver.f95:281 -> monteCarloIllumination.f95:91-95) -- by a pool of host
+    # threads, for batch b+1 while the GPU traces batch b (two sets of pinned buffers) --, handed to
+    # i3rc_computeRadiativeTransfer (host -> device copy inside), and the results are read back into host arrays.
+    # Generation, copies, kernel and read-back are all inside the clock.
     e2e = None
-    if not args.no_e2e:
-        rng = np.random.default_rng(1234 + rank)
+    if not args.no_e2e and not strong:
+        from concurrent.futures import ThreadPoolExecutor
+        nthr = max(1, min(16, (os.cpu_count() or 2) // max(world, 1)))
+        pool = ThreadPoolExecutor(nthr)
+        seeds = np.random.SeedSequence(1234 + rank)
 
         def pinned(n):
             return torch.empty(n, dtype=torch.float32).pin_memory().numpy()
 
-        ph = new_PhotonStream(numberOfPhotons=nph, **wl["source"])
-        ph.xPosition, ph.yPosition, ph.zPosition, ph.initialMu, ph.initialPhi = (pinned(nph) for _ in range(5))
-        ph.xPosition[:] = rng.random(nph, dtype=np.float32)
-        ph.yPosition[:] = rng.random(nph, dtype=np.float32)
-        ph.zPosition[:] = np.float32(1.0) - np.finfo(np.float32).eps
-        ph.initialMu[:] = -abs(wl["source"].get("solarMu", 0.5))
-        ph.initialPhi[:] = np.float32(wl["source"].get("solarAzimuth", 0.0) * np.pi / 180.0)
+        def new_stream():
+            ph = new_PhotonStream(numberOfPhotons=nph, **wl["source"])
+            ph.xPosition, ph.yPosition, ph.zPosition, ph.initialMu, ph.initialPhi = (pinned(nph) for _ in range(5))
+            ph.zPosition[:] = np.float32(1.0) - np.finfo(np.float32).eps
+            ph.initialMu[:] = -abs(wl["source"].get("solarMu", 0.5))
+            ph.initialPhi[:] = np.float32(wl["source"].get("solarAzimuth", 0.0) * np.pi / 180.0)
+            return ph
+
+        def fill(ph, batch):  # x, y ~ U(0,1): one slice per host thread, independent generator streams
+            gens = [np.random.default_rng(s) for s in seeds.spawn(nthr)]
+            cuts = np.linspace(0, nph, nthr + 1).astype(np.int64)
+
+            def part(i):
+                gens[i].random(out=ph.xPosition[cuts[i]:cuts[i + 1]], dtype=np.float32)
+                gens[i].random(out=ph.yPosition[cuts[i]:cuts[i + 1]], dtype=np.float32)
+            return [pool.submit(part, i) for i in range(nthr)]
+
+        phs = [new_stream(), new_stream()]
         want = ["meanFluxUp", "meanFluxDown", "meanFluxAbsorbed", "fluxUp", "fluxDown", "fluxAbsorbed", "absorbedProfile",
                 "meanIntensity", "intensity"]
         out = {"fluxUp": pinned(I.nx * I.ny).reshape((I.nx, I.ny), order="F"),
@@ -334,21 +462,31 @@ def main():
         d2h = 4 * (3 * I.nx * I.ny + I.nz + I.nx * I.ny * I.nDir + 3 + I.nDir) + C.sizeof(_abi.Counters)
         h2d = 5 * 4 * nph + C.sizeof(_abi.PhotonSource)
         for w in range(2):
-            computeRadiativeTransfer(I, new_RandomNumberSequence([11, 2_000_000 + w]), ph)
+            for f in fill(phs[w], w):
+                f.result()
+            computeRadiativeTransfer(I, new_RandomNumberSequence([11, 2_000_000 + w]), phs[w])
         barrier()
         t0 = time.perf_counter()
-        for b in mine:
-            computeRadiativeTransfer(I, new_RandomNumberSequence([11, b]), ph)  # H2D of the photon arrays + kernel
-            r = reportResults(I, *want, out=out)                                # D2H into host arrays
+        pending = fill(phs[0], mine[0])
+        for i, b in enumerate(mine):
+            for f in pending:
+                f.result()
+            if i + 1 < len(mine):
+                pending = fill(phs[(i + 1) % 2], mine[i + 1])  # the next batch's photons, while this one is traced
+            computeRadiativeTransfer(I, new_RandomNumberSequence([11, b]), phs[i % 2])  # H2D of the photon arrays + kernel
+            r = reportResults(I, *want, out=out)                                        # D2H into host arrays
         be.synchronize(I.handle)
         el = time.perf_counter() - t0
+        pool.shutdown()
         if world > 1:
             t = torch.tensor([el], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             el = t.item()
         e2e = {"value": total_photons / el, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": el * 1e3 / K, "path": "new_PhotonStream arrays (host, pinned) -> i3rc_computeRadiativeTransfer -> "
-               "i3rc_reportResults into host arrays, per batch", "meanFluxUp_last": float(r["meanFluxUp"])}
+               "ms_per_step": el * 1e3 / K, "host_threads_filling_photon_arrays": nthr,
+               "path": "per batch: photon arrays of type(photonStream) filled on the host (2N uniform deviates, inside the clock, "
+               "overlapped with the previous batch's kernel) -> i3rc_computeRadiativeTransfer (host->device copy inside) -> "
+               "i3rc_reportResults into host arrays", "meanFluxUp_last": float(r["meanFluxUp"])}
     barrier()
 
     if rank != 0:
@@ -362,48 +500,95 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     nc = I.nc
     abytes = algorithmic_bytes(counters, nc)  # this rank's launches
     launches = max(trace_launches, 1)
-    achieved = abytes / launches / (trace_ms / launches * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "transport_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    kernel_s = trace_ms / launches * 1e-3
+    achieved = abytes / launches / kernel_s / 1e9
     crossings = counters["crossings_photon"] + counters["crossings_intensity"]
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+    ncell = I.nx * I.ny * I.nz
+    nzc = be.get_layout(I.handle, 0)
+    gather_field_bytes = 4 * I.nx * I.ny * (nzc if nzc > 0 else I.nz)
+    l2_resident = gather_field_bytes <= 96 * 2**20  # (126 MB L2; the other fields and tables share it)
+    # ceilings measured now, on this GPU: random 4-byte gathers over an L2-resident array and over 1 GiB; issue slots
+    g = C.c_double()
+    meas = {}
+    for name, nbytes in (("l2_8MB", 8 << 20), ("l2_field", max(1 << 20, min(gather_field_bytes, 64 << 20))), ("hbm_1GiB", 1 << 30)):
+        meas[name] = g.value if be.measure_gather_rate(nbytes, 3, C.byref(g)) == 0 else None
+    issue_peak = g.value if be.measure_issue_rate(3, C.byref(g)) == 0 else None
+    torch.cuda.synchronize()
+    ncu = None if (args.no_ncu or world > 1) else ncu_one_launch(args, nph)
+    traffic, traffic_source = None, None
+    if ncu:
+        scale = 1.0  # (the probe traces the same number of photons as a bench step)
+        traffic = (ncu["dram__bytes_read.sum"] + ncu["dram__bytes_write.sum"]) * scale
+        traffic_source = "ncu pass of this run: " + ncu["command"]
+    else:
+        tpath = os.path.join(ROOT, "profiles", "transport_traffic.json")
+        try:
+            ent = json.load(open(tpath)).get(args.workload, {})
+            traffic, traffic_source = ent.get("dram_bytes_per_launch"), "profiles/transport_traffic.json (" + ent.get("source", "") + ")"
+        except Exception:
+            pass
+    gather_peak = meas["l2_8MB"] if l2_resident else meas["hbm_1GiB"]
+    if gather_peak:
+        bound, peak, peak_source = ("l2" if l2_resident else "hbm"), gather_peak * 4 / 1e9, (
+            "measured in this run: random 4-byte gathers over " + ("8 MB (L2-resident)" if l2_resident else "1 GiB (HBM)") +
+            ", useful bytes (i3rc_measure_gather_rate)")
+    else:
+        bound, peak, peak_source = "hbm", hbm_peak, "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    issue = None
+    if issue_peak:
+        issue = {"peak_warp_inst_per_s": issue_peak, "peak_source": "measured in this run (independent FMAs, i3rc_measure_issue_rate); "
+                 "nominal 148 SMs x 4 schedulers x SM clock"}
+        if ncu and "smsp__inst_executed.sum" in ncu:
+            ach = ncu["smsp__inst_executed.sum"] / (ncu["gpu__time_duration.sum"] * 1e-9)
+            issue.update({"achieved_warp_inst_per_s": ach, "frac": ach / issue_peak,
+                          "issue_slots_busy_pct": ncu.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                          "active_threads_per_warp_inst": ncu.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                          "warp_inst_per_cell_crossing": ncu["smsp__inst_executed.sum"] / max(crossings / launches, 1.0)})
+    roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_source, "peak_source": peak_source,
                 "kernel": "k_transport", "kernel_ms_per_launch": trace_ms / launches, "kernel_share_of_step": trace_ms / max(sum(step_ms), 1e-9),
                 "algorithmic_bytes_per_launch": abytes / launches, "cell_crossings_per_s": crossings / (trace_ms * 1e-3),
                 "bytes_per_crossing_model": "4 B/crossing + (4nC+16) B/collision + 32 B/absorption + 24 B/contribution + 8 B/exit",
-                "note": ("fields are L2-resident on this workload (7.8 MB per field): the kernel is issue bound, not HBM bound"
-                         if args.workload != "les" else
-                         "268 MB extinction field of which only the 80 horizontally varying layers (84 MB) are stored in 3-D")}
+                "gather_field_bytes": gather_field_bytes, "layers_stored_in_3d": nzc if nzc > 0 else I.nz,
+                "measured_ceilings": {"gathers_per_s": meas, "hbm_copy_gbs": hbm_peak,
+                                      "frac_of_hbm_copy_peak": achieved / hbm_peak},
+                "issue": issue,
+                "ncu": {k: v for k, v in (ncu or {}).items() if k != "command"} or None,
+                "note": "the gathers of the cell-crossing loop are served by " + ("L2" if l2_resident else "HBM") +
+                        "; which ceiling binds is read from `frac` (gather rate) against `issue.frac` (instruction issue)"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rate, cores, sample, el = cpu_port_rate(wl, 15.0)
+        rate_parity, _, sample_p, _ = cpu_port_rate(wl, 5.0, fast=False)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "build": "gcc -O3 -march=native -fopenmp, compiled on this machine (oracle/Makefile target `fast`)",
+               "parity_build_value": rate_parity, "parity_build": "gcc -O2 -ffp-contract=off (the build the parity tests use); " + sample_p,
                "note": "C restatement of the reference (oracle/), OpenMP threads standing in for MPI ranks; the Fortran reference "
                        "cannot be built in this image"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic illumination (photons drawn on the device from Philox streams) on the I3RC field shipped as a fixture"
                 if args.workload in ("landsat", "radar") else "synthetic",
-        "config": {"workload": wl["workload"], "photons_per_step_per_gpu": nph, "parallelism": f"batches sharded over {world} GPU(s), "
-                   "replicated domain, one all-reduce of the moment buffer", "l2": "flushed between steps (256 MiB memset), "
-                   "flush outside the CUDA-event brackets", "timing": "sum of per-step CUDA-event times on the launching stream + final "
-                   "all-reduce, max over ranks", "tuning": args.tune or "default"},
+        "config": {"workload": wl["workload"], "photons_per_step_per_gpu": nph if not strong else None,
+                   "photons_per_batch": nph, "total_batches": total_batches,
+                   "parallelism": f"batches sharded over {world} GPU(s), replicated domain, one all-reduce of the moment buffer",
+                   "l2": "flushed between steps (256 MiB memset), flush outside the CUDA-event brackets",
+                   "timing": ("strong scaling: domain upload + gather field + tables (setup_ms) + sum of per-batch CUDA-event times + "
+                              "the all-reduce, max over ranks" if strong else
+                              "sum of per-step CUDA-event times on the launching stream + final all-reduce, max over ranks"),
+                   "allreduce_ms": allreduce_ms, "allreduce_bytes": stats_bytes, "setup_ms": setup_ms,
+                   "report_volume_absorption": bool(with_volume), "tuning": args.tune or "default"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(trace_launches + other_launches),
         "roofline": roofline, "cpu_baseline": cpu,
         "wall_ms_timed_region": wall_ms, "allreduce_ms": allreduce_ms,
-        "counters_per_photon": {k: v / (nph * K * world) for k, v in counters_all.items() if v},
+        "counters_per_photon": {k: v / total_photons for k, v in counters_all.items() if v},
         "results": {"meanFluxUp": [float(stats["meanFluxUp"][0]), float(stats["meanFluxUp"][1])],
                     "meanFluxDown": [float(stats["meanFluxDown"][0]), float(stats["meanFluxDown"][1])],
                     "meanRadiance": [[float(m), float(e)] for m, e in zip(np.ravel(stats["meanRadiance"][0]), np.ravel(stats["meanRadiance"][1]))]

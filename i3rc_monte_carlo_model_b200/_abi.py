@@ -221,9 +221,16 @@ class Backend:
             "get_timing": (ci, [vp, c_double_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
             "reset_timing": (ci, [vp]),
             "set_tuning": (ci, [vp, C.c_char_p, ci]),
+            "get_layout": (ci, [vp, ci]),
             "version": (C.c_char_p, []),
             "device_count": (ci, []),
             "set_device": (ci, [ci]),
+            "probe_philox": (ci, [C.c_uint32, C.c_uint32, ci, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
+                                  C.POINTER(C.c_uint32), c_float_p]),
+            "probe_next_direct": (ci, [C.c_uint32, C.c_uint32, ci, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), c_float_p,
+                                       c_float_p, c_float_p, C.POINTER(C.c_uint32)]),
+            "measure_gather_rate": (ci, [C.c_size_t, ci, c_double_p]),
+            "measure_issue_rate": (ci, [ci, c_double_p]),
         }
         for fn, (res, args) in sig.items():
             f = getattr(lib, prefix + fn)

@@ -61,10 +61,14 @@ struct i3rc_integrator {
   std::vector<float> xe, ye, ze;
   float *d_xe = nullptr, *d_ye = nullptr, *d_ze = nullptr;
   float *d_ext = nullptr, *d_cum = nullptr, *d_ssa = nullptr;
+  float* d_extRaw = nullptr;  // un-normalised extinction of every component (kept from the first profile swap on)
   float* d_extZ = nullptr;  // totalExt again, z-fastest: the copy the rays gather from (see Problem::ext)
   int2* d_zlut = nullptr;   // layer table when only the horizontally varying layers are stored (Problem::zlut)
   int nzc = 0;
   int* d_pf = nullptr;
+  bool absorbing = true;    // some cell of some component has ssa < 1 (else volumeAbsorption / fluxAbsorbed stay zero)
+  bool volAbsDirty = true;  // d_volAbs may hold non-zero values
+  std::vector<int> maxPfIndex;  // largest phaseFunctionIndex of each component (checked against its table before tracing)
   float maxExt = 0.0f;
   bool useSurfaceBDRF = false;
   int surf_nx = 0, surf_ny = 0;
@@ -115,6 +119,7 @@ struct i3rc_integrator {
   // tuning
   int blockSize = 128, blocksPerSM = 0, residentBlocks = 0, poolShape = 0, minRunning = 16, padSmem = 0, kSteps = 16;
   int eventThreshold = 16;
+  int stageTallies = 1536;  // floats of shared memory per warp for staged tallies (few-column domains); 0 = never
   int splitLayers = 1;  // (0 never, 1 large fields, 2 always) store only the horizontally varying layers of totalExt in 3-D when that pays (Problem::zlut)
   // nccl
   void* nccl = nullptr;
@@ -207,11 +212,19 @@ int ensure_fscratch(i3rc_integrator* h, size_t n) {
 // From the dense totalExt / cumulativeExt on the device: the last cumulative fraction nudged to 1 + epsilon and the
 // domain maximum of totalExt (MCRT:233-234), and the copy of totalExt the rays gather from (z-fastest; only the
 // horizontally varying layers when that pays, see Problem::zlut).  Also run after a component profile is replaced.
+struct DevTemp {  // a temporary device buffer that is freed on every path out of the scope
+  void* p = nullptr;
+  ~DevTemp() {
+    if (p) cudaFree(p);
+  }
+};
 int build_gather_field(i3rc_integrator* h) {
   const int nx = h->nx, ny = h->ny, nz = h->nz;
   size_t ncell = (size_t)nx * ny * nz;
+  DevTemp t_max, t_mm, t_layers;
   unsigned int* d_max = nullptr;
   CUDA_OK(h, cudaMalloc(&d_max, sizeof(unsigned int)));
+  t_max.p = d_max;
   CUDA_OK(h, cudaMemsetAsync(d_max, 0, sizeof(unsigned int), h->stream));
   k_bump_and_max<<<(unsigned)((ncell + 255) / 256), 256, 0, h->stream>>>(ncell, h->d_cum + (size_t)(h->nc - 1) * ncell,
                                                                         h->d_ext, d_max);
@@ -225,12 +238,12 @@ int build_gather_field(i3rc_integrator* h) {
     const size_t ncol = (size_t)nx * ny;
     unsigned int* d_mm = nullptr;
     CUDA_OK(h, cudaMalloc(&d_mm, sizeof(unsigned int) * 2 * nz));
+    t_mm.p = d_mm;
     k_layer_minmax<<<nz, 256, 0, h->stream>>>(h->d_ext, ncol, d_mm);
     h->otherLaunches++;
     std::vector<unsigned int> mm(2 * (size_t)nz);
     CUDA_OK(h, cudaMemcpyAsync(mm.data(), d_mm, sizeof(unsigned int) * mm.size(), cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
-    cudaFree(d_mm);
     std::vector<int2> lut(nz);
     std::vector<int> layers;
     for (int k = 0; k < nz; k++) {
@@ -247,13 +260,13 @@ int build_gather_field(i3rc_integrator* h) {
     if (ncol > 1 && nzc > 0 && nzc * 4 <= nz * 3 && h->splitLayers && big) {
       int* d_layers = nullptr;
       CUDA_OK(h, upload(&d_layers, layers.data(), layers.size(), h->stream));
+      t_layers.p = d_layers;
       CUDA_OK(h, upload(&h->d_zlut, lut.data(), lut.size(), h->stream));
       CUDA_OK(h, cudaMalloc(&h->d_extZ, sizeof(float) * ncol * nzc));
       dim3 b(32, 8), g((unsigned)((nx + 31) / 32), (unsigned)((nzc + 31) / 32), (unsigned)ny);
       k_compact_zfast<<<g, b, 0, h->stream>>>(nx, ny, nzc, d_layers, h->d_ext, h->d_extZ);
       h->otherLaunches++;
       CUDA_OK(h, cudaStreamSynchronize(h->stream));
-      cudaFree(d_layers);
       h->nzc = nzc;
     } else {
       CUDA_OK(h, cudaMalloc(&h->d_extZ, sizeof(float) * ncell));
@@ -265,7 +278,6 @@ int build_gather_field(i3rc_integrator* h) {
   unsigned int bits = 0;
   CUDA_OK(h, cudaMemcpyAsync(&bits, d_max, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
-  cudaFree(d_max);
   memcpy(&h->maxExt, &bits, sizeof(float));
   return I3RC_SUCCESS;
 }
@@ -315,6 +327,26 @@ i3rc_integrator* make_handle() {
   if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess) h->numSMs = prop.multiProcessorCount;
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   return h;
+}
+
+// the value checks of validateOpticalComponent (Code/opticalProperties.f95:966-975) on host arrays; the upper bound of the
+// phase function index is checked against the component's table (maxPf is kept for that)
+const char* validate_optical_arrays(const float* ext, const float* ssa, const int32_t* pf, size_t n, int* maxPf, bool* absorbs) {
+  bool badE = false, badS = false, badP = false, ab = false;
+  int mx = 0;
+  for (size_t i = 0; i < n; i++) {
+    badE |= !(ext[i] >= 0.0f);
+    badS |= !(ssa[i] >= 0.0f && ssa[i] <= 1.0f);
+    badP |= pf[i] < 0;
+    ab |= ext[i] > 0.0f && ssa[i] < 1.0f;
+    mx = pf[i] > mx ? pf[i] : mx;
+  }
+  *maxPf = mx;
+  *absorbs |= ab;
+  if (badE) return "validateOpticalComponent: extinction must be >= 0.";
+  if (badS) return "validateOpticalComponent: singleScatteringAlbedo must be between 0 and 1";
+  if (badP) return "validateOpticalComponent: phase function index is out of bounds";
+  return nullptr;
 }
 
 bool valid_edges(const float* e, int n) {
@@ -441,6 +473,24 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
   p.excess = h->d_excess;
   p.counters = h->d_counters;
   p.nextPhoton = h->d_next;
+  // Tallies staged in shared memory, one private copy per warp, when the domain has so few columns that the whole GPU
+  // would otherwise hammer a handful of addresses: fluxes and radiances, and the volume absorption too if it fits.
+  p.tsmN = 0;
+  for (int& o : p.tsmOff) o = -1;
+  {
+    const size_t ncol = (size_t)h->nx * h->ny, ncell = ncol * h->nz;
+    const size_t budget = (size_t)h->stageTallies;  // floats per warp (0 switches the staging off)
+    const size_t nInt = p.computeIntensity ? ncol * (size_t)p.nDir : 0;
+    if (3 * ncol + nInt <= budget) {
+      p.tsmOff[TAL_UP] = 0;
+      p.tsmOff[TAL_DOWN] = (int)ncol;
+      p.tsmOff[TAL_ABS] = (int)(2 * ncol);
+      size_t n = 3 * ncol;
+      if (nInt) p.tsmOff[TAL_INT] = (int)n, n += nInt;
+      if (n + ncell <= budget) p.tsmOff[TAL_VOL] = (int)n, n += ncell;
+      p.tsmN = (int)n;
+    }
+  }
 }
 
 // validation of a photon source: the checks of the new_PhotonStream constructors
@@ -531,11 +581,14 @@ int fill_source(i3rc_integrator* h, const i3rc_photon_source* s, SourceDev& d) {
   return I3RC_SUCCESS;
 }
 
-template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP>
+template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP, bool TSM = false>
 int launch_transport_t(i3rc_integrator* h, const Problem& p) {
+  auto kern = k_transport<BLOCK, REG, FAST, SPLIT, MINB, STEPS, NSLOT, QCAP, TSM>;
+  const size_t dynSmem = (size_t)h->padSmem + (TSM ? sizeof(float) * (BLOCK / 32) * (size_t)p.tsmN : 0);
+  if (dynSmem > 8192) CUDA_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynSmem));
   int perSM = h->blocksPerSM;
   if (perSM <= 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_transport<BLOCK, REG, FAST, SPLIT, MINB, STEPS, NSLOT, QCAP>, BLOCK, 0) != cudaSuccess || perSM <= 0)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, BLOCK, dynSmem) != cudaSuccess || perSM <= 0)
       perSM = 1;
   }
   long long want = (p.src.n + BLOCK - 1) / BLOCK;
@@ -544,7 +597,7 @@ int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   if (grid < 1) grid = 1;
   ProblemT<REG, FAST, SPLIT> pt;
   static_cast<Problem&>(pt) = p;
-  k_transport<BLOCK, REG, FAST, SPLIT, MINB, STEPS, NSLOT, QCAP><<<(unsigned)grid, BLOCK, (size_t)h->padSmem, h->stream>>>(pt, h->eventThreshold, h->minRunning);
+  kern<<<(unsigned)grid, BLOCK, dynSmem, h->stream>>>(pt, h->eventThreshold, h->minRunning);
   return I3RC_SUCCESS;
 }
 // MINB = resident blocks per SM the kernel is compiled for (register cap 65536 / (MINB * BLOCK));
@@ -561,6 +614,11 @@ int launch_transport(i3rc_integrator* h, const Problem& p) {
   const bool reg = p.xyRegular && p.zRegular;
   const bool fast = p.useRayTracing && p.src.kind != 5 && p.src.kind != 6 && !p.useSurfaceBDRF && !p.useHybrid && !p.limitContrib &&
                     !p.trackByComponent;
+  if (p.tsmN > 0) {  // a domain of a few columns: tallies staged per warp in shared memory (warp_tally, kernels.cuh)
+    if (reg && fast) return launch_transport_t<128, true, true, false, 5, 16, 64, 64, true>(h, p);
+    if (reg) return launch_transport_t<128, true, false, false, 5, 16, 64, 64, true>(h, p);
+    return launch_transport_t<128, false, false, false, 5, 16, 64, 64, true>(h, p);
+  }
   if (p.nzc) {  // only the horizontally varying layers are stored (large fields): the gathers look the layer up first
     if (reg && fast) return launch_transport_t<128, true, true, true, 5, 16, 64, 64>(h, p);
     if (reg) return launch_transport_t<128, true, false, true, 5, 16, 64, 64>(h, p);
@@ -594,7 +652,10 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
   CUDA_OK(h, cudaMemsetAsync(h->d_fluxUp, 0, sizeof(float) * ncol, h->stream));
   CUDA_OK(h, cudaMemsetAsync(h->d_fluxDown, 0, sizeof(float) * ncol, h->stream));
   CUDA_OK(h, cudaMemsetAsync(h->d_fluxAbs, 0, sizeof(float) * ncol, h->stream));
-  CUDA_OK(h, cudaMemsetAsync(h->d_volAbs, 0, sizeof(float) * ncell, h->stream));
+  // (nothing is absorbed in the volume when every component has ssa = 1 everywhere: the array stays zero from the last
+  // batch that could write it, and so do its normalisation and its share of the moments)
+  if (h->volAbsDirty) CUDA_OK(h, cudaMemsetAsync(h->d_volAbs, 0, sizeof(float) * ncell, h->stream));
+  h->volAbsDirty = h->absorbing;
   if (h->d_intensity) CUDA_OK(h, cudaMemsetAsync(h->d_intensity, 0, sizeof(float) * ncol * h->nDir, h->stream));
   if (h->d_intByComp && byComp)
     CUDA_OK(h, cudaMemsetAsync(h->d_intByComp, 0, sizeof(float) * ncol * h->nDir * (h->nc + 1), h->stream));
@@ -623,7 +684,9 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
   //    column and folded into float64 sums in between;
   //  * hand-filled photon arrays: the first tenth is copied, then traced while the rest is being copied.
   const long long n = src.n;
-  const long long perPiece = std::max<long long>(1 << 19, (long long)ncol << 20);
+  // (a spotlight or an internal source puts all photons into a few columns whatever the size of the domain)
+  const bool concentrated = src.kind == I3RC_SRC_SPOTLIGHT || src.kind == I3RC_SRC_INTERNAL_FLUX || src.kind == I3RC_SRC_INTERNAL_INTENSITY;
+  const long long perPiece = concentrated ? (1 << 22) : std::max<long long>(1 << 19, (long long)ncol << 20);
   const bool arrays = src.kind == I3RC_SRC_ARRAYS;
   std::vector<long long> cuts{0};
   if (arrays && n >= (1 << 20)) cuts.push_back(std::min<long long>(((n / 10 + 127) / 128) * 128, perPiece));
@@ -706,7 +769,7 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
   NormArgs a;
   a.nx = h->nx;
   a.ny = h->ny;
-  a.nz = h->nz;
+  a.nz = h->volAbsDirty ? h->nz : 0;  // (an all-zero volume absorption needs no normalisation)
   a.nDir = nD;
   a.nc = h->nc;
   a.xyRegular = h->xyRegular;
@@ -827,15 +890,27 @@ int i3rc_new_Integrator(int nx, int ny, int nz, int nc, const float* xPos, const
     g_message = "new_Integrator: Problems reading domain.";
     return I3RC_FAILURE;
   }
+  size_t ncell = (size_t)nx * ny * nz;
+  std::vector<int> maxPf(nc, 0);
+  bool absorbs = false;
+  for (int c = 0; c < nc; c++) {  // (the dense form has cumulative fractions instead of extinctions: checked against totalExt)
+    const char* bad = validate_optical_arrays(totalExt, ssa + c * ncell, pfIndex + c * ncell, ncell, &maxPf[c], &absorbs);
+    if (bad) {
+      g_message = bad;
+      return I3RC_FAILURE;
+    }
+  }
   i3rc_integrator* h = make_handle();
   h->nx = nx;
   h->ny = ny;
   h->nz = nz;
   h->nc = nc;
+  h->maxPfIndex = maxPf;
+  h->absorbing = absorbs;
+  h->absorbing = absorbs;
   h->xe.assign(xPos, xPos + nx + 1);
   h->ye.assign(yPos, yPos + ny + 1);
   h->ze.assign(zPos, zPos + nz + 1);
-  size_t ncell = (size_t)nx * ny * nz;
   int rc = I3RC_SUCCESS;
   if (upload(&h->d_ext, totalExt, ncell, h->stream) != cudaSuccess || upload(&h->d_cum, cumExt, ncell * nc, h->stream) != cudaSuccess ||
       upload(&h->d_ssa, ssa, ncell * nc, h->stream) != cudaSuccess || upload(&h->d_pf, pfIndex, ncell * nc, h->stream) != cudaSuccess)
@@ -868,11 +943,24 @@ int i3rc_new_Integrator_components(int nx, int ny, int nz, const float* xPos, co
       g_message = "getOpticalPropertiesByComponent: component does not conform to the domain.";
       return I3RC_FAILURE;
     }
+  std::vector<int> maxPf(nc, 0);
+  bool absorbs = false;
+  for (int c = 0; c < nc; c++) {
+    const size_t n = (comps[c].horizontally_uniform ? 1 : (size_t)nx * ny) * (size_t)comps[c].nz;
+    const char* bad = validate_optical_arrays(comps[c].extinction, comps[c].ssa, comps[c].phase_index, n, &maxPf[c], &absorbs);
+    if (!bad && maxPf[c] > comps[c].table.n_entries) bad = "validateOpticalComponent: phase function index is out of bounds";
+    if (bad) {
+      g_message = bad;
+      return I3RC_FAILURE;
+    }
+  }
   i3rc_integrator* h = make_handle();
   h->nx = nx;
   h->ny = ny;
   h->nz = nz;
   h->nc = nc;
+  h->maxPfIndex = maxPf;
+  h->absorbing = absorbs;
   h->xe.assign(xPos, xPos + nx + 1);
   h->ye.assign(yPos, yPos + ny + 1);
   h->ze.assign(zPos, zPos + nz + 1);
@@ -925,6 +1013,9 @@ int i3rc_set_phase_table(i3rc_integrator* h, int comp, const i3rc_phase_table* t
   if (!h) return I3RC_FAILURE;
   if (comp < 0 || comp >= h->nc || !t) return fail(h, "set_phase_table: no such component");
   if (t->n_entries < 1) return fail(h, "set_phase_table: phase function table is not ready.");
+  if (t->n_entries > 65535) return fail(h, "set_phase_table: at most 65535 entries per phase function table in this implementation.");
+  if (comp < (int)h->maxPfIndex.size() && h->maxPfIndex[comp] > t->n_entries)
+    return fail(h, "validateOpticalComponent: phase function index is out of bounds");
   CUDA_OK(h, cudaSetDevice(h->device));
   HostTable& o = h->tables[comp];
   free_table(o);
@@ -993,6 +1084,7 @@ void i3rc_finalize_Integrator(i3rc_integrator* h) {
   dfree(h->d_ye);
   dfree(h->d_ze);
   dfree(h->d_ext);
+  dfree(h->d_extRaw);
   dfree(h->d_extZ);
   dfree(h->d_zlut);
   dfree(h->d_cum);
@@ -1144,7 +1236,6 @@ int i3rc_specifyParameters(i3rc_integrator* h, const i3rc_params* p) {
       d[2] = mu;
       for (int a = 0; a < 3; a++) d[3 + a] = fabsf(d[a]) >= 2.0f * F_TINY ? 1.0f / fabsf(d[a]) : INFINITY;
       d[6] = 4.0f * F_PI * fabsf(mu);
-    d[7] = 1.0f / d[6];
       d[7] = 1.0f / d[6];
     }
     CUDA_OK(h, upload(&h->d_dirs, h->dirs.data(), h->dirs.size(), h->stream));
@@ -1224,13 +1315,22 @@ int i3rc_set_component_profile(i3rc_integrator* h, int comp, const float* extinc
   for (int k = 0; k < h->nz; k++)
     if (!(extinction[k] >= 0.0f)) return fail(h, "set_component_profile: extinction must be >= 0.");
   CUDA_OK(h, cudaSetDevice(h->device));
-  float* d_prof = nullptr;
-  CUDA_OK(h, upload(&d_prof, extinction, (size_t)h->nz, h->stream));
   const size_t ncell = (size_t)h->nx * h->ny * h->nz;
-  k_replace_profile<<<(unsigned)((ncell + 255) / 256), 256, 0, h->stream>>>(h->nx, h->ny, h->nz, h->nc, comp, d_prof, h->d_ext, h->d_cum);
-  h->otherLaunches++;
-  CUDA_OK(h, cudaGetLastError());
-  int rc = build_gather_field(h);  // maximum extinction, 1 + epsilon nudge, the copy of totalExt the rays gather from
+  h->absorbing = true;  // (the new profile may switch an absorbing component on)
+  if (!h->d_extRaw) {
+    CUDA_OK(h, cudaMalloc(&h->d_extRaw, sizeof(float) * ncell * h->nc));
+    k_recover_extinctions<<<(unsigned)((ncell + 255) / 256), 256, 0, h->stream>>>(ncell, h->nc, h->d_ext, h->d_cum, h->d_extRaw);
+    h->otherLaunches++;
+  }
+  float* d_prof = nullptr;
+  int rc = [&]() -> int {
+    CUDA_OK(h, upload(&d_prof, extinction, (size_t)h->nz, h->stream));
+    k_replace_profile<<<(unsigned)((ncell + 255) / 256), 256, 0, h->stream>>>(h->nx, h->ny, h->nz, h->nc, comp, d_prof, h->d_extRaw,
+                                                                              h->d_ext, h->d_cum);
+    h->otherLaunches++;
+    CUDA_OK(h, cudaGetLastError());
+    return build_gather_field(h);  // maximum extinction, 1 + epsilon nudge, the copy of totalExt the rays gather from
+  }();
   cudaFree(d_prof);
   if (rc != I3RC_SUCCESS) return rc;
   h->message.clear();
@@ -1311,17 +1411,40 @@ int i3rc_copy_Integrator(const i3rc_integrator* s, i3rc_integrator** out) {
   cudaSetDevice(s->device);
   // rebuild from the device-resident dense arrays (a full copy, unlike MCRT:1082-1253 which forgets the
   // intensity-limiting members: quirk Q6)
-  size_t ncell = (size_t)s->nx * s->ny * s->nz;
-  std::vector<float> te(ncell), ce(ncell * s->nc), sa(ncell * s->nc);
-  std::vector<int32_t> pf(ncell * s->nc);
-  cudaMemcpy(te.data(), s->d_ext, sizeof(float) * ncell, cudaMemcpyDeviceToHost);
-  cudaMemcpy(ce.data(), s->d_cum, sizeof(float) * ncell * s->nc, cudaMemcpyDeviceToHost);
-  cudaMemcpy(sa.data(), s->d_ssa, sizeof(float) * ncell * s->nc, cudaMemcpyDeviceToHost);
-  cudaMemcpy(pf.data(), s->d_pf, sizeof(int32_t) * ncell * s->nc, cudaMemcpyDeviceToHost);
-  i3rc_integrator* h = nullptr;
-  int rc = i3rc_new_Integrator(s->nx, s->ny, s->nz, s->nc, s->xe.data(), s->ye.data(), s->ze.data(), te.data(), ce.data(),
-                               sa.data(), pf.data(), &h);
-  if (rc == I3RC_FAILURE) return rc;
+  const size_t ncell = (size_t)s->nx * s->ny * s->nz;
+  cudaStreamSynchronize(s->stream);  // (a profile swap or a batch may still be running on the source's stream)
+  i3rc_integrator* h = make_handle();
+  h->nx = s->nx;
+  h->ny = s->ny;
+  h->nz = s->nz;
+  h->nc = s->nc;
+  h->xe = s->xe;
+  h->ye = s->ye;
+  h->ze = s->ze;
+  h->maxPfIndex = s->maxPfIndex;
+  h->absorbing = s->absorbing;
+  h->splitLayers = s->splitLayers;
+  auto fields = [&]() -> int {  // device to device, no trip through the host
+    CUDA_OK(h, cudaMalloc(&h->d_ext, sizeof(float) * ncell));
+    CUDA_OK(h, cudaMalloc(&h->d_cum, sizeof(float) * ncell * s->nc));
+    CUDA_OK(h, cudaMalloc(&h->d_ssa, sizeof(float) * ncell * s->nc));
+    CUDA_OK(h, cudaMalloc(&h->d_pf, sizeof(int) * ncell * s->nc));
+    CUDA_OK(h, cudaMemcpyAsync(h->d_ext, s->d_ext, sizeof(float) * ncell, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_OK(h, cudaMemcpyAsync(h->d_cum, s->d_cum, sizeof(float) * ncell * s->nc, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_OK(h, cudaMemcpyAsync(h->d_ssa, s->d_ssa, sizeof(float) * ncell * s->nc, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_OK(h, cudaMemcpyAsync(h->d_pf, s->d_pf, sizeof(int) * ncell * s->nc, cudaMemcpyDeviceToDevice, h->stream));
+    if (s->d_extRaw) {
+      CUDA_OK(h, cudaMalloc(&h->d_extRaw, sizeof(float) * ncell * s->nc));
+      CUDA_OK(h, cudaMemcpyAsync(h->d_extRaw, s->d_extRaw, sizeof(float) * ncell * s->nc, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return finish_new_integrator(h);
+  };
+  int rc = fields();
+  if (rc == I3RC_FAILURE) {
+    g_message = h->message;
+    i3rc_finalize_Integrator(h);
+    return rc;
+  }
   for (int c = 0; c < s->nc; c++) {
     const HostTable& t = s->tables[c];
     if (t.kind == 0) continue;
@@ -1449,6 +1572,116 @@ int i3rc_lookup_phase_function(i3rc_integrator* h, int comp, int entry, int whic
   return probe_1d(h, m.d + (size_t)entry * m.nSteps, m.nSteps, n, angles, out, false);
 }
 
+// ---- device probes of the random-number stream and of next_direct (no handle needed) -----------------------------
+int i3rc_probe_philox(uint32_t key0, uint32_t key1, int n, const uint64_t* photon, const uint32_t* block, uint32_t* raw4,
+                      float* u4) {
+  if (!have_device() || n < 1 || !photon || !block || !raw4 || !u4) return I3RC_FAILURE;
+  unsigned long long* d_ph = nullptr;
+  uint32_t *d_bl = nullptr, *d_raw = nullptr;
+  float* d_u = nullptr;
+  bool ok = cudaMalloc(&d_ph, 8 * (size_t)n) == cudaSuccess && cudaMalloc(&d_bl, 4 * (size_t)n) == cudaSuccess &&
+            cudaMalloc(&d_raw, 16 * (size_t)n) == cudaSuccess && cudaMalloc(&d_u, 16 * (size_t)n) == cudaSuccess;
+  if (ok) {
+    cudaMemcpy(d_ph, photon, 8 * (size_t)n, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_bl, block, 4 * (size_t)n, cudaMemcpyHostToDevice);
+    k_probe_philox<<<(n + 127) / 128, 128>>>(key0, key1, n, d_ph, d_bl, d_raw, d_u);
+    ok = cudaMemcpy(raw4, d_raw, 16 * (size_t)n, cudaMemcpyDeviceToHost) == cudaSuccess &&
+         cudaMemcpy(u4, d_u, 16 * (size_t)n, cudaMemcpyDeviceToHost) == cudaSuccess;
+  }
+  cudaFree(d_ph), cudaFree(d_bl), cudaFree(d_raw), cudaFree(d_u);
+  return ok ? I3RC_SUCCESS : I3RC_FAILURE;
+}
+int i3rc_probe_next_direct(uint32_t key0, uint32_t key1, int n, const uint64_t* photon, const uint32_t* block,
+                           const float* direction, const float* cosine, float* newDirection, uint32_t* blocksUsed) {
+  if (!have_device() || n < 1 || !photon || !block || !direction || !cosine || !newDirection || !blocksUsed) return I3RC_FAILURE;
+  unsigned long long* d_ph = nullptr;
+  uint32_t *d_bl = nullptr, *d_used = nullptr;
+  float *d_S = nullptr, *d_c = nullptr, *d_o = nullptr;
+  bool ok = cudaMalloc(&d_ph, 8 * (size_t)n) == cudaSuccess && cudaMalloc(&d_bl, 4 * (size_t)n) == cudaSuccess &&
+            cudaMalloc(&d_used, 4 * (size_t)n) == cudaSuccess && cudaMalloc(&d_S, 12 * (size_t)n) == cudaSuccess &&
+            cudaMalloc(&d_c, 4 * (size_t)n) == cudaSuccess && cudaMalloc(&d_o, 12 * (size_t)n) == cudaSuccess;
+  if (ok) {
+    cudaMemcpy(d_ph, photon, 8 * (size_t)n, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_bl, block, 4 * (size_t)n, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_S, direction, 12 * (size_t)n, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_c, cosine, 4 * (size_t)n, cudaMemcpyHostToDevice);
+    k_probe_next_direct<<<(n + 127) / 128, 128>>>(key0, key1, n, d_ph, d_bl, d_S, d_c, d_o, d_used);
+    ok = cudaMemcpy(newDirection, d_o, 12 * (size_t)n, cudaMemcpyDeviceToHost) == cudaSuccess &&
+         cudaMemcpy(blocksUsed, d_used, 4 * (size_t)n, cudaMemcpyDeviceToHost) == cudaSuccess;
+  }
+  cudaFree(d_ph), cudaFree(d_bl), cudaFree(d_used), cudaFree(d_S), cudaFree(d_c), cudaFree(d_o);
+  return ok ? I3RC_SUCCESS : I3RC_FAILURE;
+}
+
+// ---- roofline ceilings measured on this GPU (the bound of C1-C4 is the L2 random-gather rate) ----
+// Random 4-byte gathers over `bytes` of device memory (rounded down to a power of two): *gathersPerSec = loads per second,
+// best of `repeats` launches timed with CUDA events.
+int i3rc_measure_gather_rate(size_t bytes, int repeats, double* gathersPerSec) {
+  if (!have_device() || !gathersPerSec || bytes < 4096) return I3RC_FAILURE;
+  size_t words = 1;
+  while (words * 2 * sizeof(float) <= bytes) words *= 2;
+  if (words > ((size_t)1 << 25)) words = (size_t)1 << 25;  // (the index is 25 bits of the generator's state)
+  float *d = nullptr, *sink = nullptr;
+  if (cudaMalloc(&d, words * sizeof(float)) != cudaSuccess || cudaMalloc(&sink, 4) != cudaSuccess) {
+    cudaFree(d);
+    return I3RC_FAILURE;
+  }
+  cudaMemset(d, 0, words * sizeof(float));
+  cudaDeviceProp prop;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaGetDeviceProperties(&prop, dev);
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 256, unr = 8;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  double best = 0.0;
+  for (int r = 0; r < std::max(repeats, 1) + 1; r++) {  // (the first launch warms the cache up)
+    cudaEventRecord(a);
+    k_gather_bench<8><<<blocks, threads>>>(d, (uint32_t)(words - 1), iters, sink);
+    cudaEventRecord(b);
+    if (cudaEventSynchronize(b) != cudaSuccess) break;
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, a, b);
+    if (r > 0 && ms > 0.0f) best = std::max(best, (double)blocks * threads * iters * unr / (ms * 1e-3));
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  cudaFree(sink);
+  *gathersPerSec = best;
+  return best > 0.0 ? I3RC_SUCCESS : I3RC_FAILURE;
+}
+// Warp instructions per second the SMs can issue (independent FMAs from a full complement of warps)
+int i3rc_measure_issue_rate(int repeats, double* warpInstPerSec) {
+  if (!have_device() || !warpInstPerSec) return I3RC_FAILURE;
+  float* sink = nullptr;
+  if (cudaMalloc(&sink, 4) != cudaSuccess) return I3RC_FAILURE;
+  cudaDeviceProp prop;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaGetDeviceProperties(&prop, dev);
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2048;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  double best = 0.0;
+  for (int r = 0; r < std::max(repeats, 1) + 1; r++) {
+    cudaEventRecord(a);
+    k_issue_bench<<<blocks, threads>>>(iters, sink);
+    cudaEventRecord(b);
+    if (cudaEventSynchronize(b) != cudaSuccess) break;
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, a, b);
+    if (r > 0 && ms > 0.0f) best = std::max(best, (double)blocks * (threads / 32) * iters * 128.0 / (ms * 1e-3));
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(sink);
+  *warpInstPerSec = best;
+  return best > 0.0 ? I3RC_SUCCESS : I3RC_FAILURE;
+}
+
 // ---- batch moments -------------------------------------------------------------------------------------
 int i3rc_stats_reset(i3rc_integrator* h, int with_volume) {
   if (!h || !h->readyToCompute) return I3RC_FAILURE;
@@ -1468,6 +1701,8 @@ int i3rc_stats_reset(i3rc_integrator* h, int with_volume) {
 
 int i3rc_stats_accumulate(i3rc_integrator* h) {
   if (!h || !h->d_stats) return h ? fail(h, "stats_accumulate: call stats_reset first") : I3RC_FAILURE;
+  if (h->statsNDir != (h->computeIntensity ? h->nDir : 0))  // (the moment buffer was laid out for other directions)
+    return fail(h, "stats_accumulate: the intensity directions changed since stats_reset; call stats_reset again");
   int nD = h->statsNDir;
   StatsLayout L = stats_layout(h, nD, h->statsVolume);
   size_t ncol = (size_t)h->nx * h->ny, ncell = ncol * h->nz;
@@ -1539,8 +1774,8 @@ int i3rc_run_batches(i3rc_integrator* h, const i3rc_photon_source* src, int32_t 
   SourceDev sd;
   int rc = prepare_compute(h, src, sd);
   if (rc != I3RC_SUCCESS) return rc;
-  if (!h->d_stats) {
-    rc = i3rc_stats_reset(h, 0);
+  if (!h->d_stats || h->statsNDir != (h->computeIntensity ? h->nDir : 0)) {  // no moments yet, or laid out for other directions
+    rc = i3rc_stats_reset(h, h->d_stats ? (int)h->statsVolume : 0);
     if (rc != I3RC_SUCCESS) return rc;
   }
   CUDA_OK(h, cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * CNT_N, h->stream));
@@ -1649,6 +1884,19 @@ int i3rc_reset_timing(i3rc_integrator* h) {
   h->traceLaunches = h->otherLaunches = 0;
   return I3RC_SUCCESS;
 }
+// what new_Integrator / the next launch decided: 0 = number of layers stored in 3-D when the uniform layers are kept out of
+// the extinction field (0: all layers stored), 1 = floats of tallies staged per warp in shared memory (0: global atomics)
+int i3rc_get_layout(i3rc_integrator* h, int what) {
+  if (!h || !h->readyToCompute) return -1;
+  if (what == 0) return h->nzc;
+  if (what == 1) {
+    Problem p;
+    fill_problem(h, p);
+    return p.tsmN;
+  }
+  return -1;
+}
+
 int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
   if (!h || !key) return I3RC_FAILURE;
   std::string k(key);
@@ -1672,6 +1920,8 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->eventThreshold = value;
   else if (k == "track_by_component")
     h->trackByComponent = value != 0;
+  else if (k == "stage_tallies" && value >= 0 && value <= 4096)
+    h->stageTallies = value;  // floats of shared memory per warp for staged tallies; 0 = global atomics only
   else
     return fail(h, "set_tuning: unknown key or bad value");
   return I3RC_SUCCESS;

@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "transport.cuh"
 
 namespace i3rc {
@@ -47,9 +49,72 @@ struct SlotPool {  // structure of arrays: lane i touches slot[k] of every array
 };
 constexpr uint32_t SLOT_RAW = 1u << 24;
 
-template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP>
+// One tally increment per lane, committed by the whole warp (call it converged).  Domains of a few columns (planeParallel:
+// one, the step cloud: 32) would otherwise send every increment of the GPU to a handful of addresses.  There, each
+// warp owns a private copy of the tallies in shared memory (wt): increments of a warp that go to the same element are
+// first summed over the lanes (match.any; a butterfly when it is the whole warp), one lane adds the sum without any
+// atomic, and at the end of the kernel the block sums its warps' copies and issues one global atomic per element
+// (flush_staged_tallies).  Larger domains (TSM = false, or a tally that is not staged) use global atomics directly.
+template <bool TSM, class P>
+__device__ __forceinline__ void warp_tally(const P& p, float* wt, bool has, int which, uint32_t off, float v) {
+  if (TSM) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int s = -1;
+    if (has) {
+      const int o = p.tsmOff[which];
+      if (o >= 0)
+        s = o + (int)off;
+      else
+        atomicAdd(tally_ptr(p, which) + off, v);
+    }
+    const unsigned m = __ballot_sync(full, s >= 0);
+    if (!m) return;
+    const unsigned peers = __match_any_sync(full, s >= 0 ? s : -1 - lane);
+    if (__all_sync(full, s < 0 || peers == m)) {  // one element for all: butterfly
+      float x = s >= 0 ? v : 0.0f;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(full, x, o);
+      if (lane == __ffs(m) - 1) wt[s] += x;
+    } else {  // groups of lanes with the same element: the first lane of a group collects
+      float sum = 0.0f;
+      unsigned rem = s >= 0 ? peers : 0u;
+      while (__any_sync(full, rem != 0u)) {
+        const int src = rem ? __ffs(rem) - 1 : lane;
+        const float x = __shfl_sync(full, v, src);
+        if (rem) sum += x;
+        rem &= rem - 1u;
+      }
+      if (s >= 0 && lane == __ffs(peers) - 1) wt[s] += sum;
+    }
+    __syncwarp();
+  } else if (has) {
+    atomicAdd(tally_ptr(p, which) + off, v);
+  }
+}
+// end of the kernel: block-level sum of the warps' private tallies, one global atomic per non-zero element
+template <int BLOCK, class P>
+__device__ __forceinline__ void flush_staged_tallies(const P& p, const float* sdyn) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.tsmN; i += BLOCK) {
+    float x = 0.0f;
+#pragma unroll
+    for (int w = 0; w < BLOCK / 32; w++) x += sdyn[w * p.tsmN + i];
+    if (x != 0.0f) {
+      int which = 0, best = -1;
+#pragma unroll
+      for (int t = 0; t < 5; t++)
+        if (p.tsmOff[t] >= 0 && p.tsmOff[t] <= i && p.tsmOff[t] > best) best = p.tsmOff[t], which = t;
+      atomicAdd(tally_ptr(p, which) + (i - best), x);
+    }
+  }
+}
+
+template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP, bool TSM = false>
 __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, FAST, SPLIT> p, const int lowWater, const int minRunning) {
   constexpr int NW = BLOCK / 32;
+  extern __shared__ float s_dyn[];  // TSM: NW private copies of the staged tallies (Problem::tsmN floats each)
+  using Tally = typename std::conditional<TSM, TallyLater, TallyNow>::type;
   constexpr int UNROLL = I3RC_STEP_UNROLL;
   static_assert(STEPS % (2 * UNROLL) == 0, "a round is a whole number of unrolled bodies");
   static_assert((QCAP & (QCAP - 1)) == 0 && QCAP >= 64, "ring size: power of two, room for one push of 32");
@@ -66,6 +131,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
   LeTask* q = s_task[warp];
   SlotPool<NSLOT>& pool = s_pool[warp];
   uint8_t* pend = s_pend[warp];
+  float* wt = s_dyn + (TSM ? warp * p.tsmN : 0);
+  if (TSM) {
+    for (int i = threadIdx.x; i < NW * p.tsmN; i += BLOCK) s_dyn[i] = 0.0f;
+    __syncthreads();
+  }
 
   // warp-uniform bookkeeping (registers): ring positions [head, tail), number of due events
   int head = 0, tail = 0, npend = NSLOT;
@@ -173,10 +243,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
       }
       if (stage == 0) {  // boundary / collision handling (MCRT:499-561, 581-649)
         alive = false;
+        Tally tal;
+        if constexpr (TSM) tal.n = 0;
         if (has && E.segDone != DONE_NEW) {
           float a0;
           E.rng.next4(p.key0, p.key1, a0, a1, a2, a3);
-          alive = photon_event(p, E, a0, a1) != 0;
+          alive = photon_event(p, E, a0, a1, tal) != 0;
+        }
+        if constexpr (TSM) {  // flux through the top / the surface, or absorption (column and cell): committed with the whole warp
+          const TallyLater& t = tal;
+          warp_tally<TSM>(p, wt, t.n > 0, t.w0, t.o0, t.v0);
+          if (__any_sync(full, t.n > 1)) warp_tally<TSM>(p, wt, t.n > 1, t.w1, t.o1, t.v1);
         }
         dcur = 0;
         stage = (p.computeIntensity && __any_sync(full, alive)) ? 1 : 2;
@@ -305,6 +382,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
     ray_after_steps(R);
     // close finished rays
     bool segEnd = false;
+    Tally talR;
+    if constexpr (TSM) talR.n = 0;
     if (R.done != DONE_RUN && R.done != DONE_IDLE) {
       uint32_t* rv = s_ray[warp][0] + lane;  // what the ray is for waits in shared memory while it is traced
       if (R.mode == MODE_PHOTON) {
@@ -339,8 +418,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
         R.tcw = __uint_as_float(rv[1 * 32]);
         R.tcfix = __uint_as_float(rv[2 * 32]);
         R.ttauFree = __uint_as_float(rv[3 * 32]);
-        if (!finish_le_ray(p, R)) R.done = DONE_IDLE;
+        if (!finish_le_ray(p, R, talR)) R.done = DONE_IDLE;
       }
+    }
+    if constexpr (TSM) {  // the local-estimate contributions of this round
+      const TallyLater& t = talR;
+      warp_tally<TSM>(p, wt, t.n > 0, t.w0, t.o0, t.v0);
     }
     const unsigned ms = __ballot_sync(full, segEnd);
     if (segEnd) pend[npend + __popc(ms & lt)] = (uint8_t)s_ray[warp][1][lane];
@@ -391,6 +474,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
   // flush the warp's counters
   __syncwarp();
   if (lane < CNT_N && s_cnt[warp][lane]) atomicAdd(p.counters + lane, (unsigned long long)s_cnt[warp][lane]);
+  if (TSM) flush_staged_tallies<BLOCK>(p, s_dyn);
 }
 
 // ---- probes: accumulateExtinctionAlongPath for explicit rays (deterministic sub-path parity) ---------------
@@ -438,6 +522,75 @@ __global__ void k_lookup_phase(const float* __restrict__ T, int nSteps, int n, c
   if (i < n) out[i] = phase_lookup(T, nSteps, ang[i]);
 }
 
+// Philox4x32-10 on the device for explicit (photon, block) counters: raw words and the deviates Rng::next4 makes of them
+__global__ void k_probe_philox(uint32_t key0, uint32_t key1, int n, const unsigned long long* __restrict__ photon,
+                               const uint32_t* __restrict__ block, uint32_t* __restrict__ raw, float* __restrict__ u) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Rng g;
+  g.init(photon[i]);
+  g.block = block[i];
+  const u32x4 ctr = {g.id_lo, g.id_hi, g.block, 0u};
+  const u32x4 r = philox4x32_10(ctr, key0, key1);
+  raw[4 * i] = r.x, raw[4 * i + 1] = r.y, raw[4 * i + 2] = r.z, raw[4 * i + 3] = r.w;
+  g.next4(key0, key1, u[4 * i], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
+}
+// next_direct (MCRT:2086-2113) exactly as the transport kernel runs it: deviates from the photon's Philox stream starting
+// at the given block; returns the new direction and the number of blocks consumed
+__global__ void k_probe_next_direct(uint32_t key0, uint32_t key1, int n, const unsigned long long* __restrict__ photon,
+                                    const uint32_t* __restrict__ block, const float* __restrict__ S,
+                                    const float* __restrict__ cosine, float* __restrict__ out,
+                                    uint32_t* __restrict__ blocksUsed) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ProblemDyn p;
+  p.key0 = key0;
+  p.key1 = key1;
+  Lane L;
+  L.rng.init(photon[i]);
+  L.rng.block = block[i];
+  L.ux = S[3 * i], L.uy = S[3 * i + 1], L.uz = S[3 * i + 2];
+  next_direct(p, L, cosine[i]);
+  out[3 * i] = L.ux, out[3 * i + 1] = L.uy, out[3 * i + 2] = L.uz;
+  blocksUsed[i] = L.rng.block - block[i];
+}
+
+// ---- roofline ceilings measured on the spot ---------------------------------------------------
+// Random 4-byte gathers over an array of nWords floats: every thread walks its own pseudo-random sequence of indices
+// (a 32-bit LCG, so consecutive loads of a thread and the loads of neighbouring threads fall into unrelated sectors) and
+// keeps UNR independent loads in flight.  Over an 8 MB array this is the L2 random-gather ceiling of the cell-crossing
+// loop for an L2-resident extinction field; over an array far larger than L2 it is the HBM gather ceiling.
+template <int UNR>
+__global__ void __launch_bounds__(256) k_gather_bench(const float* __restrict__ a, uint32_t mask, int iters, float* __restrict__ sink) {
+  uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+  float acc = 0.0f;
+  for (int it = 0; it < iters; it++) {
+    uint32_t idx[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      x = x * 1664525u + 1013904223u;
+      idx[u] = (x >> 7) & mask;
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; u++) acc += __ldg(a + idx[u]);
+  }
+  if (acc == -1.0f) sink[0] = acc;  // (never true for the zero-filled array: keeps the loads alive)
+}
+// Issue-slot ceiling: independent FMAs only, every warp scheduler can issue one warp instruction per cycle
+__global__ void __launch_bounds__(256) k_issue_bench(int iters, float* __restrict__ sink) {
+  float a0 = threadIdx.x, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float m = 1.0000001f, c = 1e-9f;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      a0 = fmaf(a0, m, c), a1 = fmaf(a1, m, c), a2 = fmaf(a2, m, c), a3 = fmaf(a3, m, c);
+      a4 = fmaf(a4, m, c), a5 = fmaf(a5, m, c), a6 = fmaf(a6, m, c), a7 = fmaf(a7, m, c);
+    }
+  }
+  const float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == -1.0f) sink[0] = s;
+}
+
 // ---- setup: getOpticalPropertiesByComponent on the device (Code/opticalProperties.f95:429-539) -------------
 struct ComponentDev {
   const float* ext;
@@ -474,23 +627,34 @@ __global__ void k_expand_components(int nx, int ny, int nz, int nc, const Compon
   if (run > F_TINY)
     for (int c = 0; c < nc; c++) cumExt[(size_t)c * ncell + cell] = cumExt[(size_t)c * ncell + cell] / run;
 }
-// One component's extinction replaced by a horizontally uniform profile (a k-distribution term of a gas component): the
-// per-component extinctions are recovered from the cumulative fractions, the component swapped, totals and fractions
-// rebuilt like getOpticalPropertiesByComponent does (Code/opticalProperties.f95:524-537).
+// One component's extinction replaced by a horizontally uniform profile (a k-distribution term of a gas component).
+// The un-normalised extinction of every component is kept on the device from the first swap on (k_recover_extinctions:
+// from the cumulative fractions, once), so that swapping band after band does not accumulate rounding: every swap
+// rebuilds totals and fractions from those, like getOpticalPropertiesByComponent does (Code/opticalProperties.f95:524-537).
+__global__ void k_recover_extinctions(size_t ncell, int nc, const float* __restrict__ totalExt, const float* __restrict__ cumExt,
+                                      float* __restrict__ raw) {
+  const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ncell) return;
+  const float tot = totalExt[cell];
+  float prev = 0.0f;
+  for (int c = 0; c < nc; c++) {
+    float frac = cumExt[(size_t)c * ncell + cell];
+    if (c == nc - 1 && tot > F_TINY) frac = 1.0f;  // (undo the 1 + epsilon nudge)
+    raw[(size_t)c * ncell + cell] = tot > F_TINY ? (frac - prev) * tot : frac - prev;
+    prev = frac;
+  }
+}
 __global__ void k_replace_profile(int nx, int ny, int nz, int nc, int comp, const float* __restrict__ profile,
-                                  float* __restrict__ totalExt, float* __restrict__ cumExt) {
+                                  float* __restrict__ raw, float* __restrict__ totalExt, float* __restrict__ cumExt) {
   const size_t ncell = (size_t)nx * ny * nz;
   const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= ncell) return;
   const int iz = (int)(cell / ((size_t)nx * ny));
-  const float tot = totalExt[cell];
-  float prev = 0.0f, run = 0.0f;
+  raw[(size_t)comp * ncell + cell] = profile[iz];
+  float run = 0.0f;
   for (int c = 0; c < nc; c++) {
-    float frac = cumExt[(size_t)c * ncell + cell];
-    if (c == nc - 1 && tot > F_TINY) frac = 1.0f;  // (undo the 1 + epsilon nudge)
-    const float a = c == comp ? profile[iz] : (tot > F_TINY ? (frac - prev) * tot : frac - prev);
-    prev = frac;
-    run += a;
+    const float e = raw[(size_t)c * ncell + cell];
+    run = (c == 0) ? e : e + run;
     cumExt[(size_t)c * ncell + cell] = run;
   }
   totalExt[cell] = run;

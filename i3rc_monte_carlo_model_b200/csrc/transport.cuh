@@ -131,6 +131,9 @@ struct Problem {
   SourceDev src;
   uint32_t key0, key1;
   float *fluxUp, *fluxDown, *fluxAbs, *volAbs, *intensity, *intByComp, *excess;
+  // Small domains (planeParallel: 1 column, the step cloud: 32): every warp keeps a private copy of the tallies in shared
+  // memory (tsmN floats; tsmOff[TAL_*] = where each tally starts in it, -1 = not staged), see warp_tally (kernels.cuh).
+  int tsmN, tsmOff[5];
   unsigned long long* counters;
   unsigned long long* nextPhoton;
   long long firstPhoton;  // photon ids of this launch are firstPhoton + [0, src.n)
@@ -187,6 +190,34 @@ I3RC_HD float ext_gather(const P& p, int idx, int iz) {
 }
 template <class P>
 I3RC_HD float ext_at(const P& p, int ix, int iy, int iz) { return ext_gather(p, ext_index(p, ix, iy, iz), iz); }
+
+// ---- tallies (MCRT:513, 530, 642-649, 574-579, 662-667) ---------------------------------------------------------
+// The physics functions hand their increments to a policy object: TallyNow adds at once (per-lane scheduler, probes, CPU
+// harness); the transport kernel collects them (TallyLater) and commits them with the whole warp, aggregated (warp_tally).
+enum { TAL_UP = 0, TAL_DOWN = 1, TAL_ABS = 2, TAL_INT = 3, TAL_VOL = 4 };
+I3RC_HD float* tally_ptr(const Problem& p, int which) {
+  return which == TAL_UP ? p.fluxUp : which == TAL_DOWN ? p.fluxDown : which == TAL_ABS ? p.fluxAbs : which == TAL_INT ? p.intensity : p.volAbs;
+}
+struct TallyNow {
+  I3RC_HD void add(const Problem& p, int which, size_t off, float v) { I3RC_ATOMIC_ADD(tally_ptr(p, which) + off, v); }
+};
+struct TallyLater {  // at most two increments per lane and commit point (an absorption: column + cell)
+  int n, w0, w1;
+  uint32_t o0, o1;
+  float v0, v1;
+  I3RC_HD void add(const Problem&, int w, size_t o, float x) {
+    if (n == 0) {
+      w0 = w;
+      o0 = (uint32_t)o;
+      v0 = x;
+    } else {
+      w1 = w;
+      o1 = (uint32_t)o;
+      v1 = x;
+    }
+    n++;
+  }
+};
 
 struct Lane {
   // current ray (regular or irregular grid): linear cell index, signed index strides per axis, and the number of
@@ -830,8 +861,8 @@ I3RC_HD void start_le_task(const P& p, Lane& L, const LeTask& t) {
                I3RC_LDG(dv + 1), I3RC_LDG(dv + 2), I3RC_LDG(dv + 3), I3RC_LDG(dv + 4), I3RC_LDG(dv + 5), t.tauLimit, t.e0);
 }
 
-template <class P>
-I3RC_HD void tally_intensity(const P& p, Lane& L, float c) {
+template <class P, class TAL>
+I3RC_HD void tally_intensity(const P& p, Lane& L, float c, TAL& tal) {
   if (!P::kFast && p.limitContrib && c > p.maxContrib) {  // MCRT:1598-1609
     I3RC_ATOMIC_ADD(p.excess + L.tcomp * p.nDir + L.td, c - p.maxContrib);
     c = p.maxContrib;
@@ -839,7 +870,7 @@ I3RC_HD void tally_intensity(const P& p, Lane& L, float c) {
   if (c != 0.0f) {
     int col = ray_iy(p, L) * p.nx + ray_ix(p, L);
     size_t ncol = (size_t)p.nx * p.ny;
-    I3RC_ATOMIC_ADD(p.intensity + (size_t)L.td * ncol + col, c);
+    tal.add(p, TAL_INT, (size_t)L.td * ncol + col, c);
     if (!P::kFast && p.trackByComponent) I3RC_ATOMIC_ADD(p.intByComp + ((size_t)L.tcomp * p.nDir + L.td) * ncol + col, c);
     I3RC_COUNT(L, CNT_CONTRIB, 1);
   }
@@ -847,8 +878,8 @@ I3RC_HD void tally_intensity(const P& p, Lane& L, float c) {
 
 // A local-estimate ray has stopped (L.done != 0).  Returns 1 when the same ray goes on with its second stage
 // (Iwabuchi's chained trace, MCRT:1576-1578), 0 when it is finished and its contribution has been tallied.
-template <class P>
-I3RC_HD int finish_le_ray(const P& p, Lane& L) {
+template <class P, class TAL>
+I3RC_HD int finish_le_ray(const P& p, Lane& L, TAL& tal) {
   int done = L.done;
   L.done = DONE_RUN;
   L.nsteps = 0;  // (the caller has counted the crossings)
@@ -875,7 +906,7 @@ I3RC_HD int finish_le_ray(const P& p, Lane& L) {
         break;
     }
   }
-  tally_intensity(p, L, c);
+  tally_intensity(p, L, c, tal);
   return 0;
 }
 
@@ -903,8 +934,8 @@ I3RC_HD void photon_done(Lane& L) {
 // Boundary and collision handling of a finished segment up to (not including) the local estimate
 // (MCRT:499-561, 581-649).  xi0, xi1: deviates of the event (surface: mu, phi; collision: component pick).
 // Returns 1 if the photon lives on (and then wants its local estimate when computeIntensity), 0 if it is finished.
-template <class P>
-I3RC_HD int photon_event(const P& p, Lane& L, float xi0, float xi1) {
+template <class P, class TAL>
+I3RC_HD int photon_event(const P& p, Lane& L, float xi0, float xi1, TAL& tal) {
   const int done = L.segDone;
   if (done == DONE_BAD) {
     I3RC_COUNT(L, CNT_BAD, 1);
@@ -912,7 +943,7 @@ I3RC_HD int photon_event(const P& p, Lane& L, float xi0, float xi1) {
     return 0;
   }
   if (done == DONE_TOP) {  // MCRT:499-514
-    I3RC_ATOMIC_ADD(p.fluxUp + L.cy * p.nx + L.cx, L.w);
+    tal.add(p, TAL_UP, (size_t)(L.cy * p.nx + L.cx), L.w);
     I3RC_COUNT(L, CNT_TOP, 1);
     photon_done(L);
     return 0;
@@ -921,7 +952,7 @@ I3RC_HD int photon_event(const P& p, Lane& L, float xi0, float xi1) {
     L.order++;
     L.cz = 0;
     L.fz = 0.0f;
-    I3RC_ATOMIC_ADD(p.fluxDown + L.cy * p.nx + L.cx, L.w);
+    tal.add(p, TAL_DOWN, (size_t)(L.cy * p.nx + L.cx), L.w);
     I3RC_COUNT(L, CNT_SURF, 1);
     float mu = sqrtf(xi0);
     while (!(fabsf(mu) > 2.0f * F_TINY)) {  // MCRT:542-549 (needs a deviate of exactly 0: once in 2^32)
@@ -959,8 +990,8 @@ I3RC_HD int photon_event(const P& p, Lane& L, float xi0, float xi1) {
     if (L.pfi < 0) L.pfi = 0;
     if (ssa < 1.0f) {  // MCRT:642-649
       float a = L.w * (1.0f - ssa);
-      I3RC_ATOMIC_ADD(p.fluxAbs + L.cy * p.nx + L.cx, a);
-      I3RC_ATOMIC_ADD(p.volAbs + cell, a);
+      tal.add(p, TAL_ABS, (size_t)(L.cy * p.nx + L.cx), a);
+      tal.add(p, TAL_VOL, cell, a);
       L.w *= ssa;
       I3RC_COUNT(L, CNT_ABS, 1);
     }
@@ -1028,7 +1059,8 @@ I3RC_HD void handle_event(const P& p, Lane& L) {
     segment_finished(p, L);
     float xi0;
     L.rng.next4(p.key0, p.key1, xi0, L.ev1, L.ev2, L.ev3);  // the event's block
-    if (!photon_event(p, L, xi0, L.ev1)) return;
+    TallyNow now;
+    if (!photon_event(p, L, xi0, L.ev1, now)) return;
     if (p.computeIntensity) {
       L.d = 0;
       advance_le(p, L);
@@ -1037,7 +1069,8 @@ I3RC_HD void handle_event(const P& p, Lane& L) {
     }
     return;
   }
-  if (finish_le_ray(p, L)) return;
+  TallyNow now;
+  if (finish_le_ray(p, L, now)) return;
   advance_le(p, L);
 }
 

@@ -16,6 +16,7 @@
  */
 #ifndef I3RC_B200_H
 #define I3RC_B200_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -187,6 +188,21 @@ int i3rc_sample_scattering_angles(i3rc_integrator* h, int comp, int entry, int n
 int i3rc_lookup_phase_function(i3rc_integrator* h, int comp, int entry, int which, int n, const float* angles,
                                float* out);      /* lookUpPhaseFuncValsFromTable, MCRT:1613 */
 
+/* The device's random-number stream (Philox4x32-10, one stream per photon: replaces Code/RandomNumbersForMC.f95:169-299)
+ * for explicit (photon, block) counters: raw4[4n] words and u4[4n] deviates.  No handle needed. */
+int i3rc_probe_philox(uint32_t key0, uint32_t key1, int n, const uint64_t* photon, const uint32_t* block,
+                      uint32_t* raw4, float* u4);
+/* next_direct (MCRT:2086-2113) as the transport kernel runs it, deviates from the photon's stream starting at `block`;
+ * direction / newDirection are [n][3], blocksUsed[n] = Philox blocks consumed (two rejection rounds per block). */
+int i3rc_probe_next_direct(uint32_t key0, uint32_t key1, int n, const uint64_t* photon, const uint32_t* block,
+                           const float* direction, const float* cosine, float* newDirection, uint32_t* blocksUsed);
+
+/* ---- roofline ceilings measured on the spot (no reference counterpart) ---------------- */
+/* random 4-byte gathers per second over `bytes` of device memory (8 MB: L2-resident field; >= 1 GB: HBM) */
+int i3rc_measure_gather_rate(size_t bytes, int repeats, double* gathersPerSec);
+/* warp instructions per second the SMs issue when nothing stalls (independent FMAs) */
+int i3rc_measure_issue_rate(int repeats, double* warpInstPerSec);
+
 /* ---- batch moments on the device (monteCarloDriver.f95:300-378) ---------------------------- */
 typedef struct {
   double* meanFluxUp;      /* [2]: mean, standard error */
@@ -222,6 +238,9 @@ int i3rc_comm_finalize(i3rc_integrator* h);
 int i3rc_synchronize(i3rc_integrator* h);
 void* i3rc_stream(i3rc_integrator* h);          /* cudaStream_t all kernels of this handle run on */
 /* device time (CUDA events on the handle's stream) of the transport kernels since the last reset */
+/* layout decisions: what = 0: layers of totalExt stored in 3-D when horizontally uniform layers are kept out of the field
+ * (0 = all), 1: floats of tallies staged per warp in shared memory (0 = global atomics only); -1 on error */
+int i3rc_get_layout(i3rc_integrator* h, int what);
 int i3rc_get_timing(i3rc_integrator* h, double* trace_ms, int64_t* trace_launches, int64_t* other_launches);
 int i3rc_reset_timing(i3rc_integrator* h);
 int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value);

@@ -34,27 +34,55 @@ class BatchStats(C.Structure):
                                        "fluxAbsorbed", "absorbedProfile", "absorbedVolume", "radiance", "meanRadiance")]
 
 
+_fast_backend = None
+
+
+def _cpu_tag():
+    """A short name for this machine's CPU (model + instruction-set flags): -march=native builds are per machine."""
+    import hashlib
+    try:
+        txt = open("/proc/cpuinfo").read()
+        keep = [ln for ln in txt.splitlines() if ln.startswith(("model name", "flags"))][:2]
+    except OSError:
+        keep = []
+    return hashlib.sha1("\n".join(keep).encode()).hexdigest()[:12]
+
+
+def fast_oracle_backend() -> _abi.Backend:
+    """The same C source built -O3 -march=native ON THIS MACHINE, for bench.py's CPU timing arm only (the parity oracle is
+    the -O2 -ffp-contract=off build).  Returns a backend with the batch driver bound."""
+    global _fast_backend
+    if _fast_backend is None:
+        d = os.path.join(_HERE, "_build", "fast_" + _cpu_tag())
+        subprocess.check_call(["make", "-C", _HERE, "-s", "fast", "FASTDIR=" + d], stdout=subprocess.DEVNULL)
+        _fast_backend = _bind(C.CDLL(os.path.join(d, "libi3rc_oracle_fast.so")), "oracle-O3-native")
+    return _fast_backend
+
+
 def oracle_backend() -> _abi.Backend:
     global _backend
     if _backend is None:
         build()
-        lib = C.CDLL(LIB_PATH)
-        be = _abi.Backend(lib, "orc_", "oracle")
-        vp, ci = C.c_void_p, C.c_int
-        u32p = C.POINTER(C.c_uint32)
-        lib.orc_mt_seed_vector.argtypes = [u32p, _abi.c_int32_p, ci]
-        lib.orc_mt_seed_scalar.argtypes = [u32p, C.c_int32]
-        lib.orc_mt_int32.argtypes, lib.orc_mt_int32.restype = [u32p], C.c_uint32
-        lib.orc_mt_real.argtypes, lib.orc_mt_real.restype = [u32p], C.c_float
-        lib.orc_findIndex.argtypes, lib.orc_findIndex.restype = [C.c_float, _abi.c_float_p, ci, ci], ci
-        lib.orc_computeLobattoMus.argtypes = [_abi.c_float_p, ci]
-        lib.orc_next_direct.argtypes = [_abi.c_float_p, ci, C.c_float, _abi.c_float_p]
-        lib.orc_hybrid_phase_functions.argtypes = [_abi.c_float_p, ci, ci, _abi.c_float_p, C.c_float, _abi.c_float_p]
-        lib.orc_run_batches.argtypes = [vp, C.POINTER(_abi.PhotonSource), C.c_int32, ci, ci, ci, ci,
-                                        C.POINTER(BatchStats), C.POINTER(_abi.Counters)]
-        lib.orc_run_batches.restype = ci
-        _backend = be
+        _backend = _bind(C.CDLL(LIB_PATH), "oracle")
     return _backend
+
+
+def _bind(lib, name) -> _abi.Backend:
+    be = _abi.Backend(lib, "orc_", name)
+    vp, ci = C.c_void_p, C.c_int
+    u32p = C.POINTER(C.c_uint32)
+    lib.orc_mt_seed_vector.argtypes = [u32p, _abi.c_int32_p, ci]
+    lib.orc_mt_seed_scalar.argtypes = [u32p, C.c_int32]
+    lib.orc_mt_int32.argtypes, lib.orc_mt_int32.restype = [u32p], C.c_uint32
+    lib.orc_mt_real.argtypes, lib.orc_mt_real.restype = [u32p], C.c_float
+    lib.orc_findIndex.argtypes, lib.orc_findIndex.restype = [C.c_float, _abi.c_float_p, ci, ci], ci
+    lib.orc_computeLobattoMus.argtypes = [_abi.c_float_p, ci]
+    lib.orc_next_direct.argtypes = [_abi.c_float_p, ci, C.c_float, _abi.c_float_p]
+    lib.orc_hybrid_phase_functions.argtypes = [_abi.c_float_p, ci, ci, _abi.c_float_p, C.c_float, _abi.c_float_p]
+    lib.orc_run_batches.argtypes = [vp, C.POINTER(_abi.PhotonSource), C.c_int32, ci, ci, ci, ci,
+                                    C.POINTER(BatchStats), C.POINTER(_abi.Counters)]
+    lib.orc_run_batches.restype = ci
+    return be
 
 
 class MT19937:
@@ -79,7 +107,7 @@ class MT19937:
 def run_batches(integ, photons, iseed, numBatches, seedOrder=0, batchBegin=1, nThreads=0, with_volume=False):
     """monteCarloDriver.f95:264-378 on the oracle with OpenMP threads standing in for MPI ranks.
     Returns (sums dict of float64 arrays shaped [2, ...], counters dict)."""
-    be = oracle_backend()
+    be = integ.backend  # (the parity oracle or its timing build: whichever made the integrator)
     nx, ny, nz, nd = integ.nx, integ.ny, integ.nz, integ.nDir
     st = BatchStats(nx=nx, ny=ny, nz=nz, nd=nd, with_volume=int(with_volume))
     arrs = {

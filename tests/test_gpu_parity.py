@@ -22,7 +22,8 @@ from i3rc_monte_carlo_model_b200.monteCarloRadiativeTransfer import (computeRadi
                                                                     reportResults, specifyParameters, traceRays)
 from i3rc_monte_carlo_model_b200.RandomNumbers import new_RandomNumberSequence
 from i3rc_monte_carlo_model_b200.surfaceProperties import new_SurfaceDescription
-from tests.cases import assert_statistical_parity, make_integrator, mean_se, oracle_summary, run_batches
+from tests.cases import (assert_counter_parity, assert_statistical_parity, make_integrator, mean_se, oracle_summary,
+                         run_batches)
 from tests.golden.make_golden import CASES as GOLDEN_CASES
 from tests.test_host_mirror import SPECIFY_CASES, check_specify
 
@@ -239,9 +240,7 @@ def test_statistical_parity_with_oracle(cuda, oracle, name):
     assert_statistical_parity(got, ref, label=name + ": ")
     gc, rc = got["counters"], ref["counters"]
     assert gc["photons"] == nph and gc["bad"] == 0
-    for c in ("collisions", "surface_hits", "exits_top"):
-        a, b = gc[c] / gc["photons"], rc[c] / rc["photons"]
-        assert abs(a - b) <= 0.08 * max(b, 0.05) + 0.03, (c, a, b)
+    assert_counter_parity(got, rc, ("collisions", "surface_hits", "exits_top", "crossings_photon"), label=name + ": ")
 
 
 def test_surface_brdf_map(cuda, oracle):
@@ -288,42 +287,77 @@ def _coarsen(a, f=8):
     return a.reshape(nx // f, f, ny // f, f, *a.shape[2:]).mean(axis=(1, 3))
 
 
-@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+# GPU photons per batch and batches for each fixture (default: twice the oracle's photons per batch, 16 batches)
+GOLDEN_GPU_SIZE = {"landsat_rr_hi": (16_000_000, 64), "les_mid_split": (200_000, 16), "radar_c1_rr": (400_000, 16),
+                   "step_mu1_rr": (1_000_000, 16)}
+
+
+def _load_golden(name):
+    """name -> dict of arrays; a fixture with a second half (name_b: further batches of the same case, independent
+    streams) is combined with it: mean of the two means, standard errors in quadrature."""
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    pb = os.path.join(GOLDEN, name + "_b.npz")
+    if os.path.exists(pb):
+        b = np.load(pb)
+        for k in list(g):
+            if k.endswith("_mean"):
+                g[k] = 0.5 * (g[k].astype(np.float64) + b[k])
+            elif k.endswith("_se"):
+                g[k] = 0.5 * np.hypot(g[k].astype(np.float64), b[k])
+            elif k.startswith("cnt_") or k == "numBatches":
+                g[k] = g[k] + b[k]
+    g["files"] = list(g)
+    return g
+
+
+@pytest.mark.parametrize("name", [n for n in GOLDEN_CASES if not n.endswith("_b")])
 def test_against_golden_fixture(cuda, name):
+    """The CUDA path against committed oracle outputs (tests/golden/make_golden.py).  Domain means: the family-wise
+    3-sigma bound of tests/cases.py (FLAT 3 sigma per quantity for landsat_rr_hi, the bench.py workload, where 6.4e7
+    oracle photons and 1e9 GPU photons give sigma(meanFluxUp) ~ 1e-4); per-column fields in blocks of 8x8 columns."""
+    from tests.cases import familywise_bound
     make, params, source, nph, nb = GOLDEN_CASES[name]
-    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    g = _load_golden(name)
+    nbo = int(g["numBatches"])
     I = make_integrator(cuda, make(), **params)
-    nbg = 16
-    got = run_batches(I, nph * 2, nbg, source=source)
-    for k in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed"):
+    if name == "les_mid_split":  # large enough for new_Integrator to choose the layer-compacted field by itself
+        assert cuda.get_layout(I.handle, 0) > 0, "expected the SPLIT kernel (layer-compacted extinction field)"
+    nphg, nbg = GOLDEN_GPU_SIZE.get(name, (nph * 2, 16))
+    got = run_batches(I, nphg, nbg, source=source)
+    dof = min(nbg, nbo) - 1
+    flat = name == "landsat_rr_hi"
+    means = ["meanFluxUp", "meanFluxDown", "meanFluxAbsorbed"]
+    zs = []
+    for k in means:
         m, s = mean_se(got[k])
-        z = (m - g[k + "_mean"]) / np.sqrt(s**2 + g[k + "_se"] ** 2 + 1e-16)
-        assert abs(z) < 3.0 + 0.5, (name, k, z)
+        zs.append((m - g[k + "_mean"]) / np.sqrt(s**2 + g[k + "_se"] ** 2 + 1e-16))
+    bound = 3.0 if flat else familywise_bound(len(zs), dof)
+    assert np.all(np.abs(zs) <= bound), (name, means, zs, bound)
     m, s = mean_se(got["absorbedProfile"])
     z = (m - g["absorbedProfile_mean"]) / np.sqrt(s**2 + g["absorbedProfile_se"] ** 2 + 1e-20)
-    assert np.abs(z).max() < 4.5, (name, "absorbedProfile", np.abs(z).max())
-    if "meanRadiance_mean" in g.files:
+    assert np.abs(z).max() <= familywise_bound(z.size, dof), (name, "absorbedProfile", np.abs(z).max())
+    f = int(g["coarsen"]) if "coarsen" in g["files"] else 1  # (fixture already stored as block means)
+
+    def blocks(per_batch, gm, gs):  # per_batch [nb, x, y(, d)], fixture [(d,) y, x] -> z per 8x8 block
+        gm, gs = np.moveaxis(gm.T, -1, -1), gs.T
+        fb = 8 // f if (per_batch.shape[1] % 8 == 0 and per_batch.shape[2] % 8 == 0) else 1
+        m, s = mean_se(np.stack([_coarsen(b, 8 if fb * f == 8 else 1) for b in per_batch]))
+        if fb > 1:
+            gm_c, gs_c = _coarsen(gm, fb), np.sqrt(_coarsen(gs**2, fb) / fb**2)
+        else:
+            gm_c, gs_c = gm, gs
+        return (m - gm_c) / np.sqrt(s**2 + gs_c**2 + 1e-20)
+
+    if "meanRadiance_mean" in g["files"]:
         m, s = mean_se(got["meanIntensity"])
         z = (m - g["meanRadiance_mean"]) / np.hypot(s, g["meanRadiance_se"])
-        assert np.all(np.abs(z) < 3.0 + 0.5), (name, "meanRadiance", z)
-        # per-column radiance, coarsened to blocks of 8x8 columns
-        gm, gs = g["radiance_mean"].transpose(2, 1, 0), g["radiance_se"].transpose(2, 1, 0)  # [x, y, d]
-        m, s = mean_se(np.stack([_coarsen(b) for b in got["intensity"]]))
-        gm_c = _coarsen(gm)
-        gs_c = np.sqrt(_coarsen(gs**2) / (gm.size / gm_c.size)) if gm_c.shape != gm.shape else gs
-        z = (m - gm_c) / np.sqrt(s**2 + gs_c**2 + 1e-20)
-        assert np.abs(z).max() < 5.0 and np.mean(z**2) < 1.6, (name, "radiance", np.abs(z).max(), np.mean(z**2))
-    # per-column upward flux, coarsened
-    gm, gs = g["fluxUp_mean"].T, g["fluxUp_se"].T
-    m, s = mean_se(np.stack([_coarsen(b) for b in got["fluxUp"]]))
-    gm_c = _coarsen(gm)
-    gs_c = np.sqrt(_coarsen(gs**2) / (gm.size / gm_c.size)) if gm_c.shape != gm.shape else gs
-    z = (m - gm_c) / np.sqrt(s**2 + gs_c**2 + 1e-20)
-    assert np.abs(z).max() < 5.0 and np.mean(z**2) < 1.6, (name, "fluxUp", np.abs(z).max(), np.mean(z**2))
-    cnt = got["counters"]
-    for c in ("collisions", "crossings_photon"):
-        a, b = cnt[c] / cnt["photons"], float(g["cnt_" + c]) / float(g["cnt_photons"])
-        assert abs(a - b) < 0.03 * b + 0.02, (c, a, b)
+        assert np.all(np.abs(z) <= (3.0 if flat else familywise_bound(z.size, dof))), (name, "meanRadiance", z)
+        z = blocks(got["intensity"], g["radiance_mean"], g["radiance_se"])
+        assert np.abs(z).max() <= familywise_bound(z.size, dof) and np.mean(z**2) < 1.6, (name, "radiance", np.abs(z).max(), np.mean(z**2))
+    z = blocks(got["fluxUp"], g["fluxUp_mean"], g["fluxUp_se"])
+    assert np.abs(z).max() <= familywise_bound(z.size, dof) and np.mean(z**2) < 1.6, (name, "fluxUp", np.abs(z).max(), np.mean(z**2))
+    ref_cnt = {k[4:]: float(g[k]) for k in g["files"] if k.startswith("cnt_")}
+    assert_counter_parity(got, ref_cnt, ("collisions", "crossings_photon", "exits_top"), label=name + ": ")
 
 
 # ---- size-independent properties at benchmark size ---------------------------------------------------------------
@@ -503,3 +537,104 @@ def test_translation_invariance_of_the_periodic_domain(cuda, case):
                                   dict(surfaceAlbedo=0.2, intensityMus=[1.0, 0.5, -0.7], intensityPhis=[0.0, 200.0, 90.0],
                                        useRussianRouletteForIntensity=False),
                                   100000, 16, source=dict(solarMu=0.5, solarAzimuth=30.0))
+
+
+# ---- round 2: device probes of the random stream and of next_direct, C-ABI validation, staged tallies ---------------
+def test_philox_on_the_device_matches_known_answers_and_numpy():
+    """Philox4x32-10 as the transport kernel runs it (csrc/philox.cuh on the GPU): the Random123 known-answer vector
+    that fits the kernel's counter layout (photon id, block, 0), and an independent numpy implementation (itself
+    checked against all three known answers, tests/test_philox_numpy.py) for random keys, photons and blocks."""
+    from i3rc_monte_carlo_model_b200._lib import backend
+    from tests.philox_numpy import photon_block, u01
+    be = backend()
+    ph = np.array([0], np.uint64)
+    bl = np.array([0], np.uint32)
+    raw, u = np.zeros(4, np.uint32), np.zeros(4, np.float32)
+    U64, U32 = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+    assert be.probe_philox(0, 0, 1, ph.ctypes.data_as(U64), bl.ctypes.data_as(U32), raw.ctypes.data_as(U32), _abi.fptr(u)) == 0
+    assert raw.tolist() == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    rng = np.random.default_rng(11)
+    n = 4096
+    ph = rng.integers(0, 2**40, n).astype(np.uint64)
+    bl = rng.integers(0, 5000, n).astype(np.uint32)
+    for key in ((10, 1), (0xFFFFFFFF, 0x9E3779B9), (123456789, 80)):
+        raw, u = np.zeros((n, 4), np.uint32), np.zeros((n, 4), np.float32)
+        assert be.probe_philox(key[0], key[1], n, ph.ctypes.data_as(U64), bl.ctypes.data_as(U32), raw.ctypes.data_as(U32),
+                               _abi.fptr(u)) == 0
+        want = photon_block(key, ph, bl)
+        assert np.array_equal(raw, want)
+        assert np.array_equal(u, u01(want))  # the deviates: bit-identical float32
+        assert u.min() >= 0.0 and u.max() <= 1.0
+
+
+def test_next_direct_on_the_device_matches_the_oracle(oracle):
+    """next_direct (MCRT:2086-2113) exactly as the kernel runs it -- rejection rounds fed by the photon's Philox blocks --
+    against the oracle's next_direct fed with the same deviates (numpy Philox): 1e-6 absolute on direction cosines."""
+    from i3rc_monte_carlo_model_b200._lib import backend
+    from tests.philox_numpy import photon_block, u01
+    be = backend()
+    rng = np.random.default_rng(3)
+    n = 4000
+    S = rng.standard_normal((n, 3))
+    S[:5] = [[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, 1, 0], [0.6, 0, 0.8]]
+    S = (S / np.linalg.norm(S, axis=1, keepdims=True)).astype(np.float32)
+    cs = np.cos(rng.random(n) * np.pi).astype(np.float32)
+    cs[:3] = [1.0, -1.0, 0.0]
+    ph = rng.integers(0, 2**33, n).astype(np.uint64)
+    bl = rng.integers(0, 100, n).astype(np.uint32)
+    key = (10, 7)
+    out, used = np.zeros((n, 3), np.float32), np.zeros(n, np.uint32)
+    U64, U32 = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+    assert be.probe_next_direct(key[0], key[1], n, ph.ctypes.data_as(U64), bl.ctypes.data_as(U32), _abi.fptr(S), _abi.fptr(cs),
+                                _abi.fptr(out), used.ctypes.data_as(U32)) == 0
+    nblk = 8  # deviates of 8 blocks = 16 rejection rounds: (1 - pi/4)^16 ~ 2e-11 that it is not enough
+    xi = np.concatenate([u01(photon_block(key, ph, bl.astype(np.uint64) + k)) for k in range(nblk)], axis=1)  # [n, 4*nblk]
+    want = S.copy()
+    rounds = np.zeros(n, int)
+    for i in range(n):
+        x = np.ascontiguousarray(xi[i])
+        oracle.lib.orc_next_direct(_abi.fptr(x), x.size, float(cs[i]), _abi.fptr(want[i]))
+        ax, ay = 1 - 2 * x[0::2], 1 - 2 * x[1::2]
+        rounds[i] = np.argmax(ax * ax + ay * ay <= 1.0) + 1
+    assert np.array_equal(used, (rounds + 1) // 2)  # two rounds per Philox block
+    assert np.max(np.abs(out - want)) < 2e-6
+    assert np.max(np.abs(np.linalg.norm(out.astype(np.float64), axis=1) - 1.0)) < 1e-5
+    dots = np.sum(out.astype(np.float64) * S, axis=1)
+    assert np.max(np.abs(dots - cs)) < 1e-5  # the new direction makes the scattering angle with the old one
+
+
+def test_components_are_validated_inside_the_c_abi(cuda):
+    """validateOpticalComponent's value checks (Code/opticalProperties.f95:966-975) hold for callers that hand file data
+    straight to the C ABI (the C++ drivers, the Fortran shim): the arrays are altered behind the Python mirror's back."""
+    for field, value, text in (("extinction", -1.0, "extinction must be >= 0"),
+                               ("singleScatteringAlbedo", 1.5, "singleScatteringAlbedo must be between 0 and 1"),
+                               ("phaseFunctionIndex", 2, "phase function index is out of bounds"),
+                               ("phaseFunctionIndex", -1, "phase function index is out of bounds")):
+        d = fields.step_cloud(0.99)
+        getattr(d.components[0], field)[3, 0, 5] = value
+        st = ErrorMessage()
+        I = new_Integrator(d, status=st, backend=cuda)
+        assert stateIsFailure(st) and not I.handle
+        assert text in cuda.last_message(None).decode(), (field, cuda.last_message(None))
+
+
+def test_tallies_staged_in_shared_memory_equal_global_atomics(cuda):
+    """Few-column domains keep per-warp tallies in shared memory (warp-aggregated, then one block-level sum and one
+    global atomic per element); the result must equal the plain global-atomic path photon for photon (same Philox
+    streams), up to float32 summation order."""
+    for make, kw in ((lambda: fields.plane_parallel(), dict(useRussianRouletteForIntensity=False)),
+                     (lambda: fields.step_cloud(0.99), dict(useRussianRouletteForIntensity=True, zetaMin=0.3)),
+                     (lambda: fields.plane_parallel(nX=3, nY=2, nLayers=4, SSA=0.9), dict())):
+        res = []
+        for stage in (1536, 0):
+            I = make_integrator(cuda, make(), surfaceAlbedo=0.3, intensityMus=[1.0, 0.5, 0.5], intensityPhis=[0.0, 0.0, 180.0], **kw)
+            assert cuda.set_tuning(I.handle, b"stage_tallies", stage) == 0
+            assert (cuda.get_layout(I.handle, 1) > 0) == (stage > 0)
+            ph = new_PhotonStream(0.5, 0.0, numberOfPhotons=300_000)
+            computeRadiativeTransfer(I, new_RandomNumberSequence([10, 1]), ph)
+            r = reportResults(I, "fluxUp", "fluxDown", "fluxAbsorbed", "intensity", "volumeAbsorption", "meanFluxUp")
+            res.append((r, getCounters(I)))
+        (a, ca), (b, cb) = res
+        assert ca == cb
+        for k in ("fluxUp", "fluxDown", "fluxAbsorbed", "intensity", "volumeAbsorption"):
+            assert np.allclose(a[k], b[k], rtol=2e-4, atol=1e-7), (k, np.max(np.abs(a[k] - b[k])))

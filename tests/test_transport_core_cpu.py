@@ -7,7 +7,7 @@ import pytest
 from i3rc_monte_carlo_model_b200 import fields
 from i3rc_monte_carlo_model_b200.monteCarloIllumination import new_PhotonStream
 from i3rc_monte_carlo_model_b200.monteCarloRadiativeTransfer import getTable, traceRays
-from tests.cases import assert_statistical_parity, make_integrator, run_batches
+from tests.cases import assert_counter_parity, assert_statistical_parity, make_integrator, run_batches
 from tests.hostsim.binding import HostSim, dense_from_domain, philox
 from tests.test_oracle_pins import _f64_optical_path
 
@@ -26,15 +26,17 @@ def _hostsim_batches(hs, nph, nb, source=None, iseed=10, **params):
     if "intensityMus" in params:
         keys += ["meanIntensity", "intensity"]
     acc = {k: [] for k in keys}
-    counters = {}
+    counters, cnts = {}, []
     for b in range(1, nb + 1):
         r = hs.run(new_PhotonStream(numberOfPhotons=nph, **source), (iseed, b), **params)
         for k in keys:
             acc[k].append(np.asarray(r[k], np.float64))
+        cnts.append(r["counters"])
         for k, v in r["counters"].items():
             counters[k] = counters.get(k, 0) + v
     out = {k: np.stack(v) for k, v in acc.items()}
     out["counters"] = counters
+    out["counters_batches"] = {k: np.array([c[k] for c in cnts], np.float64) for k in cnts[-1]}
     return out
 
 
@@ -64,9 +66,8 @@ def test_transport_core_matches_oracle(oracle, name):
     got = _hostsim_batches(HostSim(d, I, getTable), nph, nb, **params)
     assert_statistical_parity(got, ref, label=name + ": ")
     # event counters per photon agree within Monte Carlo noise
-    for c in ("collisions", "crossings_photon", "surface_hits"):
-        a, b = got["counters"][c] / got["counters"]["photons"], ref["counters"][c] / ref["counters"]["photons"]
-        assert abs(a - b) <= 0.05 * max(b, 0.02) + 0.02, (c, a, b)
+    total = {k: float(v.sum()) for k, v in ref["counters_batches"].items()}
+    assert_counter_parity(got, total, ("collisions", "crossings_photon", "surface_hits"), label=name + ": ")
 
 
 def test_transport_core_is_deterministic_per_photon(oracle):
