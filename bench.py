@@ -248,8 +248,8 @@ def ncu_one_launch(args, nph, timeout=240):
         cmd_tail += ["--tune", args.tune]
     for metrics in (NCU_METRICS + NCU_EXTRA, NCU_METRICS):
         with tempfile.NamedTemporaryFile("r", suffix=".csv") as f:
-            cmd = ["ncu", "--metrics", ",".join(metrics), "--clock-control", "none", "-k", "regex:k_transport", "-s", "2", "-c", "1",
-                   "--csv", "--log-file", f.name] + cmd_tail  # (-s 2: the table-building photon and the warm-up batch)
+            cmd = ["ncu", "--metrics", ",".join(metrics), "--clock-control", "none", "-k", "regex:k_transport", "-s", "1", "-c", "1",
+                   "--csv", "--log-file", f.name] + cmd_tail  # (-s 1: the probe's first batch warms up, the second is captured)
             try:
                 r = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout,
                                    env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0")))

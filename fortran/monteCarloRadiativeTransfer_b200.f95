@@ -11,7 +11,7 @@ module monteCarloRadiativeTransfer
                                getInfo_PhaseFunction, getPhaseFunctionCoefficients, getPhaseFunctionValues
   use opticalProperties, only: domain, getInfo_Domain, getOpticalPropertiesByComponent
   use surfaceProperties, only: surfaceDescription
-  use monteCarloIllumination, only: photonStream
+  use monteCarloIllumination, only: photonStream, i3rc_photon_source, descriptorOf   ! fortran/monteCarloIllumination_b200.f95
   implicit none
   private
 
@@ -42,14 +42,7 @@ module monteCarloRadiativeTransfer
     integer(c_int32_t) :: surf_nx, surf_ny
     type(c_ptr)        :: surf_x, surf_y, surf_params
   end type
-  type, bind(c) :: i3rc_photon_source
-    integer(c_int32_t) :: kind, reserved
-    integer(c_int64_t) :: numberOfPhotons
-    real(c_float)      :: solarMu, solarAzimuth, x, y, z, detectorMu, detectorPhi
-    integer(c_int32_t) :: detectorPointsUp, has_deltaX, has_deltaY
-    real(c_float)      :: deltaX, deltaY
-    type(c_ptr)        :: xPosition, yPosition, zPosition, initialMu, initialPhi
-  end type
+  ! (i3rc_photon_source is declared by the replacement module monteCarloIllumination, which fills it)
 
   interface
     integer(c_int) function i3rc_new_Integrator(nx, ny, nz, nc, xPos, yPos, zPos, totalExt, cumExt, ssa, pfIndex, h) bind(c)
@@ -208,28 +201,24 @@ contains
   end subroutine
 
   ! ---- computeRadiativeTransfer (monteCarloRadiativeTransfer.f95:262-398)
-  ! The photonStream of the replacement module monteCarloIllumination is a descriptor (kind + parameters); a stream whose
-  ! public arrays were filled by hand is passed as I3RC_SRC_ARRAYS.  The seed vector that created randomNumbers keys the
-  ! per-photon Philox streams (randomNumbers%state(0:1) after new_RandomNumberSequence holds no trace of the seed, so the
-  ! replacement RandomNumbers module keeps a copy in the type: randomNumbers%seed).
+  ! The photonStream of the replacement module monteCarloIllumination carries a descriptor (kind + parameters); a stream
+  ! whose public arrays were filled by hand is passed as I3RC_SRC_ARRAYS (descriptorOf).  The seed vector that created
+  ! randomNumbers keys the per-photon Philox streams: the replacement module RandomNumbers keeps it in the type
+  ! (randomNumbers%seed, %nSeed), because the twister's state holds no recoverable trace of it.
   subroutine computeRadiativeTransfer(thisIntegrator, randomNumbers, incomingPhotons, status)
     type(integrator), intent(inout) :: thisIntegrator
     type(randomNumberSequence), intent(inout) :: randomNumbers
     type(photonStream), intent(inout) :: incomingPhotons
     type(ErrorMessage), intent(inout) :: status
     type(i3rc_photon_source) :: src
-    src = incomingPhotons%descriptor          ! filled by the new_PhotonStream_* constructors of the replacement module
-    if (associated(incomingPhotons%xPosition) .and. src%kind == 7) then
-      src%numberOfPhotons = size(incomingPhotons%xPosition)
-      src%xPosition = c_loc(incomingPhotons%xPosition); src%yPosition = c_loc(incomingPhotons%yPosition)
-      src%zPosition = c_loc(incomingPhotons%zPosition); src%initialMu = c_loc(incomingPhotons%initialMu)
-      src%initialPhi = c_loc(incomingPhotons%initialPhi)
-    end if
-    call toStatus(i3rc_computeRadiativeTransfer(thisIntegrator%handle, src, randomNumbers%seed, size(randomNumbers%seed)), &
+    integer(c_int32_t) :: seed(2)
+    src  = descriptorOf(incomingPhotons)
+    seed = randomNumbers%seed
+    call toStatus(i3rc_computeRadiativeTransfer(thisIntegrator%handle, src, seed, min(max(randomNumbers%nSeed, 1), 2)), &
                   thisIntegrator%handle, status, "computeRadiativeTransfer")
     if (.not. stateIsFailure(status)) then
       call setStateToCompleteSuccess(status, "computeRadiativeTransfer: finished with photons")
-      incomingPhotons%currentPhoton = int(src%numberOfPhotons) + 1
+      incomingPhotons%currentPhoton = int(src%numberOfPhotons) + 1      ! the stream is used up (MCRT:472, 700)
     end if
   end subroutine
 
@@ -243,18 +232,45 @@ contains
     real, dimension(:, :, :), optional, target, contiguous, intent(out) :: volumeAbsorption, intensity
     type(ErrorMessage), intent(inout) :: status
     type(c_ptr) :: p(10)
+    integer :: nX, nY, nZ, nD
+    nX = thisIntegrator%nX; nY = thisIntegrator%nY; nZ = thisIntegrator%nZ; nD = thisIntegrator%nDirections
     p(:) = c_null_ptr
     if (present(meanFluxUp)) p(1) = c_loc(meanFluxUp)
     if (present(meanFluxDown)) p(2) = c_loc(meanFluxDown)
     if (present(meanFluxAbsorbed)) p(3) = c_loc(meanFluxAbsorbed)
     if (present(fluxUp)) then
-      if (any(shape(fluxUp) /= (/ thisIntegrator%nX, thisIntegrator%nY /))) then
-        call setStateToFailure(status, "reportResults: fluxUp array is the wrong size"); return
-      end if
+      if (any(shape(fluxUp) /= (/ nX, nY /))) call setStateToFailure(status, "reportResults: fluxUp array is the wrong size")
       p(4) = c_loc(fluxUp)
     end if
-    ! ... fluxDown, fluxAbsorbed, absorbedProfile (nZ), volumeAbsorption (nX,nY,nZ), meanIntensity (nDirections),
-    !     intensity (nX,nY,nDirections): same size check, same message texts as the reference, then c_loc.
+    if (present(fluxDown)) then
+      if (any(shape(fluxDown) /= (/ nX, nY /))) call setStateToFailure(status, "reportResults: fluxDown array is the wrong size")
+      p(5) = c_loc(fluxDown)
+    end if
+    if (present(fluxAbsorbed)) then
+      if (any(shape(fluxAbsorbed) /= (/ nX, nY /))) &
+        call setStateToFailure(status, "reportResults: fluxAbsorbed array is the wrong size")
+      p(6) = c_loc(fluxAbsorbed)
+    end if
+    if (present(absorbedProfile)) then
+      if (size(absorbedProfile) /= nZ) call setStateToFailure(status, "reportResults: absorbedProfile array is the wrong size")
+      p(7) = c_loc(absorbedProfile)
+    end if
+    if (present(volumeAbsorption)) then
+      if (any(shape(volumeAbsorption) /= (/ nX, nY, nZ /))) &
+        call setStateToFailure(status, "reportResults: volumeAbsorption array is the wrong size")
+      p(8) = c_loc(volumeAbsorption)
+    end if
+    if (present(meanIntensity)) then
+      if (nD == 0) call setStateToFailure(status, "reportResults: intensity information not available")
+      if (size(meanIntensity) /= nD) call setStateToFailure(status, "reportResults: requesting mean intensity in the wrong number of directions.")
+      p(9) = c_loc(meanIntensity)
+    end if
+    if (present(intensity)) then
+      if (nD == 0) call setStateToFailure(status, "reportResults: intensity information not available")
+      if (any(shape(intensity) /= (/ nX, nY, nD /))) call setStateToFailure(status, "reportResults: intensity array has wrong dimensions.")
+      p(10) = c_loc(intensity)
+    end if
+    if (stateIsFailure(status)) return
     call toStatus(i3rc_reportResults(thisIntegrator%handle, p(1), p(2), p(3), p(4), p(5), p(6), p(7), p(8), p(9), p(10)), &
                   thisIntegrator%handle, status, "reportResults")
   end subroutine

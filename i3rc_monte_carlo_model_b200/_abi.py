@@ -129,6 +129,7 @@ COUNTER_FIELDS = [
     "rng_draws",
     "roulette_kills",
     "null_collisions",
+    "cells_skipped",
 ]
 
 

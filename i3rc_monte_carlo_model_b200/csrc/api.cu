@@ -62,6 +62,9 @@ struct i3rc_integrator {
   float *d_xe = nullptr, *d_ye = nullptr, *d_ze = nullptr;
   float *d_ext = nullptr, *d_cum = nullptr, *d_ssa = nullptr;
   float* d_extRaw = nullptr;  // un-normalised extinction of every component (kept from the first profile swap on)
+  float* d_extJ = nullptr;    // the gather field with empty-space codes (transport.cuh JUMP_*), when that pays
+  double codedFraction = 0.0; // share of the cells that carry a code
+  int skipEmpty = 1;          // (tuning) 0: never use empty-space codes
   float* d_extZ = nullptr;  // totalExt again, z-fastest: the copy the rays gather from (see Problem::ext)
   int2* d_zlut = nullptr;   // layer table when only the horizontally varying layers are stored (Problem::zlut)
   int nzc = 0;
@@ -279,6 +282,35 @@ int build_gather_field(i3rc_integrator* h) {
   CUDA_OK(h, cudaMemcpyAsync(&bits, d_max, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
   memcpy(&h->maxExt, &bits, sizeof(float));
+  // Empty-space codes: a second copy of the gather field in which empty cells far from any extinction say how far a ray
+  // may run without looking (regular grids, every layer stored, L2-resident fields wider than two maximal jumps).
+  dfree(h->d_extJ);
+  h->codedFraction = 0.0;
+  if (const char* e = getenv("I3RC_SKIP_EMPTY")) h->skipEmpty = atoi(e);  // (development switch)
+  if (h->skipEmpty && h->xyRegular && h->zRegular && h->nzc == 0 && nx > 2 * JUMP_MAX && ny > 2 * JUMP_MAX &&
+      ncell * sizeof(float) <= ((size_t)48 << 20)) {
+    DevTemp t_D, t_cnt;
+    uint8_t* d_D = nullptr;
+    unsigned long long* d_cnt = nullptr;
+    CUDA_OK(h, cudaMalloc(&d_D, ncell));
+    t_D.p = d_D;
+    CUDA_OK(h, cudaMalloc(&d_cnt, sizeof(unsigned long long)));
+    t_cnt.p = d_cnt;
+    CUDA_OK(h, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), h->stream));
+    CUDA_OK(h, cudaMalloc(&h->d_extJ, sizeof(float) * ncell));
+    const unsigned nb = (unsigned)((ncell + 255) / 256);
+    k_empty_init<<<nb, 256, 0, h->stream>>>(h->d_extZ, ncell, d_D);
+    for (int k = 1; k <= JUMP_MAX + 2; k++) k_empty_grow<<<nb, 256, 0, h->stream>>>(nx, ny, nz, k, d_D);
+    int jumpMin = JUMP_MIN;
+    if (const char* e = getenv("I3RC_JUMP_MIN")) jumpMin = std::max(2, std::min(JUMP_MAX, atoi(e)));  // (development switch)
+    k_empty_code<<<nb, 256, 0, h->stream>>>(h->d_extZ, d_D, ncell, jumpMin, h->d_extJ, d_cnt);
+    h->otherLaunches += JUMP_MAX + 4;
+    unsigned long long cnt = 0;
+    CUDA_OK(h, cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    h->codedFraction = (double)cnt / (double)ncell;
+    if (h->codedFraction < 0.02) dfree(h->d_extJ);  // hardly any empty space: the plain kernels are the faster ones
+  }
   return I3RC_SUCCESS;
 }
 
@@ -581,9 +613,9 @@ int fill_source(i3rc_integrator* h, const i3rc_photon_source* s, SourceDev& d) {
   return I3RC_SUCCESS;
 }
 
-template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP, bool TSM = false>
+template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP, bool TSM = false, bool JUMP = false>
 int launch_transport_t(i3rc_integrator* h, const Problem& p) {
-  auto kern = k_transport<BLOCK, REG, FAST, SPLIT, MINB, STEPS, NSLOT, QCAP, TSM>;
+  auto kern = k_transport<BLOCK, REG, FAST, SPLIT, MINB, STEPS, NSLOT, QCAP, TSM, JUMP>;
   const size_t dynSmem = (size_t)h->padSmem + (TSM ? sizeof(float) * (BLOCK / 32) * (size_t)p.tsmN : 0);
   if (dynSmem > 8192) CUDA_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynSmem));
   int perSM = h->blocksPerSM;
@@ -595,8 +627,9 @@ int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   long long grid = (long long)h->numSMs * perSM;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  ProblemT<REG, FAST, SPLIT> pt;
+  ProblemT<REG, FAST, SPLIT, JUMP> pt;
   static_cast<Problem&>(pt) = p;
+  if (JUMP) pt.ext = h->d_extJ;  // the copy of the gather field that carries the empty-space codes
   kern<<<(unsigned)grid, BLOCK, dynSmem, h->stream>>>(pt, h->eventThreshold, h->minRunning);
   return I3RC_SUCCESS;
 }
@@ -615,14 +648,21 @@ int launch_transport(i3rc_integrator* h, const Problem& p) {
   const bool fast = p.useRayTracing && p.src.kind != 5 && p.src.kind != 6 && !p.useSurfaceBDRF && !p.useHybrid && !p.limitContrib &&
                     !p.trackByComponent;
   if (p.tsmN > 0) {  // a domain of a few columns: tallies staged per warp in shared memory (warp_tally, kernels.cuh)
-    if (reg && fast) return launch_transport_t<128, true, true, false, 5, 16, 64, 64, true>(h, p);
-    if (reg) return launch_transport_t<128, true, false, false, 5, 16, 64, 64, true>(h, p);
-    return launch_transport_t<128, false, false, false, 5, 16, 64, 64, true>(h, p);
+    // (SPLIT = true: these variants honour a layer table when there is one, see ext_gather)
+    if (reg && fast) return launch_transport_t<128, true, true, true, 5, 16, 64, 64, true>(h, p);
+    if (reg) return launch_transport_t<128, true, false, true, 5, 16, 64, 64, true>(h, p);
+    return launch_transport_t<128, false, false, true, 5, 16, 64, 64, true>(h, p);
   }
   if (p.nzc) {  // only the horizontally varying layers are stored (large fields): the gathers look the layer up first
     if (reg && fast) return launch_transport_t<128, true, true, true, 5, 16, 64, 64>(h, p);
     if (reg) return launch_transport_t<128, true, false, true, 5, 16, 64, 64>(h, p);
     return launch_transport_t<128, false, false, true, 5, 16, 64, 64>(h, p);
+  }
+  if (reg && h->d_extJ && p.useRayTracing) {  // enough empty space for the rays to jump through it
+    const int blocks = h->residentBlocks ? h->residentBlocks : 6;
+    if (fast) return blocks == 5 ? launch_transport_t<128, true, true, false, 5, 16, 64, 64, false, true>(h, p)
+                                 : launch_transport_t<128, true, true, false, 6, 16, 64, 64, false, true>(h, p);
+    return launch_transport_t<128, true, false, false, 5, 16, 64, 64, false, true>(h, p);
   }
   if (reg && fast) {
     // resident blocks per SM, 0 = automatic: 6 while the extinction field is L2-resident; 5 (more of the 256 KB left as
@@ -822,6 +862,7 @@ int fetch_counters(i3rc_integrator* h) {
   o.rng_draws = c[CNT_RNG];
   o.roulette_kills = c[CNT_KILL];
   o.null_collisions = c[CNT_NULL];
+  o.cells_skipped = c[CNT_SKIP];
   return I3RC_SUCCESS;
 }
 
@@ -1085,6 +1126,7 @@ void i3rc_finalize_Integrator(i3rc_integrator* h) {
   dfree(h->d_ze);
   dfree(h->d_ext);
   dfree(h->d_extRaw);
+  dfree(h->d_extJ);
   dfree(h->d_extZ);
   dfree(h->d_zlut);
   dfree(h->d_cum);
@@ -1894,6 +1936,7 @@ int i3rc_get_layout(i3rc_integrator* h, int what) {
     fill_problem(h, p);
     return p.tsmN;
   }
+  if (what == 2) return h->d_extJ ? (int)(h->codedFraction * 1000.0 + 0.5) : 0;  // per mille of cells with an empty-space code
   return -1;
 }
 
@@ -1920,7 +1963,10 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->eventThreshold = value;
   else if (k == "track_by_component")
     h->trackByComponent = value != 0;
-  else if (k == "stage_tallies" && value >= 0 && value <= 4096)
+  else if (k == "skip_empty" && (value == 0 || value == 1)) {
+    h->skipEmpty = value;  // 0: drop the coded copy of the field (takes effect at once); 1: at the next new_Integrator
+    if (!value) dfree(h->d_extJ);
+  } else if (k == "stage_tallies" && value >= 0 && value <= 4096)
     h->stageTallies = value;  // floats of shared memory per warp for staged tallies; 0 = global atomics only
   else
     return fail(h, "set_tuning: unknown key or bad value");

@@ -110,8 +110,8 @@ __device__ __forceinline__ void flush_staged_tallies(const P& p, const float* sd
   }
 }
 
-template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP, bool TSM = false>
-__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, FAST, SPLIT> p, const int lowWater, const int minRunning) {
+template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP, bool TSM = false, bool JUMP = false>
+__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, FAST, SPLIT, JUMP> p, const int lowWater, const int minRunning) {
   constexpr int NW = BLOCK / 32;
   extern __shared__ float s_dyn[];  // TSM: NW private copies of the staged tallies (Problem::tsmN floats each)
   using Tally = typename std::conditional<TSM, TallyLater, TallyNow>::type;
@@ -690,6 +690,49 @@ __global__ void k_transpose_zfast(int nx, int ny, int nz, const float* __restric
     const int ix = x0 + k, iz = z0 + threadIdx.x;
     if (ix < nx && iz < nz) out[((size_t)ix * ny + iy) * nz + iz] = tile[threadIdx.x][k];
   }
+}
+
+// ---- empty-space codes (transport.cuh, JUMP_MIN / JUMP_MAX) -----------------------------------------------------------
+// D[cell] = Chebyshev distance (in cells; periodic in x and y, nothing beyond the top and the bottom) to the nearest cell
+// with extinction, grown one shell per launch: 0 = the cell has extinction, 255 = not reached yet.  Layout of the gather
+// field (z fastest).
+__global__ void k_empty_init(const float* __restrict__ ext, size_t n, uint8_t* __restrict__ D) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) D[i] = ext[i] > 0.0f ? 0 : 255;
+}
+__global__ void k_empty_grow(int nx, int ny, int nz, int k, uint8_t* D) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)nx * ny * nz || D[i] != 255) return;
+  const int iz = (int)(i % nz), iy = (int)((i / nz) % ny), ix = (int)(i / ((size_t)nz * ny));
+  bool hit = false;
+  for (int dx = -1; dx <= 1 && !hit; dx++) {
+    const int jx = (ix + dx + nx) % nx;
+    for (int dy = -1; dy <= 1 && !hit; dy++) {
+      const int jy = (iy + dy + ny) % ny;
+      for (int dz = -1; dz <= 1; dz++) {
+        const int jz = iz + dz;
+        if (jz < 0 || jz >= nz) continue;
+        if (D[((size_t)jx * ny + jy) * nz + jz] == k - 1) {  // (shell k-1 is complete; this launch only writes k)
+          hit = true;
+          break;
+        }
+      }
+    }
+  }
+  if (hit) D[i] = (uint8_t)k;
+}
+// coded copy of the field: an empty cell at distance D >= jumpMin + 2 holds -(min(D - 2, JUMP_MAX)); counts the coded cells
+__global__ void k_empty_code(const float* __restrict__ ext, const uint8_t* __restrict__ D, size_t n, int jumpMin,
+                             float* __restrict__ coded, unsigned long long* __restrict__ count) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float e = ext[i];
+  const int d = D[i];
+  if (d >= jumpMin + 2) {
+    e = -(float)min(d - 2, JUMP_MAX);
+    atomicAdd(count, 1ull);
+  }
+  coded[i] = e;
 }
 
 // per layer: are all cells of the layer equal?  out[iz] = {min bits, max bits} (extinctions are >= 0: bits order = value order)

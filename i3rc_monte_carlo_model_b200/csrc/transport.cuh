@@ -69,7 +69,12 @@ constexpr int DIR_STRIDE = 8;
 constexpr int MAX_RAY_STEPS = 1 << 26;  // hang protection: a ray that long is dropped as "bad"
 
 enum { CNT_PHOTONS = 0, CNT_BAD, CNT_CROSS_PH, CNT_CROSS_LE, CNT_COLL, CNT_ABS, CNT_CONTRIB, CNT_TOP, CNT_SURF,
-       CNT_RNG, CNT_KILL, CNT_NULL, CNT_N };
+       CNT_RNG, CNT_KILL, CNT_NULL, CNT_SKIP, CNT_N };
+// Empty-space codes (Problem::ext of a JUMP kernel): an empty cell whose whole Chebyshev neighbourhood of radius n + 1 is
+// empty (periodic in x and y; beyond the top and the bottom counts as empty) holds -n instead of 0, for n in
+// [JUMP_MIN, JUMP_MAX].  A ray that has just crossed such a cell may cross up to n further cells on every axis without
+// looking at them (ray_advance_far).
+constexpr int JUMP_MIN = 3, JUMP_MAX = 15;
 
 enum { DONE_RUN = 0, DONE_INSIDE = 1, DONE_TOP = 2, DONE_BOTTOM = 3, DONE_BAD = 4,
        DONE_IDLE = 5,   // warp-cooperative kernel: the lane holds no ray
@@ -145,17 +150,21 @@ struct Problem {
 // functions, no contribution limiting): the rarely used code paths are compiled out, which keeps the kernel's
 // instruction footprint small (the SM's instruction cache holds ~32 KB).
 // SPLIT = the field stores only the horizontally varying layers (Problem::zlut): the gather first looks the layer up.
-template <bool REG, bool FAST = false, bool SPLIT = false>
+// JUMP = the field carries empty-space codes (above) and the rays use them (regular grids, every layer stored).
+template <bool REG, bool FAST = false, bool SPLIT = false, bool JUMP = false>
 struct ProblemT : Problem {
   static constexpr bool kRegular = REG;
   static constexpr bool kFast = FAST;
   static constexpr bool kSplit = SPLIT;
+  static constexpr bool kJump = JUMP;
+  static_assert(!JUMP || (REG && !SPLIT), "empty-space codes: regular grids with every layer stored");
 };
 // the general-purpose instantiation (probes, CPU harness): the layer table is honoured at run time
 struct ProblemDyn : Problem {
   static constexpr bool kRegular = false;
   static constexpr bool kFast = false;
   static constexpr bool kSplit = true;
+  static constexpr bool kJump = false;
 };
 
 I3RC_HD int ext_index(const Problem& p, int ix, int iy, int iz) { return ix * p.esx + iy * p.esy + iz * p.esz; }
@@ -416,6 +425,45 @@ I3RC_HD bool ray_advance(const P& p, Lane& L) {
   L.sp = s;
   return out;
 }
+// The same through up to n cells on every axis at once (n >= 2), all of them known to be empty: the geometry moves
+// along the ray for the path length T at which the FIRST axis has crossed its n-th face (or the ray leaves the domain),
+// and every axis then counts the faces it has crossed by T.  No axis moves by more than n cells, so the cell reached and
+// all cells passed on the way lie within Chebyshev distance n of the starting cell.  Regular grids only.
+template <class P>
+I3RC_HD bool ray_advance_far(const P& p, Lane& L, int n) {
+  const float ax = fabsf(L.rx), ay = fabsf(L.ry), az = fabsf(L.rz);
+  const float fn = (float)(n - 1);
+  float T = fminf(fmaf(fn, L.iax, ax), fminf(fmaf(fn, L.iay, ay), fmaf(fn, L.iaz, az)));
+  T = fminf(T, fmaf((float)(L.cntz - 1), L.iaz, az));  // not beyond the top / the bottom of the domain
+  int mx = 0, my = 0, mz = 0;
+  float qx = ax - T, qy = ay - T, qz = az - T;
+  if (ax <= T) {
+    mx = (int)I3RC_FDIV(T - ax, L.iax) + 1;
+    qx = fmaxf(fmaf((float)mx, L.iax, ax) - T, 0.0f);
+  }
+  if (ay <= T) {
+    my = (int)I3RC_FDIV(T - ay, L.iay) + 1;
+    qy = fmaxf(fmaf((float)my, L.iay, ay) - T, 0.0f);
+  }
+  if (az <= T) {
+    mz = (int)I3RC_FDIV(T - az, L.iaz) + 1;
+    qz = fmaxf(fmaf((float)mz, L.iaz, az) - T, 0.0f);
+  }
+  mz = mz < L.cntz ? mz : L.cntz;
+  int nx_ = L.cntx - mx, ny_ = L.cnty - my, idx = L.idx + mx * L.stx + my * L.sty + mz * L.stz;
+  if (nx_ <= 0) idx -= L.stx * p.nx, nx_ += p.nx;  // periodic in x and y (n < nx, ny: at most one wrap)
+  if (ny_ <= 0) idx -= L.sty * p.ny, ny_ += p.ny;
+  L.idx = idx;
+  L.cntx = nx_;
+  L.cnty = ny_;
+  L.cntz -= mz;
+  L.rx = qx;
+  L.ry = qy;
+  L.rz = qz;
+  L.sp = T;
+  I3RC_COUNT(L, CNT_SKIP, mx + my + mz - 1);  // cells passed without a look (one of them is the ordinary step's)
+  return L.cntz == 0;
+}
 // (Re)start the pipeline from the cell the geometry is in, whose extinction is eCell: it becomes the pending cell
 // (in e0: rays always start on an even step) and the gather of the next cell is issued (into e1).
 template <class P>
@@ -474,41 +522,59 @@ I3RC_HD void start_ray(const P& p, Lane& L, float dx, float dy, float dz, float 
 // cell (ray_advance).  A ray that ends -- target optical path reached inside the pending cell (MCRT:1721-1731), or the
 // pending cell was the last one of the domain (MCRT:1793-1804) -- just stops with DONE_STOP; which of the two it was
 // and where the ray is then are worked out by ray_after_steps() / ray_stop_inside(), outside the hot loop.
+// the extinction a (possibly coded) field value stands for
+template <class P>
+I3RC_HD float ext_value(float e) { return P::kJump ? fmaxf(e, 0.0f) : e; }
+// The geometry leaves the cell it is in (which becomes the pending cell); ePending, just consumed, receives the gather of
+// the cell it arrives in.  With empty-space codes: a pending cell that says "the next n cells on every axis are empty"
+// lets the geometry run through all of them at once; they become ONE empty pending stretch (eOther, the value in flight
+// for the first of them, is replaced by a plain zero so that ITS code is not mistaken for a statement about the last).
+template <class P>
+I3RC_HD void ray_move_on(const P& p, Lane& L, float& ePending, float& eOther) {
+  if (P::kJump && ePending < 0.0f) {  // (a code: at least -JUMP_MIN, see k_empty_code)
+    const int n = (int)(-ePending);
+    eOther = 0.0f;
+    if (!ray_advance_far(p, L, n)) ePending = ext_gather(p, L.idx, ray_iz(p, L));
+    return;
+  }
+  if (!ray_advance(p, L)) ePending = ext_gather(p, L.idx, ray_iz(p, L));  // (the register is free now: it becomes the look-ahead)
+}
 template <int PAR, class P>
 I3RC_HD void dda_step(const P& p, Lane& L) {
   float& ePending = PAR ? L.e1 : L.e0;
-  const float t = fmaf(L.sp, ePending, L.tau);
+  float& eOther = PAR ? L.e0 : L.e1;
+  const float t = fmaf(L.sp, ext_value<P>(ePending), L.tau);
   L.nsteps++;
   if (t > L.tauLimit || L.cntz == 0) {
-    L.e = ePending;
+    L.e = ext_value<P>(ePending);
     L.done = DONE_STOP;
     return;
   }
   L.tau = t;
-  if (!ray_advance(p, L)) ePending = ext_gather(p, L.idx, ray_iz(p, L));  // (the register is free now: it becomes the look-ahead)
+  ray_move_on(p, L, ePending, eOther);
 }
 // Two crossings in a row, the form the kernel's trace round uses: the second step is nested in the first one's
 // "goes on" branch, so a running ray pays one test per step and nothing has to be re-examined in between.
 template <class P>
 I3RC_HD void dda_step_pair(const P& p, Lane& L) {
-  const float tA = fmaf(L.sp, L.e0, L.tau);
+  const float tA = fmaf(L.sp, ext_value<P>(L.e0), L.tau);
   if (tA > L.tauLimit || L.cntz == 0) {
     L.nsteps += 1;
-    L.e = L.e0;
+    L.e = ext_value<P>(L.e0);
     L.done = DONE_STOP;
     return;
   }
   L.tau = tA;
-  if (!ray_advance(p, L)) L.e0 = ext_gather(p, L.idx, ray_iz(p, L));
-  const float tB = fmaf(L.sp, L.e1, L.tau);
+  ray_move_on(p, L, L.e0, L.e1);
+  const float tB = fmaf(L.sp, ext_value<P>(L.e1), L.tau);
   L.nsteps += 2;
   if (tB > L.tauLimit || L.cntz == 0) {
-    L.e = L.e1;
+    L.e = ext_value<P>(L.e1);
     L.done = DONE_STOP;
     return;
   }
   L.tau = tB;
-  if (!ray_advance(p, L)) L.e1 = ext_gather(p, L.idx, ray_iz(p, L));
+  ray_move_on(p, L, L.e1, L.e0);
 }
 // one lane at a time (CPU harness, probes): the parity is kept in the lane
 template <class P>

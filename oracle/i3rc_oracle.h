@@ -113,6 +113,8 @@ typedef struct {
   int64_t crossings_photon, crossings_intensity;
   int64_t collisions, absorptions, contributions, exits_top, surface_hits;
   int64_t rng_draws, roulette_kills, null_collisions;
+  int64_t cells_skipped; /* cells a ray passed without gathering them (empty-space codes); 0 in the reference's algorithm:
+                            crossings_photon + crossings_intensity + cells_skipped = its number of cell crossings */
 } orc_counters;
 
 /* status codes shared with the product */

@@ -53,6 +53,8 @@ def lib():
     L.hostsim_run.argtypes = [C.POINTER(Args)]
     L.hostsim_philox.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
     L.hostsim_trace_rays.argtypes = [C.POINTER(Args), C.c_int, fp, fp, fp, fp, fp, ip]
+    L.hostsim_trace_rays_jump.argtypes = [C.POINTER(Args), C.c_int, fp, fp, fp, fp, fp, ip, C.POINTER(C.c_ulonglong)]
+    L.hostsim_set_jump.argtypes = [C.c_int]
     return L
 
 
@@ -183,13 +185,25 @@ class HostSim:
         res["counters"] = {n_: int(cnt[i]) for i, n_ in enumerate(CNT_NAMES)}
         return res
 
-    def trace_rays(self, pos, direction, tauLimit=None):
+    def trace_rays(self, pos, direction, tauLimit=None, jump=False):
+        """accumulateExtinctionAlongPath for explicit rays; jump=True: through the field with empty-space codes (regular
+        grids), then also returns (cells skipped, DDA steps taken)."""
         from i3rc_monte_carlo_model_b200.monteCarloIllumination import new_PhotonStream
         a, out, cnt, keep, nD = self._args(new_PhotonStream(0.5, 0.0, numberOfPhotons=1), (0, 0))
         pos, direction = _abi.f32(pos).reshape(-1, 3), _abi.f32(direction).reshape(-1, 3)
         n = pos.shape[0]
         tau, pout, idx = np.zeros(n, np.float32), np.zeros((n, 3), np.float32), np.zeros((n, 3), np.int32)
         lim = _abi.f32(tauLimit) if tauLimit is not None else None
+        if jump:
+            sk = (C.c_ulonglong * 2)()
+            rc = self.L.hostsim_trace_rays_jump(C.byref(a), n, _abi.fptr(pos), _abi.fptr(direction), _abi.fptr(lim), _abi.fptr(tau),
+                                                _abi.fptr(pout), _abi.iptr(idx), sk)
+            assert rc == 0, "empty-space codes need a regular grid"
+            return tau, pout, idx, (int(sk[0]), int(sk[1]))
         self.L.hostsim_trace_rays(C.byref(a), n, _abi.fptr(pos), _abi.fptr(direction), _abi.fptr(lim), _abi.fptr(tau),
                                   _abi.fptr(pout), _abi.iptr(idx))
         return tau, pout, idx
+
+    def set_jump(self, on):
+        """Photon batches (run) use the empty-space codes too (regular grids, ray tracing)."""
+        self.L.hostsim_set_jump(int(on))

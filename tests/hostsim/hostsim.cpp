@@ -111,10 +111,45 @@ static void fill(const HostSimArgs* a, Problem& p, std::vector<TableDesc>& td, s
 
 }  // extern "C"
 
-template <bool REG>
+// Empty-space codes on the CPU (what k_empty_init / k_empty_grow / k_empty_code do on the device), for a field in any
+// layout given by its strides: Chebyshev distance to the nearest cell with extinction, periodic in x and y.
+static int g_jump = 0;
+static std::vector<float> coded_field(const Problem& p) {
+  const int nx = p.nx, ny = p.ny, nz = p.nz;
+  const size_t n = (size_t)nx * ny * nz;
+  std::vector<float> out(p.ext, p.ext + n);
+  std::vector<uint8_t> D(n);
+  auto at = [&](int ix, int iy, int iz) { return (size_t)ext_index(p, ix, iy, iz); };
+  for (size_t i = 0; i < n; i++) D[i] = p.ext[i] > 0.0f ? 0 : 255;
+  for (int k = 1; k <= JUMP_MAX + 2; k++)
+    for (int ix = 0; ix < nx; ix++)
+      for (int iy = 0; iy < ny; iy++)
+        for (int iz = 0; iz < nz; iz++) {
+          if (D[at(ix, iy, iz)] != 255) continue;
+          bool hit = false;
+          for (int dx = -1; dx <= 1 && !hit; dx++)
+            for (int dy = -1; dy <= 1 && !hit; dy++)
+              for (int dz = -1; dz <= 1 && !hit; dz++) {
+                const int jz = iz + dz;
+                if (jz < 0 || jz >= nz) continue;
+                hit = D[at((ix + dx + nx) % nx, (iy + dy + ny) % ny, jz)] == k - 1;
+              }
+          if (hit) D[at(ix, iy, iz)] = (uint8_t)k;
+        }
+  for (size_t i = 0; i < n; i++)
+    if (D[i] >= JUMP_MIN + 2) out[i] = -(float)(D[i] - 2 < JUMP_MAX ? D[i] - 2 : JUMP_MAX);
+  return out;
+}
+
+template <bool REG, bool JUMP = false>
 static void run_lanes(const HostSimArgs* a, const Problem& p0) {
-  ProblemT<REG> p;
+  ProblemT<REG, false, false, JUMP> p;
   static_cast<Problem&>(p) = p0;
+  std::vector<float> coded;
+  if (JUMP) {
+    coded = coded_field(p0);
+    p.ext = coded.data();
+  }
   Lane L;
   memset(&L, 0, sizeof(L));
   uint32_t cnt[CNT_N] = {0};
@@ -138,17 +173,18 @@ int hostsim_run(const HostSimArgs* a) {
   std::vector<float> dirs;
   fill(a, p, td, dirs);
   // the same specialisation rule as the product's launcher (api.cu)
-  if (p.xyRegular && p.zRegular) run_lanes<true>(a, p);
+  if (p.xyRegular && p.zRegular && g_jump && p.useRayTracing) run_lanes<true, true>(a, p);
+  else if (p.xyRegular && p.zRegular) run_lanes<true>(a, p);
   else run_lanes<false>(a, p);
   return 0;
 }
 
-int hostsim_trace_rays(const HostSimArgs* a, int n, const float* pos, const float* dir, const float* tauLimit,
-                       float* tauOut, float* posOut, int* idxOut) {
-  ProblemDyn p;
-  std::vector<TableDesc> td;
-  std::vector<float> dirs;
-  fill(a, p, td, dirs);
+void hostsim_set_jump(int on) { g_jump = on; }
+}  // extern "C"
+
+template <class P>
+static void trace_rays_t(P& p, int n, const float* pos, const float* dir, const float* tauLimit, float* tauOut, float* posOut,
+                         int* idxOut, unsigned long long* skipped) {
   for (int r = 0; r < n; r++) {
     Lane L;
     memset(&L, 0, sizeof(L));
@@ -170,7 +206,35 @@ int hostsim_trace_rays(const HostSimArgs* a, int n, const float* pos, const floa
       posOut[3 * r + 2] = L.done == DONE_TOP ? p.zmax : (L.done == DONE_BOTTOM ? p.z0 : abs_z(p, iz, L.fz));
     }
     if (idxOut) { idxOut[3 * r] = ix + 1; idxOut[3 * r + 1] = iy + 1; idxOut[3 * r + 2] = iz + 1; }
+    if (skipped) skipped[0] += cnt[CNT_SKIP], skipped[1] += (unsigned long long)L.nsteps;
   }
+}
+
+extern "C" {
+// the same rays through the field with empty-space codes (regular grids); skipped[0] += cells passed without a look,
+// skipped[1] += DDA steps taken
+int hostsim_trace_rays_jump(const HostSimArgs* a, int n, const float* pos, const float* dir, const float* tauLimit,
+                            float* tauOut, float* posOut, int* idxOut, unsigned long long* skipped) {
+  Problem p0;
+  std::vector<TableDesc> td;
+  std::vector<float> dirs;
+  fill(a, p0, td, dirs);
+  if (!(p0.xyRegular && p0.zRegular)) return 1;
+  ProblemT<true, false, false, true> p;
+  static_cast<Problem&>(p) = p0;
+  std::vector<float> coded = coded_field(p0);
+  p.ext = coded.data();
+  trace_rays_t(p, n, pos, dir, tauLimit, tauOut, posOut, idxOut, skipped);
+  return 0;
+}
+
+int hostsim_trace_rays(const HostSimArgs* a, int n, const float* pos, const float* dir, const float* tauLimit,
+                       float* tauOut, float* posOut, int* idxOut) {
+  ProblemDyn p;
+  std::vector<TableDesc> td;
+  std::vector<float> dirs;
+  fill(a, p, td, dirs);
+  trace_rays_t(p, n, pos, dir, tauLimit, tauOut, posOut, idxOut, nullptr);
   return 0;
 }
 }

@@ -136,3 +136,31 @@ def test_dda_with_optical_path_limit(oracle):
     dxy = np.abs(pout[inside, :2] - pout_o[inside, :2])
     dxy = np.minimum(dxy, 500.0 - dxy)
     assert dxy.max() < 5e-3 and np.abs(pout[inside, 2] - pout_o[inside, 2]).max() < 5e-3
+
+
+def test_empty_space_jumps_along_fixed_rays(oracle):
+    """accumulateExtinctionAlongPath through the Landsat field with and without the empty-space codes (transport.cuh
+    JUMP_*; the product's code compiled for the CPU): same end cell for every ray, optical path within 1e-5 relative
+    (a jump re-derives the distances to the next cell faces, so later path lengths differ in the last bits), and the
+    steps saved are exactly the cells skipped."""
+    from i3rc_monte_carlo_model_b200.monteCarloRadiativeTransfer import getTable
+    d = fields.landsat_cloud(1.0, nLegendreCoefficients=8)
+    I = make_integrator(oracle, d, surfaceAlbedo=0.0)
+    oracle.tabulate(I.handle)
+    hs = HostSim(d, I, getTable)
+    rng = np.random.default_rng(5)
+    n = 1500
+    hi = np.array([d.xPosition[-1], d.yPosition[-1], d.zPosition[-1] - d.zPosition[0]])
+    pos = (rng.random((n, 3)) * hi + np.array([0, 0, d.zPosition[0]])).astype(np.float32)
+    mu = rng.uniform(0.05, 1.0, n) * rng.choice([-1, 1], n)
+    phi = rng.uniform(0, 2 * np.pi, n)
+    u = np.column_stack([np.sqrt(1 - mu**2) * np.cos(phi), np.sqrt(1 - mu**2) * np.sin(phi), mu]).astype(np.float32)
+    u[:6] = [[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, 1, 0], [0.6, 0, 0.8], [0, -0.6, 0.8]]  # axis-parallel rays too
+    lim = np.where(rng.random(n) < 0.5, np.inf, rng.exponential(3.0, n)).astype(np.float32)
+    lim[2:4] = 5.0  # (horizontal rays never leave a periodic domain)
+    t0, p0, i0 = hs.trace_rays(pos, u, lim)
+    t1, p1, i1, (skipped, steps) = hs.trace_rays(pos, u, lim, jump=True)
+    assert np.array_equal(i0, i1)
+    assert np.max(np.abs(t0 - t1) / np.maximum(np.abs(t0), 1e-3)) < 1e-5
+    assert np.max(np.abs(p0 - p1)) < 5e-3  # metres, on coordinates up to 3840 m in float32
+    assert skipped > 0.1 * steps

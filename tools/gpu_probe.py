@@ -5,6 +5,8 @@
     python tools/gpu_probe.py tune <workload> <photons> '{"resident_blocks": 5}' '{"min_running": 20}' ...
                                                               one workload, one line per tuning dict (i3rc_set_tuning)
     python tools/gpu_probe.py sizes ['{tuning}']              Landsat at 1, 4, 16, 64 M photons per launch (tail effect)
+    python tools/gpu_probe.py ceilings                        measured roofline ceilings: random 4-byte gathers per second
+                                                              over arrays of 1 MB .. 1 GiB, and the issue rate
 """
 import ctypes as C
 import sys
@@ -54,6 +56,16 @@ if __name__ == "__main__":
         for name, nph in (("planeparallel", 4_000_000), ("step", 2_000_000), ("radar", 1_000_000), ("landsat", 4_000_000),
                           ("les-small", 1_000_000), ("les", 1_000_000)):
             run(name, nph, 2, {}, verbose=True)
+    elif mode == "ceilings":
+        be = backend()
+        g = C.c_double()
+        for mb in (1, 8, 32, 64, 128, 256, 1024):
+            assert be.measure_gather_rate(mb << 20, 5, C.byref(g)) == 0
+            print(f"random 4-byte gathers over {mb:5d} MB: {g.value:.4g} loads/s = {g.value*4/1e9:.1f} GB/s useful, "
+                  f"{g.value*32/1e9:.1f} GB/s of 32-byte sectors", flush=True)
+        assert be.measure_issue_rate(5, C.byref(g)) == 0
+        print(f"issue rate (independent FMAs): {g.value:.4g} warp instructions/s "
+              f"(nominal 148 SMs x 4 schedulers x 1.965 GHz = {148*4*1.965e9:.4g})", flush=True)
     elif mode == "tune":
         for t in sys.argv[4:] or ["{}"]:
             run(sys.argv[2], int(sys.argv[3]), 1, eval(t))
