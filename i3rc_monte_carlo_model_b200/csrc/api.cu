@@ -676,6 +676,10 @@ int launch_transport(i3rc_integrator* h, const Problem& p) {
         return launch_transport_fast<4, 64, 64>(h, p);
       case 52:
         return launch_transport_fast<5, 48, 64>(h, p);
+      case 72:  // (experiments: more resident warps at the price of registers)
+        return launch_transport_t<128, true, true, false, 7, 16, 48, 64>(h, p);
+      case 83:
+        return launch_transport_t<128, true, true, false, 8, 16, 32, 64>(h, p);
       default:  // the shared-memory footprint is kept small on purpose: what is left of the 256 KB is L1 for the gathers
         return launch_transport_fast<5, 64, 64>(h, p);
     }
@@ -1949,7 +1953,7 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->blocksPerSM = value;
   else if (k == "steps_per_event_phase" && value >= 1)
     h->kSteps = value;
-  else if (k == "resident_blocks" && (value == 0 || (value >= 4 && value <= 6)))
+  else if (k == "resident_blocks" && (value == 0 || (value >= 4 && value <= 8)))
     h->residentBlocks = value;
   else if (k == "split_layers")
     h->splitLayers = value;  // takes effect at the next new_Integrator / copy_Integrator
