@@ -62,6 +62,8 @@ struct i3rc_integrator {
   float *d_xe = nullptr, *d_ye = nullptr, *d_ze = nullptr;
   float *d_ext = nullptr, *d_cum = nullptr, *d_ssa = nullptr;
   float* d_extRaw = nullptr;  // un-normalised extinction of every component (kept from the first profile swap on)
+  float* d_colTau = nullptr;  // column suffix sums of extinction x layer depth (Problem::colTau)
+  int verticalShortcut = 1;   // (tuning) 0: trace straight-up local-estimate rays like all others
   float* d_extJ = nullptr;    // the gather field with empty-space codes (transport.cuh JUMP_*), when that pays
   double codedFraction = 0.0; // share of the cells that carry a code
   int skipEmpty = 1;          // (tuning) 0: never use empty-space codes
@@ -282,6 +284,11 @@ int build_gather_field(i3rc_integrator* h) {
   CUDA_OK(h, cudaMemcpyAsync(&bits, d_max, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
   memcpy(&h->maxExt, &bits, sizeof(float));
+  // column suffix sums for the radiance directions that point straight up (Problem::colTau)
+  dfree(h->d_colTau);
+  CUDA_OK(h, cudaMalloc(&h->d_colTau, sizeof(float) * (size_t)nx * ny * (nz + 1)));
+  k_column_suffix<<<(unsigned)(((size_t)nx * ny + 127) / 128), 128, 0, h->stream>>>(nz, (size_t)nx * ny, h->d_ext, h->d_ze, h->d_colTau);
+  h->otherLaunches++;
   // Empty-space codes: a second copy of the gather field in which empty cells far from any extinction say how far a ray
   // may run without looking (regular grids, every layer stored, L2-resident fields wider than two maximal jumps).
   dfree(h->d_extJ);
@@ -479,6 +486,11 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
   p.computeIntensity = h->computeIntensity;
   p.nDir = h->computeIntensity ? h->nDir : 0;
   p.dirs = h->d_dirs;
+  p.colTau = h->d_colTau;
+  p.vertMask = 0;
+  if (h->verticalShortcut && h->d_colTau)
+    for (int d = 0; d < p.nDir && d < 32; d++)
+      if (h->dirs[d * DIR_STRIDE] == 0.0f && h->dirs[d * DIR_STRIDE + 1] == 0.0f && h->dirs[d * DIR_STRIDE + 2] == 1.0f) p.vertMask |= 1u << d;
   p.useRayTracing = h->useRayTracing;
   p.useRussianRoulette = h->useRussianRoulette;
   p.useRRIntensity = h->useRRIntensity;
@@ -1130,6 +1142,7 @@ void i3rc_finalize_Integrator(i3rc_integrator* h) {
   dfree(h->d_ze);
   dfree(h->d_ext);
   dfree(h->d_extRaw);
+  dfree(h->d_colTau);
   dfree(h->d_extJ);
   dfree(h->d_extZ);
   dfree(h->d_zlut);
@@ -1967,6 +1980,8 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->eventThreshold = value;
   else if (k == "track_by_component")
     h->trackByComponent = value != 0;
+  else if (k == "vertical_shortcut" && (value == 0 || value == 1))
+    h->verticalShortcut = value;  // 0: straight-up local-estimate rays are traced like the others
   else if (k == "skip_empty" && (value == 0 || value == 1)) {
     h->skipEmpty = value;  // 0: drop the coded copy of the field (takes effect at once); 1: at the next new_Integrator
     if (!value) dfree(h->d_extJ);

@@ -274,10 +274,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
           float c0 = c2, c1 = c3;
           if ((dcur & 1) == 0 && alive) E.rng.next4(p.key0, p.key1, c0, c1, c2, c3);  // one block per two directions
           LeTask t;
-          const bool push = alive && make_le_task(p, E, dcur, c0, c1, t);
+          const int what = alive ? make_le_task(p, E, dcur, c0, c1, t) : 0;
+          const bool push = what == 1;
           const unsigned m = __ballot_sync(full, push);
           if (push) q[(tail + __popc(m & lt)) & (QCAP - 1)] = t;
           tail += __popc(m);
+          if ((p.vertMask >> dcur) & 1u) {  // straight up: worked out on the spot, tallied in the event's own column
+            Tally tv;
+            if constexpr (TSM) tv.n = 0;
+            if (what == 2) tally_intensity_at(p, E, dcur, E.comp, E.cy * p.nx + E.cx, t.cw, tv);
+            if constexpr (TSM) warp_tally<TSM>(p, wt, tv.n > 0, tv.w0, tv.o0, tv.v0);
+          }
           dcur++;
         }
         if (dcur >= p.nDir) stage = 2;
@@ -733,6 +740,19 @@ __global__ void k_empty_code(const float* __restrict__ ext, const uint8_t* __res
     atomicAdd(count, 1ull);
   }
   coded[i] = e;
+}
+
+// colTau[k][col] = sum over layers j >= k of totalExt[j][col] * (ze[j+1] - ze[j]), k = 0 .. nz (Problem::colTau)
+__global__ void k_column_suffix(int nz, size_t ncol, const float* __restrict__ ext, const float* __restrict__ ze,
+                                float* __restrict__ S) {
+  const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  float run = 0.0f;
+  S[(size_t)nz * ncol + col] = 0.0f;
+  for (int k = nz - 1; k >= 0; k--) {
+    run = fmaf(ext[(size_t)k * ncol + col], ze[k + 1] - ze[k], run);
+    S[(size_t)k * ncol + col] = run;
+  }
 }
 
 // per layer: are all cells of the layer equal?  out[iz] = {min bits, max bits} (extinctions are >= 0: bits order = value order)

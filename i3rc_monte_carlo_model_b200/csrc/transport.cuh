@@ -127,6 +127,11 @@ struct Problem {
   float maxExt;
   const TableDesc* tables;
   int computeIntensity, nDir;
+  // Radiance directions that point straight up (mu = 1: the nadir view of every I3RC case): their local-estimate rays stay
+  // in the column they start in, so the optical path to the top is read from the column's suffix sums of extinction x
+  // layer depth, colTau[k][iy][ix] = sum over layers >= k (k = 0 .. nz), instead of being traced (make_le_task).
+  const float* colTau;
+  uint32_t vertMask;  // bit d: direction d is (0, 0, 1)
   const float* dirs;  // [nDir][DIR_STRIDE]: d.x d.y d.z 1/|d.x| 1/|d.y| 1/|d.z| 4*pi*|mu| 1/(4*pi*|mu|)
   int useRayTracing, useRussianRoulette, useRRIntensity, useHybrid, numOrdersOrig, limitContrib, useSurfaceBDRF;
   int trackByComponent;
@@ -868,7 +873,8 @@ struct LeTask {
 
 // Build the local-estimate task towards direction d from the lane's event point (MCRT:1473-1510, 1540-1569); xiTau and
 // xiAcc are the two deviates Iwabuchi's roulette may need.  Returns 0 when the contribution is known to be zero
-// without tracing.
+// without tracing, 1 when the task has to be traced, 2 when the direction points straight up and the contribution has
+// been worked out on the spot (in t.cw; to be tallied in the event's own column by tally_intensity_at).
 template <class P>
 I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, LeTask& t) {
   const float* dv = p.dirs + d * DIR_STRIDE;
@@ -899,6 +905,24 @@ I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, L
       lim = -I3RC_LOG(I3RC_FDIV(p.zetaMin, fmaxf(F_TINY, F_PI * phat)));
     }
   }
+  if ((p.vertMask >> d) & 1u) {
+    // Straight up: the ray never leaves its column.  Same estimator, same deviates, no tracing: the optical path to the
+    // top is the rest of the event cell plus the suffix sum of the layers above; the roulette stages (MCRT:1554-1559,
+    // 1570-1587) only ask whether that path fits into their optical-path limits.
+    const size_t ncol = (size_t)p.nx * p.ny;
+    const float tauTop = (1.0f - L.fz) * cell_w(p.ze, p.zRegular, p.dz, L.cz) * ext_value<P>(L.eCell) +
+                         I3RC_LDG(p.colTau + (size_t)(L.cz + 1) * ncol + (size_t)(L.cy * p.nx + L.cx));
+    const float cfix = L.w * p.zetaMin * (1.0f / F_PI);
+    float c;
+    if (mode == MODE_LE_PLAIN)
+      c = L.w * phat * I3RC_EXP(-tauTop);
+    else if (mode == MODE_LE_SMALL)
+      c = tauTop <= lim ? cfix : 0.0f;
+    else
+      c = tauTop <= lim ? L.w * phat * I3RC_EXP(-tauTop) : (tauTop - lim <= tauFree ? cfix : 0.0f);
+    t.cw = c;
+    return 2;
+  }
   t.xy = (uint32_t)L.cx | ((uint32_t)L.cy << 16);
   t.zdmc = (uint32_t)L.cz | ((uint32_t)d << 16) | ((uint32_t)mode << 21) | ((uint32_t)L.comp << 24);
   t.fx = L.fx;
@@ -927,19 +951,23 @@ I3RC_HD void start_le_task(const P& p, Lane& L, const LeTask& t) {
                I3RC_LDG(dv + 1), I3RC_LDG(dv + 2), I3RC_LDG(dv + 3), I3RC_LDG(dv + 4), I3RC_LDG(dv + 5), t.tauLimit, t.e0);
 }
 
+// contribution c of component comp towards direction d, leaving the domain through column col (MCRT:574-579, 662-667)
 template <class P, class TAL>
-I3RC_HD void tally_intensity(const P& p, Lane& L, float c, TAL& tal) {
+I3RC_HD void tally_intensity_at(const P& p, Lane& L, int d, int comp, int col, float c, TAL& tal) {
   if (!P::kFast && p.limitContrib && c > p.maxContrib) {  // MCRT:1598-1609
-    I3RC_ATOMIC_ADD(p.excess + L.tcomp * p.nDir + L.td, c - p.maxContrib);
+    I3RC_ATOMIC_ADD(p.excess + comp * p.nDir + d, c - p.maxContrib);
     c = p.maxContrib;
   }
   if (c != 0.0f) {
-    int col = ray_iy(p, L) * p.nx + ray_ix(p, L);
     size_t ncol = (size_t)p.nx * p.ny;
-    tal.add(p, TAL_INT, (size_t)L.td * ncol + col, c);
-    if (!P::kFast && p.trackByComponent) I3RC_ATOMIC_ADD(p.intByComp + ((size_t)L.tcomp * p.nDir + L.td) * ncol + col, c);
+    tal.add(p, TAL_INT, (size_t)d * ncol + col, c);
+    if (!P::kFast && p.trackByComponent) I3RC_ATOMIC_ADD(p.intByComp + ((size_t)comp * p.nDir + d) * ncol + col, c);
     I3RC_COUNT(L, CNT_CONTRIB, 1);
   }
+}
+template <class P, class TAL>
+I3RC_HD void tally_intensity(const P& p, Lane& L, float c, TAL& tal) {
+  tally_intensity_at(p, L, L.td, L.tcomp, ray_iy(p, L) * p.nx + ray_ix(p, L), c, tal);
 }
 
 // A local-estimate ray has stopped (L.done != 0).  Returns 1 when the same ray goes on with its second stage
@@ -1110,9 +1138,14 @@ I3RC_HD void advance_le(const P& p, Lane& L) {
       xiTau = L.le2;
       xiAcc = L.le3;
     }
-    if (make_le_task(p, L, d, xiTau, xiAcc, t)) {
+    const int what = make_le_task(p, L, d, xiTau, xiAcc, t);
+    if (what == 1) {
       start_le_task(p, L, t);
       return;
+    }
+    if (what == 2) {
+      TallyNow now;
+      tally_intensity_at(p, L, d, L.comp, L.cy * p.nx + L.cx, t.cw, now);
     }
   }
   continue_photon(p, L, L.ev1, L.ev2, L.ev3);

@@ -55,6 +55,7 @@ def lib():
     L.hostsim_trace_rays.argtypes = [C.POINTER(Args), C.c_int, fp, fp, fp, fp, fp, ip]
     L.hostsim_trace_rays_jump.argtypes = [C.POINTER(Args), C.c_int, fp, fp, fp, fp, fp, ip, C.POINTER(C.c_ulonglong)]
     L.hostsim_set_jump.argtypes = [C.c_int]
+    L.hostsim_set_vertical.argtypes = [C.c_int]
     return L
 
 
@@ -203,6 +204,10 @@ class HostSim:
         self.L.hostsim_trace_rays(C.byref(a), n, _abi.fptr(pos), _abi.fptr(direction), _abi.fptr(lim), _abi.fptr(tau),
                                   _abi.fptr(pout), _abi.iptr(idx))
         return tau, pout, idx
+
+    def set_vertical(self, on):
+        """Radiance directions that point straight up are integrated from column suffix sums (Problem::colTau)."""
+        self.L.hostsim_set_vertical(int(on))
 
     def set_jump(self, on):
         """Photon batches (run) use the empty-space codes too (regular grids, ray tracing)."""

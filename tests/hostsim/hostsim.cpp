@@ -114,6 +114,25 @@ static void fill(const HostSimArgs* a, Problem& p, std::vector<TableDesc>& td, s
 // Empty-space codes on the CPU (what k_empty_init / k_empty_grow / k_empty_code do on the device), for a field in any
 // layout given by its strides: Chebyshev distance to the nearest cell with extinction, periodic in x and y.
 static int g_jump = 0;
+static int g_vertical = 0;  // straight-up radiance directions from column suffix sums (Problem::colTau) instead of traced
+static std::vector<float> g_colTau;
+static void vertical_setup(Problem& p) {
+  p.colTau = nullptr;
+  p.vertMask = 0;
+  if (!g_vertical) return;
+  const size_t ncol = (size_t)p.nx * p.ny;
+  g_colTau.assign(ncol * (p.nz + 1), 0.0f);
+  for (size_t c = 0; c < ncol; c++) {
+    float run = 0.0f;
+    for (int k = p.nz - 1; k >= 0; k--) {
+      run = fmaf(p.ext[(size_t)k * ncol + c], p.ze[k + 1] - p.ze[k], run);  // (hostsim's field is x fastest, like d_ext)
+      g_colTau[(size_t)k * ncol + c] = run;
+    }
+  }
+  p.colTau = g_colTau.data();
+  for (int d = 0; d < p.nDir && d < 32; d++)
+    if (p.dirs[d * DIR_STRIDE] == 0.0f && p.dirs[d * DIR_STRIDE + 1] == 0.0f && p.dirs[d * DIR_STRIDE + 2] == 1.0f) p.vertMask |= 1u << d;
+}
 static std::vector<float> coded_field(const Problem& p) {
   const int nx = p.nx, ny = p.ny, nz = p.nz;
   const size_t n = (size_t)nx * ny * nz;
@@ -172,6 +191,7 @@ int hostsim_run(const HostSimArgs* a) {
   std::vector<TableDesc> td;
   std::vector<float> dirs;
   fill(a, p, td, dirs);
+  vertical_setup(p);
   // the same specialisation rule as the product's launcher (api.cu)
   if (p.xyRegular && p.zRegular && g_jump && p.useRayTracing) run_lanes<true, true>(a, p);
   else if (p.xyRegular && p.zRegular) run_lanes<true>(a, p);
@@ -180,6 +200,7 @@ int hostsim_run(const HostSimArgs* a) {
 }
 
 void hostsim_set_jump(int on) { g_jump = on; }
+void hostsim_set_vertical(int on) { g_vertical = on; }
 }  // extern "C"
 
 template <class P>

@@ -669,3 +669,28 @@ def test_empty_space_codes_change_nothing_but_the_number_of_gathers(cuda, monkey
     for k in ("meanFluxUp", "meanFluxDown", "meanIntensity"):
         assert np.allclose(a[k], b[k], rtol=2e-4), k
     assert np.abs(a["fluxUp"] - b["fluxUp"]).mean() < 0.01 * b["fluxUp"].mean()
+
+
+def test_straight_up_directions_from_column_sums_equal_traced_rays_on_the_device(cuda):
+    """The nadir view (mu = 1) integrated from column suffix sums instead of traced: same photons, same contributions up
+    to float32 summation order, fewer cell crossings -- on a two-component field with Russian roulette for intensity and
+    on an irregular grid with the plain local estimate."""
+    cases = [(fields.synthetic_les(nx=24, ny=16, nz=32, n_entries=3, seed=7, nLegendreCoefficients=16),
+              dict(surfaceAlbedo=0.1, intensityMus=[1.0, 0.6, 1.0], intensityPhis=[0.0, 40.0, 180.0], useRussianRouletteForIntensity=True,
+                   zetaMin=0.3)),
+             (_irregular_domain(), dict(surfaceAlbedo=0.3, intensityMus=[0.7, 1.0], intensityPhis=[10.0, 0.0],
+                                        useRussianRouletteForIntensity=False))]
+    for d, kw in cases:
+        res = []
+        for v in (1, 0):
+            I = make_integrator(cuda, d, **kw)
+            assert cuda.set_tuning(I.handle, b"vertical_shortcut", v) == 0
+            computeRadiativeTransfer(I, new_RandomNumberSequence([10, 2]), new_PhotonStream(0.6, 20.0, numberOfPhotons=200_000))
+            res.append((reportResults(I, "intensity", "fluxUp", "meanIntensity"), getCounters(I)))
+        (a, ca), (b, cb) = res
+        assert np.allclose(a["meanIntensity"], b["meanIntensity"], rtol=1e-4)
+        assert np.allclose(a["intensity"], b["intensity"], rtol=2e-3, atol=1e-6)
+        assert np.allclose(a["fluxUp"], b["fluxUp"], rtol=1e-4, atol=1e-7)
+        for k in ("crossings_photon", "collisions", "contributions", "rng_draws", "exits_top", "surface_hits"):
+            assert ca[k] == cb[k], k
+        assert ca["crossings_intensity"] < 0.9 * cb["crossings_intensity"]

@@ -164,3 +164,34 @@ def test_empty_space_jumps_along_fixed_rays(oracle):
     assert np.max(np.abs(t0 - t1) / np.maximum(np.abs(t0), 1e-3)) < 1e-5
     assert np.max(np.abs(p0 - p1)) < 5e-3  # metres, on coordinates up to 3840 m in float32
     assert skipped > 0.1 * steps
+
+
+@pytest.mark.parametrize("name,make,kw", [
+    ("roulette", lambda: fields.step_cloud(0.99), dict(surfaceAlbedo=0.2, intensityMus=[1.0, 0.5, 1.0], intensityPhis=[0.0, 180.0, 90.0],
+                                                       useRussianRouletteForIntensity=True, zetaMin=0.3)),
+    ("plain", lambda: fields.step_cloud(1.0), dict(surfaceAlbedo=0.3, intensityMus=[1.0, 0.5], intensityPhis=[0.0, 0.0],
+                                                   useRussianRouletteForIntensity=False)),
+])
+def test_straight_up_directions_from_column_sums_equal_traced_rays(oracle, name, make, kw):
+    """A radiance direction with mu = 1 is integrated from the column's suffix sums of extinction x layer depth instead
+    of being traced (transport.cuh, make_le_task): same deviates, same estimator, so every contribution is the same up
+    to float32 summation order -- and the photons' own paths are untouched."""
+    from i3rc_monte_carlo_model_b200.monteCarloRadiativeTransfer import getTable
+    d = make()
+    I = make_integrator(oracle, d, **kw)
+    oracle.tabulate(I.handle)
+    hs = HostSim(d, I, getTable)
+    res = []
+    try:
+        for v in (0, 1):
+            hs.set_vertical(v)
+            res.append(hs.run(new_PhotonStream(0.5, 0.0, numberOfPhotons=8000), (10, 1), **kw))
+    finally:
+        hs.set_vertical(0)
+    a, b = res
+    assert np.allclose(a["intensity"], b["intensity"], rtol=2e-5, atol=1e-9)
+    assert np.array_equal(a["fluxUp"], b["fluxUp"]) and np.array_equal(a["fluxDown"], b["fluxDown"])
+    ca, cb = a["counters"], b["counters"]
+    for k in ("crossings_photon", "collisions", "contributions", "rng_draws", "exits_top", "surface_hits"):
+        assert ca[k] == cb[k], k
+    assert cb["crossings_intensity"] < 0.8 * ca["crossings_intensity"]
