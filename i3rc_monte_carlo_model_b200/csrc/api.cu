@@ -66,7 +66,9 @@ struct i3rc_integrator {
   int verticalShortcut = 1;   // (tuning) 0: trace straight-up local-estimate rays like all others
   float* d_extJ = nullptr;    // the gather field with empty-space codes (transport.cuh JUMP_*), when that pays
   double codedFraction = 0.0; // share of the cells that carry a code
-  int skipEmpty = 1;          // (tuning) 0: never use empty-space codes
+  int skipEmpty = 0;          // (tuning / I3RC_SKIP_EMPTY) 1: build and use empty-space codes.  Off by default: measured
+                              // slower on the Landsat cloud (1.80e8 .. 2.01e8 photons/s against 2.20e8, profiles/r02_summary.md):
+                              // a jump costs the whole warp more than the lanes that jump save
   float* d_extZ = nullptr;  // totalExt again, z-fastest: the copy the rays gather from (see Problem::ext)
   int2* d_zlut = nullptr;   // layer table when only the horizontally varying layers are stored (Problem::zlut)
   int nzc = 0;
