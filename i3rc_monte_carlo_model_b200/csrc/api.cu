@@ -63,6 +63,8 @@ struct i3rc_integrator {
   float *d_ext = nullptr, *d_cum = nullptr, *d_ssa = nullptr;
   float* d_extRaw = nullptr;  // un-normalised extinction of every component (kept from the first profile swap on)
   float* d_colTau = nullptr;  // column suffix sums of extinction x layer depth (Problem::colTau)
+  int debugZeroStrides = 0;   // (experiment) every gather reads element 0 of the field: on a homogeneous domain the results
+                              // are unchanged and the run time is what the kernel would need if gathers always hit L1
   int verticalShortcut = 1;   // (tuning) 0: trace straight-up local-estimate rays like all others
   float* d_extJ = nullptr;    // the gather field with empty-space codes (transport.cuh JUMP_*), when that pays
   double codedFraction = 0.0; // share of the cells that carry a code
@@ -480,6 +482,7 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
   p.esy = h->nzc ? h->nzc : h->nz;
   p.esz = 1;
   p.extN = (long long)h->nx * h->ny * (h->nzc ? h->nzc : h->nz);
+  if (h->debugZeroStrides && !h->nzc) p.esx = p.esy = p.esz = 0;
   p.cumExt = h->d_cum;
   p.ssa = h->d_ssa;
   p.pfIdx = h->d_pf;
@@ -1982,6 +1985,8 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->eventThreshold = value;
   else if (k == "track_by_component")
     h->trackByComponent = value != 0;
+  else if (k == "debug_zero_strides" && (value == 0 || value == 1))
+    h->debugZeroStrides = value;
   else if (k == "vertical_shortcut" && (value == 0 || value == 1))
     h->verticalShortcut = value;  // 0: straight-up local-estimate rays are traced like the others
   else if (k == "skip_empty" && (value == 0 || value == 1)) {

@@ -66,6 +66,23 @@ if __name__ == "__main__":
         assert be.measure_issue_rate(5, C.byref(g)) == 0
         print(f"issue rate (independent FMAs): {g.value:.4g} warp instructions/s "
               f"(nominal 148 SMs x 4 schedulers x 1.965 GHz = {148*4*1.965e9:.4g})", flush=True)
+    elif mode == "locality":
+        # What would perfect gather locality buy?  A homogeneous domain of the Landsat case's shape and mean optical depth:
+        # with all field strides zero every gather reads the same element (an L1 hit), and the results do not change.
+        import bench
+        from i3rc_monte_carlo_model_b200 import fields
+        wl0 = bench.make_workload("landsat")
+        bench_make = bench.make_workload
+        def homogeneous(name):
+            w = dict(wl0)
+            w["domain"] = lambda: fields.plane_parallel(nX=128, nY=128, nLayers=119, domainSize=3840.0, physicalThickness=2380.0,
+                                                        opticalDepth=10.0, nLegendreCoefficients=299)
+            return w
+        bench.make_workload = homogeneous
+        globals()["make_workload"] = homogeneous
+        for t in ({"vertical_shortcut": 0}, {"vertical_shortcut": 0, "debug_zero_strides": 1}, {}, {"debug_zero_strides": 1}):
+            run("landsat-shaped homogeneous slab", 8_000_000, 1, t, verbose=True)
+        bench.make_workload = bench_make
     elif mode == "tune":
         for t in sys.argv[4:] or ["{}"]:
             run(sys.argv[2], int(sys.argv[3]), 1, eval(t))
