@@ -284,6 +284,10 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="strong: --steps batches IN TOTAL are shared by the ranks (monteCarloDriver.f95:264-274); domain setup, "
                          "table building and the all-reduce are inside the clock")
+    ap.add_argument("--c5-leg", default="auto", choices=["auto", "on", "off"],
+                    help="after the main measurement, a STRONG-scaling leg on BASELINE config 5 (synthetic 512x512x256, 2 components, "
+                         "16 directions) with reportVolumeAbsorption: 8 batches of 1 M photons in total, set-up and the 1.15 GB "
+                         "all-reduce inside the clock; reported as `c5_strong`.  auto = when more than one GPU takes part")
     ap.add_argument("--report-volume", action="store_true", help="keep batch moments of volumeAbsorption too "
                     "(reportVolumeAbsorption: the all-reduce payload grows by 2 x 8 B per cell)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -489,6 +493,56 @@ def main():
                "i3rc_reportResults into host arrays", "meanFluxUp_last": float(r["meanFluxUp"])}
     barrier()
 
+    # ---- strong-scaling leg on BASELINE config 5 with volume absorption (the case whose all-reduce payload is large) ----
+    c5 = None
+    if args.c5_leg == "on" or (args.c5_leg == "auto" and world > 1 and args.workload == "landsat"):
+        from i3rc_monte_carlo_model_b200.monteCarloRadiativeTransfer import finalize_Integrator
+        wl5 = make_workload("les")
+        nph5, nb5 = 1_000_000, 8
+        dom5 = wl5["domain"]()  # (the synthetic field is made on the host outside the clock)
+        barrier()
+        t0 = time.perf_counter()
+        I5 = new_Integrator(dom5, backend=be)
+        assert I5.handle, "new_Integrator failed (config 5)"
+        specifyParameters(I5, **wl5["params"])
+        assert be.tabulate(I5.handle) == 0, I5._msg()
+        be.synchronize(I5.handle)
+        setup5 = (time.perf_counter() - t0) * 1e3
+        src5 = new_PhotonStream(numberOfPhotons=nph5, **wl5["source"]).as_c()
+        assert be.stats_reset(I5.handle, 1) == 0
+        assert be.run_batches(I5.handle, C.byref(src5), 10, 0, 1_000_000, 1) == 0, I5._msg()  # warm-up
+        assert be.stats_reset(I5.handle, 1) == 0
+        nB5, mine5 = partition_batches(nb5, world, rank)
+        stream5 = torch.cuda.ExternalStream(be.stream(I5.handle), device=torch.device("cuda", local))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream5)
+        for b in mine5:
+            assert be.run_batches(I5.handle, C.byref(src5), 10, 0, b, 1) == 0, I5._msg()
+        e1.record(stream5)
+        e1.synchronize()
+        trace5 = e0.elapsed_time(e1)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        allreduce_device_stats(I5, dist if world > 1 else None)
+        a1.record()
+        a1.synchronize()
+        ar5 = a0.elapsed_time(a1) if world > 1 else 0.0
+        ptr, n = C.c_void_p(), C.c_int64()
+        be.stats_device_buffer(I5.handle, C.byref(ptr), C.byref(n))
+        t5 = torch.tensor([setup5 + trace5 + ar5, setup5, trace5, ar5], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        tot5, setup5, trace5, ar5 = t5.tolist()
+        st5 = device_stats_report(I5, 1.0, nB5)
+        c5 = {"workload": wl5["workload"], "scaling": "strong", "total_batches": nB5, "photons_per_batch": nph5,
+              "value": nph5 * nB5 / (tot5 * 1e-3), "unit": UNIT, "ms_total": tot5, "setup_ms": setup5, "trace_ms": trace5,
+              "allreduce_ms": ar5, "allreduce_bytes": 8 * n.value, "report_volume_absorption": True,
+              "meanFluxUp": [float(st5["meanFluxUp"][0]), float(st5["meanFluxUp"][1])],
+              "timing": "domain upload + gather field + tables + this rank's batches (CUDA events) + the all-reduce, max over ranks"}
+        finalize_Integrator(I5)
+        barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -586,7 +640,7 @@ def main():
                    "allreduce_ms": allreduce_ms, "allreduce_bytes": stats_bytes, "setup_ms": setup_ms,
                    "report_volume_absorption": bool(with_volume), "tuning": args.tune or "default"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(trace_launches + other_launches),
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "c5_strong": c5,
         "wall_ms_timed_region": wall_ms, "allreduce_ms": allreduce_ms,
         "counters_per_photon": {k: v / total_photons for k, v in counters_all.items() if v},
         "results": {"meanFluxUp": [float(stats["meanFluxUp"][0]), float(stats["meanFluxUp"][1])],

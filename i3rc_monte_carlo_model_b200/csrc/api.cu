@@ -671,7 +671,9 @@ int launch_transport(i3rc_integrator* h, const Problem& p) {
     return launch_transport_t<128, false, false, true, 5, 16, 64, 64, true>(h, p);
   }
   if (p.nzc) {  // only the horizontally varying layers are stored (large fields): the gathers look the layer up first
-    if (reg && fast) return launch_transport_t<128, true, true, true, 5, 16, 64, 64>(h, p);
+    if (reg && fast)  // (6 resident blocks: 512x512x256 3.19e7 photons/s against 2.85e7 with 5, profiles/r02_ab_tuning_grid.txt)
+      return h->residentBlocks == 5 ? launch_transport_t<128, true, true, true, 5, 16, 64, 64>(h, p)
+                                    : launch_transport_t<128, true, true, true, 6, 16, 64, 64>(h, p);
     if (reg) return launch_transport_t<128, true, false, true, 5, 16, 64, 64>(h, p);
     return launch_transport_t<128, false, false, true, 5, 16, 64, 64>(h, p);
   }
