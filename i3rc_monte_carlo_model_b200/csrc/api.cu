@@ -114,7 +114,8 @@ struct i3rc_integrator {
   size_t srcArraysN = 0;
   const float* hostArrays[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaStream_t copyStream = nullptr;
-  cudaEvent_t copyDone[2] = {nullptr, nullptr}, computeDone = nullptr;
+  std::vector<cudaEvent_t> copyDone;  // one per piece of a batch
+  cudaEvent_t computeDone = nullptr;
   // batch moments
   double* d_stats = nullptr;
   size_t statsN = 0;
@@ -618,7 +619,6 @@ int fill_source(i3rc_integrator* h, const i3rc_photon_source* s, SourceDev& d) {
     for (int k = 0; k < 5; k++) h->hostArrays[k] = srcs[k];  // (copied by run_one_batch, piecewise)
     if (!h->copyStream) {
       CUDA_OK(h, cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
-      for (auto& e : h->copyDone) CUDA_OK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       CUDA_OK(h, cudaEventCreateWithFlags(&h->computeDone, cudaEventDisableTiming));
     }
     d.ax = h->d_srcArrays;
@@ -745,14 +745,20 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
   //  * float32 tallies: an element that receives more than ~2^24 increments stops growing (a 1-column plane-parallel
   //    domain with 1e8 photons), and small increments are lost long before that.  Pieces are kept below 2^20 photons per
   //    column and folded into float64 sums in between;
-  //  * hand-filled photon arrays: the first tenth is copied, then traced while the rest is being copied.
+  //  * hand-filled photon arrays: a first twentieth is copied and traced while the next quarter is being copied, and
+  //    that while the rest is (every piece's copy runs under the kernel of the piece before: 0.6 ms of the 13 ms that
+  //    320 MB take over PCIe stay exposed).
   const long long n = src.n;
   // (a spotlight or an internal source puts all photons into a few columns whatever the size of the domain)
   const bool concentrated = src.kind == I3RC_SRC_SPOTLIGHT || src.kind == I3RC_SRC_INTERNAL_FLUX || src.kind == I3RC_SRC_INTERNAL_INTENSITY;
   const long long perPiece = concentrated ? (1 << 22) : std::max<long long>(1 << 19, (long long)ncol << 20);
   const bool arrays = src.kind == I3RC_SRC_ARRAYS;
   std::vector<long long> cuts{0};
-  if (arrays && n >= (1 << 20)) cuts.push_back(std::min<long long>(((n / 10 + 127) / 128) * 128, perPiece));
+  if (arrays && n >= (1 << 20)) {
+    cuts.push_back(std::min<long long>(((n / 20 + 127) / 128) * 128, perPiece));
+    const long long second = ((3 * n / 10 + 127) / 128) * 128;
+    if (second - cuts.back() <= perPiece) cuts.push_back(second);
+  }
   while (n - cuts.back() > perPiece) cuts.push_back(cuts.back() + perPiece);
   cuts.push_back(n);
   const int nPieces = (int)cuts.size() - 1;
@@ -778,14 +784,16 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
   if (arrays) {
     CUDA_OK(h, cudaEventRecord(h->computeDone, h->stream));  // the previous batch may still be reading the arrays
     CUDA_OK(h, cudaStreamWaitEvent(h->copyStream, h->computeDone, 0));
-    // two copies: [0, cuts[1]) and the rest (when the batch has a first tenth), each followed by an event
-    const long long c1 = (n >= (1 << 20)) ? cuts[1] : n;
-    const long long copyCuts[3] = {0, c1, n};
-    for (int c = 0; c < 2; c++) {
-      const long long len = copyCuts[c + 1] - copyCuts[c];
-      if (len <= 0) continue;
-      for (int k = 0; k < 5; k++)
-        CUDA_OK(h, cudaMemcpyAsync(h->d_srcArrays + k * n + copyCuts[c], h->hostArrays[k] + copyCuts[c], sizeof(float) * len,
+    // one copy per piece, back to back on the copy stream, each followed by an event its kernel waits for
+    while ((int)h->copyDone.size() < nPieces) {
+      cudaEvent_t e;
+      CUDA_OK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->copyDone.push_back(e);
+    }
+    for (int c = 0; c < nPieces; c++) {
+      const long long len = cuts[c + 1] - cuts[c];
+      for (int k = 0; k < 5 && len > 0; k++)
+        CUDA_OK(h, cudaMemcpyAsync(h->d_srcArrays + k * n + cuts[c], h->hostArrays[k] + cuts[c], sizeof(float) * len,
                                    cudaMemcpyHostToDevice, h->copyStream));
       CUDA_OK(h, cudaEventRecord(h->copyDone[c], h->copyStream));
     }
@@ -793,7 +801,7 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
   for (int c = 0; c < nPieces && rc == I3RC_SUCCESS; c++) {
     const long long off = cuts[c], len = cuts[c + 1] - cuts[c];
     if (len <= 0) continue;
-    if (arrays && c < 2) CUDA_OK(h, cudaStreamWaitEvent(h->stream, h->copyDone[(c == 0 || n < (1 << 20)) ? 0 : 1], 0));
+    if (arrays) CUDA_OK(h, cudaStreamWaitEvent(h->stream, h->copyDone[c], 0));
     if (c) CUDA_OK(h, cudaMemsetAsync(h->d_next, 0, sizeof(unsigned long long), h->stream));
     p.src.n = len;
     if (arrays) {

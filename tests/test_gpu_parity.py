@@ -694,3 +694,34 @@ def test_straight_up_directions_from_column_sums_equal_traced_rays_on_the_device
         for k in ("crossings_photon", "collisions", "contributions", "rng_draws", "exits_top", "surface_hits"):
             assert ca[k] == cb[k], k
         assert ca["crossings_intensity"] < 0.9 * cb["crossings_intensity"]
+
+
+def test_large_hand_filled_photon_arrays_are_traced_in_overlapped_pieces(cuda):
+    """More than 2^20 hand-filled photons: the arrays are uploaded piece by piece on a copy stream while the piece before
+    is traced.  Every photon is traced exactly once (counter), and the result agrees with the device-drawn source."""
+    from tests.cases import familywise_bound
+    d = fields.step_cloud(0.99)
+    n, nb = 1_300_000, 6
+    kw = dict(surfaceAlbedo=0.1, intensityMus=[1.0, 0.5], intensityPhis=[0.0, 180.0], useRussianRouletteForIntensity=True, zetaMin=0.3)
+    res = {}
+    for how in ("arrays", "descriptor"):
+        I = make_integrator(cuda, d, **kw)
+        vals = []
+        for b in range(nb):
+            ph = new_PhotonStream(0.5, 0.0, numberOfPhotons=n)
+            if how == "arrays":
+                r2 = np.random.default_rng(500 + b)
+                ph.xPosition, ph.yPosition = r2.random(n, dtype=np.float32), r2.random(n, dtype=np.float32)
+                ph.zPosition = np.full(n, 1.0 - np.finfo(np.float32).eps, np.float32)
+                ph.initialMu, ph.initialPhi = np.full(n, -0.5, np.float32), np.zeros(n, np.float32)
+            computeRadiativeTransfer(I, new_RandomNumberSequence([10, b + 1]), ph)
+            c = getCounters(I)
+            assert c["photons"] == n and c["bad"] == 0
+            r = reportResults(I, "meanFluxUp", "meanFluxDown", "meanFluxAbsorbed", "meanIntensity")
+            vals.append([r["meanFluxUp"], r["meanFluxDown"], r["meanFluxAbsorbed"], *r["meanIntensity"]])
+        res[how] = np.array(vals, np.float64)
+    a, b = res["arrays"], res["descriptor"]
+    z = (a.mean(0) - b.mean(0)) / np.sqrt(a.var(0, ddof=1) / nb + b.var(0, ddof=1) / nb)
+    assert np.all(np.abs(z) <= familywise_bound(z.size, nb - 1)), z
+    closure = a[:, 0] + a[:, 2] + 0.9 * a[:, 1]
+    assert abs(closure.mean() - 1.0) < 2e-3
