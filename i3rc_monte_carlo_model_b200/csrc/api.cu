@@ -63,6 +63,7 @@ struct i3rc_integrator {
   float *d_ext = nullptr, *d_cum = nullptr, *d_ssa = nullptr;
   float* d_extRaw = nullptr;  // un-normalised extinction of every component (kept from the first profile swap on)
   float* d_colTau = nullptr;  // column suffix sums of extinction x layer depth (Problem::colTau)
+  int tablesInSmem = 0;       // (experiment) stage the phase-function tables in shared memory (one 16-warp block per SM)
   int debugZeroStrides = 0;   // (experiment) every gather reads element 0 of the field: on a homogeneous domain the results
                               // are unchanged and the run time is what the kernel would need if gathers always hit L1
   int verticalShortcut = 1;   // (tuning) 0: trace straight-up local-estimate rays like all others
@@ -630,10 +631,13 @@ int fill_source(i3rc_integrator* h, const i3rc_photon_source* s, SourceDev& d) {
   return I3RC_SUCCESS;
 }
 
-template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP, bool TSM = false, bool JUMP = false>
+template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP, bool TSM = false, bool JUMP = false,
+          bool TABSM = false>
 int launch_transport_t(i3rc_integrator* h, const Problem& p) {
-  auto kern = k_transport<BLOCK, REG, FAST, SPLIT, MINB, STEPS, NSLOT, QCAP, TSM, JUMP>;
-  const size_t dynSmem = (size_t)h->padSmem + (TSM ? sizeof(float) * (BLOCK / 32) * (size_t)p.tsmN : 0);
+  auto kern = k_transport<BLOCK, REG, FAST, SPLIT, MINB, STEPS, NSLOT, QCAP, TSM, JUMP, TABSM>;
+  size_t dynSmem = (size_t)h->padSmem + (TSM ? sizeof(float) * (BLOCK / 32) * (size_t)p.tsmN : 0);
+  if (TABSM)  // the warps' state + the inverse and the forward table of the one component
+    dynSmem = (sizeof(WarpShared<NSLOT, QCAP>) * (BLOCK / 32) + 15) / 16 * 16 + sizeof(float) * ((size_t)h->inv[0].nSteps + h->fwd[0].nSteps);
   if (dynSmem > 8192) CUDA_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynSmem));
   int perSM = h->blocksPerSM;
   if (perSM <= 0) {
@@ -644,7 +648,7 @@ int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   long long grid = (long long)h->numSMs * perSM;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  ProblemT<REG, FAST, SPLIT, JUMP> pt;
+  ProblemT<REG, FAST, SPLIT, JUMP, TABSM> pt;
   static_cast<Problem&>(pt) = p;
   if (JUMP) pt.ext = h->d_extJ;  // the copy of the gather field that carries the empty-space codes
   kern<<<(unsigned)grid, BLOCK, dynSmem, h->stream>>>(pt, h->eventThreshold, h->minRunning);
@@ -683,6 +687,11 @@ int launch_transport(i3rc_integrator* h, const Problem& p) {
                                  : launch_transport_t<128, true, true, false, 6, 16, 64, 64, false, true>(h, p);
     return launch_transport_t<128, true, false, false, 5, 16, 64, 64, false, true>(h, p);
   }
+  // (experiment, `tables_in_smem`) one block of 16 warps per SM with the inverse and the forward phase-function table of the
+  // single component staged in shared memory: measured against the default in profiles/r02_summary.md
+  if (reg && fast && h->tablesInSmem && p.nc == 1 && p.computeIntensity && h->inv[0].nEntries == 1 && h->fwd[0].d &&
+      sizeof(float) * ((size_t)h->inv[0].nSteps + h->fwd[0].nSteps) <= 90 * 1024)
+    return launch_transport_t<512, true, true, false, 1, 16, 64, 64, false, false, true>(h, p);
   if (reg && fast) {
     // resident blocks per SM, 0 = automatic: 6 while the extinction field is L2-resident; 5 (more of the 256 KB left as
     // L1) when the gathers go to HBM
@@ -1995,6 +2004,8 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->eventThreshold = value;
   else if (k == "track_by_component")
     h->trackByComponent = value != 0;
+  else if (k == "tables_in_smem" && (value == 0 || value == 1))
+    h->tablesInSmem = value;
   else if (k == "debug_zero_strides" && (value == 0 || value == 1))
     h->debugZeroStrides = value;
   else if (k == "vertical_shortcut" && (value == 0 || value == 1))

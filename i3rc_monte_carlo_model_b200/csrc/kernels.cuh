@@ -49,6 +49,17 @@ struct SlotPool {  // structure of arrays: lane i touches slot[k] of every array
 };
 constexpr uint32_t SLOT_RAW = 1u << 24;
 
+// everything a warp keeps in shared memory (8 KB with NSLOT = QCAP = 64)
+template <int NSLOT, int QCAP>
+struct WarpShared {
+  LeTask task[QCAP];
+  SlotPool<NSLOT> pool;
+  uint32_t susp[7][32];  // per-lane state of a suspended event batch
+  uint32_t ray[4][32];   // per lane: what its ray is for (photon slot, or local-estimate parameters)
+  uint32_t cnt[CNT_N];
+  uint8_t pend[NSLOT];
+};
+
 // One tally increment per lane, committed by the whole warp (call it converged).  Domains of a few columns (planeParallel:
 // one, the step cloud: 32) would otherwise send every increment of the GPU to a handful of addresses.  There, each
 // warp owns a private copy of the tallies in shared memory (wt): increments of a warp that go to the same element are
@@ -110,8 +121,9 @@ __device__ __forceinline__ void flush_staged_tallies(const P& p, const float* sd
   }
 }
 
-template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP, bool TSM = false, bool JUMP = false>
-__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, FAST, SPLIT, JUMP> p, const int lowWater, const int minRunning) {
+template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP, bool TSM = false, bool JUMP = false,
+          bool TABSM = false>
+__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, FAST, SPLIT, JUMP, TABSM> p, const int lowWater, const int minRunning) {
   constexpr int NW = BLOCK / 32;
   extern __shared__ float s_dyn[];  // TSM: NW private copies of the staged tallies (Problem::tsmN floats each)
   using Tally = typename std::conditional<TSM, TallyLater, TallyNow>::type;
@@ -119,19 +131,33 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
   static_assert(STEPS % (2 * UNROLL) == 0, "a round is a whole number of unrolled bodies");
   static_assert((QCAP & (QCAP - 1)) == 0 && QCAP >= 64, "ring size: power of two, room for one push of 32");
   static_assert(NSLOT >= 32 && NSLOT <= 255, "slot ids are bytes");
-  __shared__ LeTask s_task[NW][QCAP];
-  __shared__ SlotPool<NSLOT> s_pool[NW];
-  __shared__ uint8_t s_pend[NW][NSLOT];
-  __shared__ uint32_t s_cnt[NW][CNT_N];
-  __shared__ uint32_t s_susp[NW][7][32];  // per-lane state of a suspended event batch
-  __shared__ uint32_t s_ray[NW][4][32];   // per lane: what its ray is for (photon slot, or local-estimate parameters)
+  // The warps' state is a static array for the usual blocks of 4 warps; the one-block-per-SM variant that also stages the
+  // phase-function tables (TABSM: 16 warps + two 40 KB tables) carves everything out of dynamic shared memory.
+  static_assert(!(TABSM && TSM), "the staging of tables and of tallies are not combined");
+  __shared__ WarpShared<NSLOT, QCAP> s_warps[TABSM ? 1 : NW];
+  WarpShared<NSLOT, QCAP>* const warps = TABSM ? reinterpret_cast<WarpShared<NSLOT, QCAP>*>(s_dyn) : s_warps;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  LeTask* q = s_task[warp];
-  SlotPool<NSLOT>& pool = s_pool[warp];
-  uint8_t* pend = s_pend[warp];
+  WarpShared<NSLOT, QCAP>& W = warps[warp];
+  LeTask* q = W.task;
+  SlotPool<NSLOT>& pool = W.pool;
+  uint8_t* pend = W.pend;
   float* wt = s_dyn + (TSM ? warp * p.tsmN : 0);
+  if constexpr (TABSM) {
+    // one component, one table entry: the inverse and the forward table (40 KB each at 10001 steps) behind the warps' state
+    float* tab = s_dyn + (sizeof(WarpShared<NSLOT, QCAP>) * NW + 15) / 16 * 4;
+    const TableDesc T = p.tables[0];
+    for (int i = threadIdx.x; i < T.nInv; i += BLOCK) tab[i] = __ldg(T.inv + i);
+    for (int i = threadIdx.x; i < T.nFwd; i += BLOCK) tab[T.nInv + i] = __ldg(T.fwd + i);
+    if (threadIdx.x == 0) {
+      g_smTables = T;
+      g_smTables.inv = tab;
+      g_smTables.fwd = tab + T.nInv;
+      g_smTables.fwdOrig = tab + T.nInv;
+    }
+    __syncthreads();
+  }
   if (TSM) {
     for (int i = threadIdx.x; i < NW * p.tsmN; i += BLOCK) s_dyn[i] = 0.0f;
     __syncthreads();
@@ -144,7 +170,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
     pend[k] = (uint8_t)k;
     pool.zs[k] = (uint32_t)DONE_NEW << 16;
   }
-  if (lane < CNT_N) s_cnt[warp][lane] = 0;
+  if (lane < CNT_N) W.cnt[lane] = 0;
   if (lane < p.nDir) {  // (at most MAX_DIRS = 32 directions)
     pool.ux[NSLOT + lane] = __ldg(p.dirs + lane * DIR_STRIDE + 0);
     pool.uy[NSLOT + lane] = __ldg(p.dirs + lane * DIR_STRIDE + 1);
@@ -153,7 +179,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
   __syncwarp();
 
   Lane R;  // the ray this lane is tracing
-  R.cnt = s_cnt[warp];
+  R.cnt = W.cnt;
   R.done = DONE_IDLE;
   R.mode = MODE_PHOTON;
   R.nsteps = 0;
@@ -186,12 +212,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
     }
     if (run) {
       if (stage != 0) {  // resuming a suspended batch
-        const uint32_t w = s_susp[warp][6][lane];
+        const uint32_t w = W.susp[6][lane];
         eslot = (int)(w & 0xffu);
         has = (w & 0x100u) != 0;
       }
       Lane E;  // the photon whose event this lane is processing
-      E.cnt = s_cnt[warp];
+      E.cnt = W.cnt;
       E.active = 0;
       E.comp = 0;
       E.pfi = 0;
@@ -258,7 +284,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
         dcur = 0;
         stage = (p.computeIntensity && __any_sync(full, alive)) ? 1 : 2;
       } else {  // resume: the rest of the batch state comes back from shared memory
-        const uint32_t* sv = s_susp[warp][0] + lane;
+        const uint32_t* sv = W.susp[0] + lane;
         alive = (sv[6 * 32] & 0x200u) != 0;
         a1 = __uint_as_float(sv[0 * 32]);
         a2 = __uint_as_float(sv[1 * 32]);
@@ -357,7 +383,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
           pool.order[eslot] = E.order;
           pool.block[eslot] = E.rng.block;
         }
-        uint32_t* sv = s_susp[warp][0] + lane;
+        uint32_t* sv = W.susp[0] + lane;
         sv[0 * 32] = __float_as_uint(a1);
         sv[1 * 32] = __float_as_uint(a2);
         sv[2 * 32] = __float_as_uint(a3);
@@ -392,7 +418,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
     Tally talR;
     if constexpr (TSM) talR.n = 0;
     if (R.done != DONE_RUN && R.done != DONE_IDLE) {
-      uint32_t* rv = s_ray[warp][0] + lane;  // what the ray is for waits in shared memory while it is traced
+      uint32_t* rv = W.ray[0] + lane;  // what the ray is for waits in shared memory while it is traced
       if (R.mode == MODE_PHOTON) {
         const int done = R.done;
         R.slot = (int)rv[1 * 32];
@@ -433,7 +459,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
       warp_tally<TSM>(p, wt, t.n > 0, t.w0, t.o0, t.v0);
     }
     const unsigned ms = __ballot_sync(full, segEnd);
-    if (segEnd) pend[npend + __popc(ms & lt)] = (uint8_t)s_ray[warp][1][lane];
+    if (segEnd) pend[npend + __popc(ms & lt)] = (uint8_t)W.ray[1][lane];
     npend += __popc(ms);
     I3RC_ASSERT(R, npend <= NSLOT && tail - head <= QCAP && tail - head >= 0);
     // idle lanes take the next tasks
@@ -450,7 +476,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
       I3RC_ASSERT(R, j >= 0 && j < NSLOT + MAX_DIRS && (int)(t.xy & 0xffffu) < p.nx && (int)(t.xy >> 16) < p.ny &&
                          (int)(t.zdmc & 0xffffu) < p.nz);
       const float ux = pool.ux[j], uy = pool.uy[j], uz = pool.uz[j];
-      uint32_t* rv = s_ray[warp][0] + lane;
+      uint32_t* rv = W.ray[0] + lane;
       rv[0] = t.zdmc >> 16;  // d | mode << 5 | comp << 8
       rv[1 * 32] = __float_as_uint(t.cw);  // (a path segment: the slot number)
       rv[2 * 32] = __float_as_uint(t.cfix);
@@ -480,7 +506,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
   }
   // flush the warp's counters
   __syncwarp();
-  if (lane < CNT_N && s_cnt[warp][lane]) atomicAdd(p.counters + lane, (unsigned long long)s_cnt[warp][lane]);
+  if (lane < CNT_N && W.cnt[lane]) atomicAdd(p.counters + lane, (unsigned long long)W.cnt[lane]);
   if (TSM) flush_staged_tallies<BLOCK>(p, s_dyn);
 }
 

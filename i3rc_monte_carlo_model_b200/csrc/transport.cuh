@@ -156,12 +156,14 @@ struct Problem {
 // instruction footprint small (the SM's instruction cache holds ~32 KB).
 // SPLIT = the field stores only the horizontally varying layers (Problem::zlut): the gather first looks the layer up.
 // JUMP = the field carries empty-space codes (above) and the rays use them (regular grids, every layer stored).
-template <bool REG, bool FAST = false, bool SPLIT = false, bool JUMP = false>
+// TABSM = the kernel has staged the phase-function tables of the (single) component in shared memory (tables_of).
+template <bool REG, bool FAST = false, bool SPLIT = false, bool JUMP = false, bool TABSM = false>
 struct ProblemT : Problem {
   static constexpr bool kRegular = REG;
   static constexpr bool kFast = FAST;
   static constexpr bool kSplit = SPLIT;
   static constexpr bool kJump = JUMP;
+  static constexpr bool kTabSm = TABSM;
   static_assert(!JUMP || (REG && !SPLIT), "empty-space codes: regular grids with every layer stored");
 };
 // the general-purpose instantiation (probes, CPU harness): the layer table is honoured at run time
@@ -170,7 +172,28 @@ struct ProblemDyn : Problem {
   static constexpr bool kFast = false;
   static constexpr bool kSplit = true;
   static constexpr bool kJump = false;
+  static constexpr bool kTabSm = false;
 };
+// the table descriptors the physics reads: the integrator's (global memory), or -- TABSM kernels -- the block's staged copy
+#ifdef __CUDACC__
+__shared__ TableDesc g_smTables;  // (written by k_transport<.., TABSM> before any lookup)
+#endif
+template <class P>
+I3RC_HD const TableDesc* tables_of(const P& p) {
+#ifdef __CUDA_ARCH__
+  if (P::kTabSm) return &g_smTables;
+#endif
+  return p.tables;
+}
+// a table element: through the read-only path from global memory, or a plain load when the table is in shared memory
+template <bool SM>
+I3RC_HD float tab_load(const float* q) {
+#ifdef __CUDA_ARCH__
+  return SM ? *q : __ldg(q);
+#else
+  return *q;
+#endif
+}
 
 I3RC_HD int ext_index(const Problem& p, int ix, int iy, int iz) { return ix * p.esx + iy * p.esy + iz * p.esz; }
 // extinction of layer iz of the column whose index (ext_index) is idx
@@ -341,24 +364,26 @@ I3RC_HD void make_direction(float mu, float phi, float* ux, float* uy, float* uz
 }
 
 // computeScatteringAngle, MCRT:1390-1417 (quirk Q1 kept: the interpolation weight is not scaled)
+template <bool SM = false>
 I3RC_HD float scattering_angle(const float* T, int n, float xi) {
   int k = (int)(xi * (float)n);  // angleIndex - 1
   if (k + 1 < n) {
     float leftOver = xi - I3RC_FDIV((float)k, (float)n);
-    return (1.0f - leftOver) * I3RC_LDG(T + k) + leftOver * I3RC_LDG(T + k + 1);
+    return (1.0f - leftOver) * tab_load<SM>(T + k) + leftOver * tab_load<SM>(T + k + 1);
   }
-  return I3RC_LDG(T + n - 1);
+  return tab_load<SM>(T + n - 1);
 }
 
 // lookUpPhaseFuncValsFromTable, MCRT:1613-1652
+template <bool SM = false>
 I3RC_HD float phase_lookup(const float* T, int n, float angle) {
   float deltaTheta = I3RC_FDIV(F_PI, (float)(n - 1));
   int k = (int)I3RC_FDIV(angle, deltaTheta);  // angleIndex - 1
   if (k + 1 < n) {
     float wgt = 1.0f - I3RC_FDIV(angle - (float)k * deltaTheta, deltaTheta);
-    return wgt * I3RC_LDG(T + k) + (1.0f - wgt) * I3RC_LDG(T + k + 1);
+    return wgt * tab_load<SM>(T + k) + (1.0f - wgt) * tab_load<SM>(T + k + 1);
   }
-  return I3RC_LDG(T + n - 1);
+  return tab_load<SM>(T + n - 1);
 }
 
 // next_direct, MCRT:2086-2113 (Marchuk rotation, rejection sampling in the unit disc; one block = two rounds)
@@ -885,9 +910,9 @@ I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, L
     float proj = L.ux * I3RC_LDG(dv + 0) + L.uy * I3RC_LDG(dv + 1) + L.uz * I3RC_LDG(dv + 2);
     proj = fminf(fmaxf(proj, -1.0f), 1.0f);
     float ang = acosf(proj);
-    const TableDesc& T = p.tables[L.comp - 1];
+    const TableDesc& T = tables_of(p)[L.comp - 1];
     const float* tab = (!P::kFast && p.useHybrid && L.order <= p.numOrdersOrig) ? T.fwdOrig : T.fwd;
-    float val = phase_lookup(tab + (size_t)L.pfi * T.nFwd, T.nFwd, ang);
+    float val = phase_lookup<P::kTabSm>(tab + (size_t)L.pfi * T.nFwd, T.nFwd, ang);
     phat = val * I3RC_LDG(dv + 7);  // 1 / (4 pi |mu|), MCRT:1509
   }
   int mode = MODE_LE_PLAIN;
@@ -1111,8 +1136,8 @@ I3RC_HD void scatter_photon(const P& p, Lane& L, float xiRoulette, float xiAngle
       photon_done(L);
       return;
     }
-    const TableDesc& T = p.tables[L.comp - 1];
-    float theta = scattering_angle(T.inv + (size_t)L.pfi * T.nInv, T.nInv, xiAngle);
+    const TableDesc& T = tables_of(p)[L.comp - 1];
+    float theta = scattering_angle<P::kTabSm>(T.inv + (size_t)L.pfi * T.nInv, T.nInv, xiAngle);
     next_direct(p, L, I3RC_COS(theta));
   }
 }

@@ -725,3 +725,22 @@ def test_large_hand_filled_photon_arrays_are_traced_in_overlapped_pieces(cuda):
     assert np.all(np.abs(z) <= familywise_bound(z.size, nb - 1)), z
     closure = a[:, 0] + a[:, 2] + 0.9 * a[:, 1]
     assert abs(closure.mean() - 1.0) < 2e-3
+
+
+def test_phase_tables_staged_in_shared_memory_give_the_same_photons(cuda):
+    """The experimental one-block-per-SM kernel that stages the inverse and forward phase-function tables in shared memory
+    (`tables_in_smem`): same Philox streams, same table values, so the same batch up to float32 summation order."""
+    d = fields.landsat_cloud(1.0, nLegendreCoefficients=32)
+    kw = dict(surfaceAlbedo=0.0, intensityMus=[1.0, 0.5, 0.5], intensityPhis=[0.0, 0.0, 180.0], useRussianRouletteForIntensity=True,
+              zetaMin=0.3, minInverseTableSize=10001, minForwardTableSize=10001)
+    res = []
+    for staged in (1, 0):
+        I = make_integrator(cuda, d, **kw)
+        assert cuda.set_tuning(I.handle, b"tables_in_smem", staged) == 0
+        computeRadiativeTransfer(I, new_RandomNumberSequence([10, 4]), new_PhotonStream(0.5, 0.0, numberOfPhotons=300_000))
+        res.append((reportResults(I, "meanFluxUp", "meanFluxDown", "meanIntensity", "fluxUp"), getCounters(I)))
+    (a, ca), (b, cb) = res
+    assert ca == cb
+    for k in ("meanFluxUp", "meanFluxDown", "meanIntensity"):
+        assert np.allclose(a[k], b[k], rtol=1e-5), k
+    assert np.allclose(a["fluxUp"], b["fluxUp"], rtol=1e-4, atol=1e-6)

@@ -1,4 +1,5 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -k "arrays" 2>&1 | tail -5
+python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -k "arrays or staged" 2>&1 | tail -5
+python tools/gpu_probe.py tune landsat 16000000 '{}' '{"tables_in_smem":1}' '{"resident_blocks":4}' > gpurun_out/r02_h_tabsm.txt 2>&1; cat gpurun_out/r02_h_tabsm.txt
 python bench.py --no-cpu-baseline --no-ncu > gpurun_out/r02_h_bench.json 2> gpurun_out/r02_h_bench.err
 python - <<'PY'
 import json

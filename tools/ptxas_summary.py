@@ -10,6 +10,6 @@ pat = (r"Compiling entry function '(\S+)'[^\n]*\n[^\n]*\n\s*(\d+) bytes stack fr
 for m in re.finditer(pat, t):
     n = m.group(1)
     if "k_transport" in n:
-        args = re.search(r"k_transportILi(\d+)ELb(\d)ELb(\d)ELb(\d)ELi(\d+)ELi(\d+)ELi(\d+)ELi(\d+)ELb(\d)ELb(\d)", n)
-        print("k_transport<BLOCK=%s REG=%s FAST=%s SPLIT=%s MINB=%s STEPS=%s NSLOT=%s QCAP=%s TSM=%s JUMP=%s>" % args.groups(),
+        args = re.search(r"k_transportILi(\d+)ELb(\d)ELb(\d)ELb(\d)ELi(\d+)ELi(\d+)ELi(\d+)ELi(\d+)ELb(\d)ELb(\d)ELb(\d)", n)
+        print("k_transport<BLOCK=%s REG=%s FAST=%s SPLIT=%s MINB=%s STEPS=%s NSLOT=%s QCAP=%s TSM=%s JUMP=%s TABSM=%s>" % args.groups(),
               "stack", m.group(2), "spill st/ld", m.group(3), m.group(4), "regs", m.group(5), "smem", m.group(6))
