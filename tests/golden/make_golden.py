@@ -51,18 +51,18 @@ CASES = {
     "radar_c1_rr": (lambda: fields.radar_cloud(0.99, "C1"), dict(
         surfaceAlbedo=0.0, intensityMus=[1.0, 0.5, 0.5], intensityPhis=[0.0, 0.0, 180.0],
         useRussianRouletteForIntensity=True, zetaMin=0.3, minInverseTableSize=10001, minForwardTableSize=10001),
-        dict(solarMu=0.5, solarAzimuth=0.0), 50000, 32),
+        dict(solarMu=0.5, solarAzimuth=0.0), 500000, 64),
     # BASELINE config 2 (step cloud) with the sun overhead
     "step_mu1_rr": (lambda: fields.step_cloud(0.99), dict(
         surfaceAlbedo=0.0, intensityMus=[1.0, 0.5, 0.5], intensityPhis=[0.0, 0.0, 180.0],
-        useRussianRouletteForIntensity=True, zetaMin=0.3), dict(solarMu=1.0, solarAzimuth=0.0), 200000, 32),
+        useRussianRouletteForIntensity=True, zetaMin=0.3), dict(solarMu=1.0, solarAzimuth=0.0), 1000000, 64),
     # BASELINE config 5 scaled to 256x256x200 (52 MB extinction field: large enough for new_Integrator to choose the
     # layer-compacted field and the SPLIT kernel by itself), 2 components, 27-entry table, 16 directions
     "les_mid_split": (lambda: fields.synthetic_les(nx=256, ny=256, nz=200), dict(
         surfaceAlbedo=0.05, intensityMus=[m for m in (1.0, 0.8, 0.6, 0.4) for _ in range(4)],
         intensityPhis=[p for _ in range(4) for p in (0.0, 90.0, 180.0, 270.0)], useRussianRouletteForIntensity=True,
         zetaMin=0.3, minInverseTableSize=10001, minForwardTableSize=10001),
-        dict(solarMu=0.5, solarAzimuth=30.0), 20000, 32),
+        dict(solarMu=0.5, solarAzimuth=30.0), 50000, 64),
 }
 BATCH_BEGIN = {"landsat_rr_hi_b": 65}  # first batch number (default 1): seeds are (/ iseed, batch /)
 COARSEN = {"les_mid_split": 8}  # per-column fields stored as means over 8x8 blocks of columns (fixture size)

@@ -288,8 +288,8 @@ def _coarsen(a, f=8):
 
 
 # GPU photons per batch and batches for each fixture (default: twice the oracle's photons per batch, 16 batches)
-GOLDEN_GPU_SIZE = {"landsat_rr_hi": (16_000_000, 64), "les_mid_split": (200_000, 16), "radar_c1_rr": (400_000, 16),
-                   "step_mu1_rr": (1_000_000, 16)}
+GOLDEN_GPU_SIZE = {"landsat_rr_hi": (16_000_000, 64), "les_mid_split": (1_000_000, 16), "radar_c1_rr": (4_000_000, 16),
+                   "step_mu1_rr": (8_000_000, 16)}
 
 
 def _load_golden(name):
