@@ -526,6 +526,7 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
   p.nextPhoton = h->d_next;
   // Tallies staged in shared memory, one private copy per warp, when the domain has so few columns that the whole GPU
   // would otherwise hammer a handful of addresses: fluxes and radiances, and the volume absorption too if it fits.
+  p.deriveAbs = 1;
   p.tsmN = 0;
   for (int& o : p.tsmOff) o = -1;
   {
@@ -823,6 +824,10 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
     p.firstPhoton = off;
     rc = launch_transport(h, p);
     h->traceLaunches++;
+    if (rc == I3RC_SUCCESS && h->volAbsDirty) {  // absorbed flux per column = the column sums of the volume absorption
+      k_abs_from_volume<<<(unsigned)((ncol + 127) / 128), 128, 0, h->stream>>>(h->nz, ncol, h->d_volAbs, h->d_fluxAbs);
+      h->otherLaunches++;
+    }
     if (fold && rc == I3RC_SUCCESS) {
       size_t o = 0;
       for (auto& t : tallies) {

@@ -838,6 +838,14 @@ __global__ void k_slab_sums(const float* __restrict__ in, size_t ncol, double* _
   }
   if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
 }
+// fluxAbsorbed[col] = sum over layers of the raw volume absorption (the same increments, MCRT:644-647; Problem::deriveAbs)
+__global__ void k_abs_from_volume(int nz, size_t ncol, const float* __restrict__ volAbs, float* __restrict__ fluxAbs) {
+  const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  float s = 0.0f;
+  for (int k = 0; k < nz; k++) s += volAbs[(size_t)k * ncol + col];
+  fluxAbs[col] = s;
+}
 // A batch traced in pieces: acc += tally; the tally restarts from zero, or -- after the last piece -- gets the total
 __global__ void k_fold_tally(float* __restrict__ tally, double* __restrict__ acc, size_t n, int last) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -144,6 +144,9 @@ struct Problem {
   // Small domains (planeParallel: 1 column, the step cloud: 32): every warp keeps a private copy of the tallies in shared
   // memory (tsmN floats; tsmOff[TAL_*] = where each tally starts in it, -1 = not staged), see warp_tally (kernels.cuh).
   int tsmN, tsmOff[5];
+  // fluxAbsorbed(x,y) receives exactly the increments of volumeAbsorption(x,y,:) (MCRT:644-647), so the library does not
+  // tally it: it sums the column of the (raw) volume absorption after the kernel (k_abs_from_volume).  0: tally it.
+  int deriveAbs;
   unsigned long long* counters;
   unsigned long long* nextPhoton;
   long long firstPhoton;  // photon ids of this launch are firstPhoton + [0, src.n)
@@ -1109,7 +1112,7 @@ I3RC_HD int photon_event(const P& p, Lane& L, float xi0, float xi1, TAL& tal) {
     if (L.pfi < 0) L.pfi = 0;
     if (ssa < 1.0f) {  // MCRT:642-649
       float a = L.w * (1.0f - ssa);
-      tal.add(p, TAL_ABS, (size_t)(L.cy * p.nx + L.cx), a);
+      if (!p.deriveAbs) tal.add(p, TAL_ABS, (size_t)(L.cy * p.nx + L.cx), a);
       tal.add(p, TAL_VOL, cell, a);
       L.w *= ssa;
       I3RC_COUNT(L, CNT_ABS, 1);
