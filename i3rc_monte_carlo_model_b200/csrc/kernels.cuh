@@ -29,6 +29,11 @@ namespace i3rc {
 //                  device photon counter (one warp-aggregated atomicAdd), and the task of the next path segment.
 // So both the cell-crossing loop and the event code run with (nearly) full warps, whatever the individual photons do.
 // A batch that finds the ring full is suspended between two directions and resumed after more trace rounds.
+// Variants (template flags): TSM = the tallies of a few-column domain are staged per warp in shared memory and committed
+// warp-aggregated (warp_tally, flush_staged_tallies); JUMP = rays use the empty-space codes of the gather field
+// (transport.cuh, ray_advance_far; measured slower, off by default); TABSM = one 16-warp block per SM with the
+// phase-function tables staged in shared memory (measured slower, an experiment).  A radiance direction that points
+// straight up is never traced: make_le_task works its contribution out from the column's suffix sums.
 // The physics functions are the ones of transport.cuh; the per-photon Philox streams make the result independent of
 // which lane traces which ray (up to float summation order in the tallies).
 template <int NSLOT>
