@@ -470,6 +470,7 @@ def main():
                 f.result()
             computeRadiativeTransfer(I, new_RandomNumberSequence([11, 2_000_000 + w]), phs[w])
         barrier()
+        be.reset_timing(I.handle)
         t0 = time.perf_counter()
         pending = fill(phs[0], mine[0])
         for i, b in enumerate(mine):
@@ -481,13 +482,15 @@ def main():
             r = reportResults(I, *want, out=out)                                        # D2H into host arrays
         be.synchronize(I.handle)
         el = time.perf_counter() - t0
+        e2e_trace_ms = timing_of(be, I)[0]  # first transport launch to last one of every batch, copies it waits for included
         pool.shutdown()
         if world > 1:
             t = torch.tensor([el], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             el = t.item()
         e2e = {"value": total_photons / el, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": el * 1e3 / K, "host_threads_filling_photon_arrays": nthr,
+               "ms_per_step": el * 1e3 / K, "transport_ms_per_step": e2e_trace_ms / max(len(mine), 1),
+               "host_threads_filling_photon_arrays": nthr,
                "path": "per batch: photon arrays of type(photonStream) filled on the host (2N uniform deviates, inside the clock, "
                "overlapped with the previous batch's kernel) -> i3rc_computeRadiativeTransfer (host->device copy inside) -> "
                "i3rc_reportResults into host arrays", "meanFluxUp_last": float(r["meanFluxUp"])}

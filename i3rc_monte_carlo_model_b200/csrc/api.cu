@@ -116,6 +116,8 @@ struct i3rc_integrator {
   const float* hostArrays[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaStream_t copyStream = nullptr;
   std::vector<cudaEvent_t> copyDone;  // one per piece of a batch
+  unsigned long long* d_avail = nullptr;   // photons of the batch uploaded so far (SourceDev::avail)
+  unsigned long long* h_avail = nullptr;   // pinned: the values the copy engine writes there, one per piece
   cudaEvent_t computeDone = nullptr;
   // batch moments
   double* d_stats = nullptr;
@@ -791,6 +793,10 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
     }
     CUDA_OK(h, cudaMemsetAsync(h->d_fold, 0, sizeof(double) * nTally, h->stream));
   }
+  // Hand-filled arrays of a batch that needs no folding are traced by ONE launch that starts when the first piece has
+  // arrived and is told, by the copy engine, how far the upload has got (SourceDev::avail): no kernel ever waits for
+  // another kernel, only for the DMA engine, which does not need an SM.
+  const bool streamed = arrays && !fold && nPieces > 1;
   if (arrays) {
     CUDA_OK(h, cudaEventRecord(h->computeDone, h->stream));  // the previous batch may still be reading the arrays
     CUDA_OK(h, cudaStreamWaitEvent(h->copyStream, h->computeDone, 0));
@@ -800,15 +806,38 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
       CUDA_OK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       h->copyDone.push_back(e);
     }
+    if (streamed) {
+      if (!h->d_avail) {
+        CUDA_OK(h, cudaMalloc(&h->d_avail, sizeof(unsigned long long)));
+        CUDA_OK(h, cudaHostAlloc(&h->h_avail, sizeof(unsigned long long) * 64, cudaHostAllocDefault));
+      }
+      CUDA_OK(h, cudaMemsetAsync(h->d_avail, 0, sizeof(unsigned long long), h->copyStream));
+    }
     for (int c = 0; c < nPieces; c++) {
       const long long len = cuts[c + 1] - cuts[c];
       for (int k = 0; k < 5 && len > 0; k++)
         CUDA_OK(h, cudaMemcpyAsync(h->d_srcArrays + k * n + cuts[c], h->hostArrays[k] + cuts[c], sizeof(float) * len,
                                    cudaMemcpyHostToDevice, h->copyStream));
+      if (streamed && c < 64) {
+        h->h_avail[c] = (unsigned long long)cuts[c + 1];
+        CUDA_OK(h, cudaMemcpyAsync(h->d_avail, h->h_avail + c, sizeof(unsigned long long), cudaMemcpyHostToDevice, h->copyStream));
+      }
       CUDA_OK(h, cudaEventRecord(h->copyDone[c], h->copyStream));
     }
   }
-  for (int c = 0; c < nPieces && rc == I3RC_SUCCESS; c++) {
+  if (streamed) {  // one launch over the whole batch
+    CUDA_OK(h, cudaStreamWaitEvent(h->stream, h->copyDone[0], 0));
+    p.src.n = n;
+    p.src.avail = h->d_avail;
+    p.firstPhoton = 0;
+    rc = launch_transport(h, p);
+    h->traceLaunches++;
+    if (rc == I3RC_SUCCESS && h->volAbsDirty) {
+      k_abs_from_volume<<<(unsigned)((ncol + 127) / 128), 128, 0, h->stream>>>(h->nz, ncol, h->d_volAbs, h->d_fluxAbs);
+      h->otherLaunches++;
+    }
+  }
+  for (int c = 0; c < nPieces && rc == I3RC_SUCCESS && !streamed; c++) {
     const long long off = cuts[c], len = cuts[c + 1] - cuts[c];
     if (len <= 0) continue;
     if (arrays) CUDA_OK(h, cudaStreamWaitEvent(h->stream, h->copyDone[c], 0));
@@ -1203,6 +1232,9 @@ void i3rc_finalize_Integrator(i3rc_integrator* h) {
     h->copyStream = nullptr;
   }
   dfree(h->d_next);
+  dfree(h->d_avail);
+  if (h->h_avail) cudaFreeHost(h->h_avail);
+  h->h_avail = nullptr;
   dfree(h->d_scratch);
   dfree(h->d_fscratch);
   dfree(h->d_srcArrays);

@@ -335,6 +335,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
           const int leader = __ffs(mn) - 1;
           if (lane == leader) base = atomicAdd(p.nextPhoton, (unsigned long long)__popc(mn));
           base = __shfl_sync(full, base, leader);
+          if (p.src.avail) {  // hand-filled arrays still being uploaded: wait until this warp's photons have arrived
+            const unsigned long long want = min(base + (unsigned long long)__popc(mn), (unsigned long long)p.src.n);
+            unsigned spins = 0;
+            while (*(const volatile unsigned long long*)p.src.avail < want && ++spins < (1u << 24)) __nanosleep(256);
+            if (spins >= (1u << 24)) I3RC_COUNT(E, CNT_BAD, 1);  // (4 s without the copy: give up rather than hang)
+          }
           if (need) {
             const long long id = (long long)base + __popc(mn & lt);
             if (id < p.src.n) {

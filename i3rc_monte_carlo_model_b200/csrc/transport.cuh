@@ -98,6 +98,9 @@ struct SourceDev {
   int pointsUp, hasDx, hasDy;
   float deltaX, deltaY;
   const float *ax, *ay, *az, *amu, *aphi;  // I3RC_SRC_ARRAYS (device copies)
+  // I3RC_SRC_ARRAYS uploaded while the kernel runs: number of photons whose array elements have arrived so far (written
+  // by the copy engine after every piece of the upload); null = everything is there before the launch
+  const unsigned long long* avail;
 };
 
 struct Problem {
@@ -795,11 +798,21 @@ I3RC_HD float init_photon_state(const P& p, Lane& L, long long id) {
       phi = s.phi;
       break;
     case 7:  // hand-filled public arrays of the reference type
-      qx = I3RC_LDG(s.ax + id);
-      qy = I3RC_LDG(s.ay + id);
-      qz = I3RC_LDG(s.az + id);
-      mu = I3RC_LDG(s.amu + id);
-      phi = I3RC_LDG(s.aphi + id);
+#ifdef __CUDA_ARCH__
+      // (read past L1: parts of the arrays may arrive while the kernel runs, and a cache line fetched for a neighbour
+      //  before its own elements were there must not be served again)
+      qx = __ldcg(s.ax + id);
+      qy = __ldcg(s.ay + id);
+      qz = __ldcg(s.az + id);
+      mu = __ldcg(s.amu + id);
+      phi = __ldcg(s.aphi + id);
+#else
+      qx = s.ax[id];
+      qy = s.ay[id];
+      qz = s.az[id];
+      mu = s.amu[id];
+      phi = s.aphi[id];
+#endif
       break;
     default:
       break;
