@@ -767,9 +767,11 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
   const bool arrays = src.kind == I3RC_SRC_ARRAYS;
   std::vector<long long> cuts{0};
   if (arrays && n >= (1 << 20)) {
-    cuts.push_back(std::min<long long>(((n / 20 + 127) / 128) * 128, perPiece));
-    const long long second = ((3 * n / 10 + 127) / 128) * 128;
-    if (second - cuts.back() <= perPiece) cuts.push_back(second);
+    // (2 %, 8 %, 30 % of the batch, then the rest: the first piece only has to feed the photon slots of the grid)
+    for (const long long per1000 : {20LL, 80LL, 300LL}) {
+      const long long cut = ((n * per1000 / 1000 + 127) / 128) * 128;
+      if (cut > cuts.back() && cut < n && cut - cuts.back() <= perPiece) cuts.push_back(cut);
+    }
   }
   while (n - cuts.back() > perPiece) cuts.push_back(cuts.back() + perPiece);
   cuts.push_back(n);
