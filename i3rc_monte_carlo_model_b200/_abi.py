@@ -130,6 +130,7 @@ COUNTER_FIELDS = [
     "roulette_kills",
     "null_collisions",
     "cells_skipped",
+    "cells_skipped_intensity",
 ]
 
 

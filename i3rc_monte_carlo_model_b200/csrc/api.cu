@@ -63,6 +63,9 @@ struct i3rc_integrator {
   float *d_ext = nullptr, *d_cum = nullptr, *d_ssa = nullptr;
   float* d_extRaw = nullptr;  // un-normalised extinction of every component (kept from the first profile swap on)
   float* d_colTau = nullptr;  // column suffix sums of extinction x layer depth (Problem::colTau)
+  int l2Persist = 1;          // persisting L2 access window over a gather field of 32 MB or more (512x512x256: +2.5 %,
+                              // profiles/r02_ab_l2_persisting_window_les.txt)
+  const void* l2WindowFor = nullptr;
   int tablesInSmem = 0;       // (experiment) stage the phase-function tables in shared memory (one 16-warp block per SM)
   int debugZeroStrides = 0;   // (experiment) every gather reads element 0 of the field: on a homogeneous domain the results
                               // are unchanged and the run time is what the kernel would need if gathers always hit L1
@@ -74,6 +77,8 @@ struct i3rc_integrator {
                               // a jump costs the whole warp more than the lanes that jump save
   float* d_extZ = nullptr;  // totalExt again, z-fastest: the copy the rays gather from (see Problem::ext)
   int2* d_zlut = nullptr;   // layer table when only the horizontally varying layers are stored (Problem::zlut)
+  float4* d_zslab = nullptr;  // runs of uniform layers a ray may cross in one go (Problem::zslab; regular grids)
+  int slabJump = 1;           // (tuning) 0: uniform slabs are walked cell by cell
   int nzc = 0;
   int* d_pf = nullptr;
   bool absorbing = true;    // some cell of some component has ssa < 1 (else volumeAbsorption / fluxAbsorbed stay zero)
@@ -244,6 +249,7 @@ int build_gather_field(i3rc_integrator* h) {
   h->otherLaunches++;
   dfree(h->d_extZ);
   dfree(h->d_zlut);
+  dfree(h->d_zslab);
   h->nzc = 0;
   {
     // which layers are horizontally uniform?  If enough are, only the others are stored in 3-D (Problem::zlut)
@@ -275,6 +281,23 @@ int build_gather_field(i3rc_integrator* h) {
       CUDA_OK(h, upload(&d_layers, layers.data(), layers.size(), h->stream));
       t_layers.p = d_layers;
       CUDA_OK(h, upload(&h->d_zlut, lut.data(), lut.size(), h->stream));
+      if (h->xyRegular && h->zRegular) {  // runs of consecutive uniform layers (Problem::zslab)
+        std::vector<float4> slab(nz, make_float4(0.f, 0.f, 0.f, 0.f));
+        auto layer_tau = [&](int j) {
+          float e;
+          memcpy(&e, &mm[2 * j], sizeof e);
+          return e * (h->ze[j + 1] - h->ze[j]);
+        };
+        for (int k = 0; k < nz; k++) {
+          if (lut[k].x >= 0) continue;
+          int up = 0, dn = 0;
+          float vUp = 0.0f, vDn = 0.0f;
+          for (int j = k + 1; j < nz && lut[j].x < 0; j++) up++, vUp += layer_tau(j);
+          for (int j = k - 1; j >= 0 && lut[j].x < 0; j--) dn++, vDn += layer_tau(j);
+          slab[k] = make_float4((float)up, (float)dn, vUp, vDn);
+        }
+        CUDA_OK(h, upload(&h->d_zslab, slab.data(), slab.size(), h->stream));
+      }
       CUDA_OK(h, cudaMalloc(&h->d_extZ, sizeof(float) * ncol * nzc));
       dim3 b(32, 8), g((unsigned)((nx + 31) / 32), (unsigned)((nzc + 31) / 32), (unsigned)ny);
       k_compact_zfast<<<g, b, 0, h->stream>>>(nx, ny, nzc, d_layers, h->d_ext, h->d_extZ);
@@ -481,6 +504,7 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
   p.ze = h->d_ze;
   p.ext = h->d_extZ;
   p.zlut = h->d_zlut;
+  p.zslab = h->slabJump ? h->d_zslab : nullptr;
   p.nzc = h->nzc;
   p.esx = h->ny * (h->nzc ? h->nzc : h->nz);
   p.esy = h->nzc ? h->nzc : h->nz;
@@ -667,7 +691,36 @@ int launch_transport_fast(i3rc_integrator* h, const Problem& p) {
          : steps == 16 ? launch_transport_t<128, true, true, false, MINB, 16, NSLOT, QCAP>(h, p)
                        : launch_transport_t<128, true, true, false, MINB, 32, NSLOT, QCAP>(h, p);
 }
+// A gather field that does not share L2 comfortably with the rest of the traffic (the per-component fields of a collision
+// and the volume tallies of a 512x512x256 domain are gigabytes) is given a persisting L2 access window: its lines are
+// kept, everything else streams.  (tuning `l2_persist`; set up once per gather field)
+void set_l2_window(i3rc_integrator* h) {
+  if (h->l2WindowFor == h->d_extZ) return;
+  h->l2WindowFor = h->d_extZ;
+  const size_t bytes = sizeof(float) * (size_t)h->nx * h->ny * (h->nzc ? h->nzc : h->nz);
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof(attr));
+  int maxPersist = 0, maxWindow = 0;
+  cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+  cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+  if (!h->l2Persist || bytes < ((size_t)32 << 20) || maxPersist <= 0 || maxWindow <= 0) {
+    attr.accessPolicyWindow.num_bytes = 0;  // no window
+    cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    return;
+  }
+  const size_t persist = std::min<size_t>((size_t)maxPersist, bytes);
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist);
+  attr.accessPolicyWindow.base_ptr = h->d_extZ;
+  attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)maxWindow);
+  attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)attr.accessPolicyWindow.num_bytes);
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+  cudaGetLastError();
+}
+
 int launch_transport(i3rc_integrator* h, const Problem& p) {
+  set_l2_window(h);
   const bool reg = p.xyRegular && p.zRegular;
   const bool fast = p.useRayTracing && p.src.kind != 5 && p.src.kind != 6 && !p.useSurfaceBDRF && !p.useHybrid && !p.limitContrib &&
                     !p.trackByComponent;
@@ -939,6 +992,7 @@ int fetch_counters(i3rc_integrator* h) {
   o.roulette_kills = c[CNT_KILL];
   o.null_collisions = c[CNT_NULL];
   o.cells_skipped = c[CNT_SKIP];
+  o.cells_skipped_intensity = c[CNT_SKIP_LE];
   return I3RC_SUCCESS;
 }
 
@@ -1204,6 +1258,7 @@ void i3rc_finalize_Integrator(i3rc_integrator* h) {
   dfree(h->d_extRaw);
   dfree(h->d_colTau);
   dfree(h->d_extJ);
+  dfree(h->d_zslab);
   dfree(h->d_extZ);
   dfree(h->d_zlut);
   dfree(h->d_cum);
@@ -1644,9 +1699,16 @@ int i3rc_trace_rays(i3rc_integrator* h, int n, const float* pos, const float* di
     CUDA_OK(h, cudaMalloc(&d_tau, sizeof(float) * n));
     CUDA_OK(h, cudaMalloc(&d_po, sizeof(float) * 3 * n));
     CUDA_OK(h, cudaMalloc(&d_idx, sizeof(int) * 3 * n));
-    ProblemDyn p;
-    fill_problem(h, p);
-    k_trace_rays<<<(n + 127) / 128, 128, 0, h->stream>>>(p, n, d_pos, d_dir, d_lim, d_tau, d_po, d_idx);
+    if (h->xyRegular && h->zRegular && h->nzc) {
+      // the stepping code of the production kernel for regular grids with a layer table (uniform slabs crossed in one go)
+      ProblemT<true, false, true> p;
+      fill_problem(h, p);
+      k_trace_rays<<<(n + 127) / 128, 128, 0, h->stream>>>(p, n, d_pos, d_dir, d_lim, d_tau, d_po, d_idx);
+    } else {
+      ProblemDyn p;
+      fill_problem(h, p);
+      k_trace_rays<<<(n + 127) / 128, 128, 0, h->stream>>>(p, n, d_pos, d_dir, d_lim, d_tau, d_po, d_idx);
+    }
     h->otherLaunches++;
     CUDA_OK(h, cudaGetLastError());
     CUDA_OK(h, cudaMemcpyAsync(tauOut, d_tau, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
@@ -2043,7 +2105,12 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->eventThreshold = value;
   else if (k == "track_by_component")
     h->trackByComponent = value != 0;
-  else if (k == "tables_in_smem" && (value == 0 || value == 1))
+  else if (k == "slab_jump" && (value == 0 || value == 1))
+    h->slabJump = value;  // 0: runs of horizontally uniform layers are walked cell by cell
+  else if (k == "l2_persist" && (value == 0 || value == 1)) {
+    h->l2Persist = value;
+    h->l2WindowFor = nullptr;
+  } else if (k == "tables_in_smem" && (value == 0 || value == 1))
     h->tablesInSmem = value;
   else if (k == "debug_zero_strides" && (value == 0 || value == 1))
     h->debugZeroStrides = value;

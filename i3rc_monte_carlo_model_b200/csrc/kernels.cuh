@@ -522,7 +522,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
 }
 
 // ---- probes: accumulateExtinctionAlongPath for explicit rays (deterministic sub-path parity) ---------------
-__global__ void k_trace_rays(const ProblemDyn p, int n, const float* __restrict__ pos, const float* __restrict__ dir,
+template <class P>
+__global__ void k_trace_rays(const P p, int n, const float* __restrict__ pos, const float* __restrict__ dir,
                              const float* __restrict__ tauLimit, float* __restrict__ tauOut,
                              float* __restrict__ posOut, int* __restrict__ idxOut) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;

@@ -47,8 +47,11 @@
 #endif
 
 #ifndef __CUDACC__
-struct int2 {  // (the CUDA vector type, for the CPU build of this header)
+struct int2 {  // (the CUDA vector types, for the CPU build of this header)
   int x, y;
+};
+struct float4 {
+  float x, y, z, w;
 };
 #endif
 
@@ -69,7 +72,7 @@ constexpr int DIR_STRIDE = 8;
 constexpr int MAX_RAY_STEPS = 1 << 26;  // hang protection: a ray that long is dropped as "bad"
 
 enum { CNT_PHOTONS = 0, CNT_BAD, CNT_CROSS_PH, CNT_CROSS_LE, CNT_COLL, CNT_ABS, CNT_CONTRIB, CNT_TOP, CNT_SURF,
-       CNT_RNG, CNT_KILL, CNT_NULL, CNT_SKIP, CNT_N };
+       CNT_RNG, CNT_KILL, CNT_NULL, CNT_SKIP, CNT_SKIP_LE, CNT_N };
 // Empty-space codes (Problem::ext of a JUMP kernel): an empty cell whose whole Chebyshev neighbourhood of radius n + 1 is
 // empty (periodic in x and y; beyond the top and the bottom counts as empty) holds -n instead of 0, for n in
 // [JUMP_MIN, JUMP_MAX].  A ray that has just crossed such a cell may cross up to n further cells on every axis without
@@ -124,6 +127,10 @@ struct Problem {
   // fits the L2 cache.
   const int2* zlut;
   int nzc;
+  // Runs of consecutive horizontally uniform layers ("slabs": the clear air above and below the clouds) can be crossed
+  // in one go whatever the horizontal position: zslab[iz] = { layers of the slab above iz, layers below iz, vertical
+  // optical depth of those above, of those below } for a uniform layer iz (regular grids; ray_cross_slab).  Null: unused.
+  const float4* zslab;
   const float* cumExt;
   const float* ssa;
   const int* pfIdx;
@@ -180,6 +187,21 @@ struct ProblemDyn : Problem {
   static constexpr bool kJump = false;
   static constexpr bool kTabSm = false;
 };
+// Kernels that cross uniform slabs in one go (regular grids with a layer table): the value gathered for a cell of a uniform
+// layer may be a CODE, -(1 + tau), tau = the optical path of the ray from where it is to the far side of the slab.
+template <class P>
+struct SlabJump {
+  static constexpr bool on = P::kSplit && P::kRegular;
+};
+constexpr int SLAB_MIN = 2;  // fewest further layers of a slab worth a jump
+// what a (possibly coded) gathered value contributes: the extinction of the cell (to be multiplied by the path length
+// in it), or -- a slab code, path length 1 -- the optical path through the rest of the slab
+template <class P>
+I3RC_HD float ext_value(float e) {
+  if (P::kJump) return fmaxf(e, 0.0f);
+  if (SlabJump<P>::on) return e < 0.0f ? -e - 1.0f : e;
+  return e;
+}
 // the table descriptors the physics reads: the integrator's (global memory), or -- TABSM kernels -- the block's staged copy
 #ifdef __CUDACC__
 __shared__ TableDesc g_smTables;  // (written by k_transport<.., TABSM> before any lookup)
@@ -497,8 +519,85 @@ I3RC_HD bool ray_advance_far(const P& p, Lane& L, int n) {
   L.ry = qy;
   L.rz = qz;
   L.sp = T;
-  I3RC_COUNT(L, CNT_SKIP, mx + my + mz - 1);  // cells passed without a look (one of them is the ordinary step's)
+  I3RC_COUNT(L, L.mode == MODE_PHOTON ? CNT_SKIP : CNT_SKIP_LE, mx + my + mz - 1);  // cells passed without a look (one of them is the ordinary step's)
   return L.cntz == 0;
+}
+// The gather for the cell the geometry has just entered.  In a uniform layer with at least SLAB_MIN further layers of
+// the same slab ahead (in the ray's direction), the value is a slab code: the optical path from the ray's position to the
+// far side of the slab, which does not depend on the horizontal position.
+template <class P>
+I3RC_HD float ext_gather_ray(const P& p, const Lane& L) {
+  const int iz = ray_iz(p, L);
+  if (SlabJump<P>::on) {
+    if (p.nzc != 0 && p.zslab) {
+#ifdef __CUDA_ARCH__
+      const int2 t = __ldg(p.zlut + iz);
+#else
+      const int2 t = p.zlut[iz];
+#endif
+      if (t.x < 0) {
+        float e;
+        memcpy(&e, &t.y, sizeof e);
+#ifdef __CUDA_ARCH__
+        const float4 s = __ldg(p.zslab + iz);
+#else
+        const float4 s = p.zslab[iz];
+#endif
+        const bool up = L.stz > 0;
+        const int ahead = (int)(up ? s.x : s.y);
+        if (ahead >= SLAB_MIN && !isinf(L.iaz)) {
+          // rest of this layer + the layers ahead: vertical optical depth / |cosine| (iaz = dz / |cosine| on a regular grid)
+          const float tauB = fmaf(e, fabsf(L.rz), (up ? s.z : s.w) * I3RC_FDIV(L.iaz, p.dz));
+          return -(tauB + 1.0f);
+        }
+        return e;
+      }
+      return I3RC_LDG(p.ext + (L.idx - iz) + t.x);
+    }
+  }
+  return ext_gather(p, L.idx, iz);
+}
+// Move the geometry from where it is in a uniform layer to the far side of the slab (the ray's optical path through it
+// has been taken from the slab code): every axis counts the faces crossed in the time it takes, x and y wrap as often
+// as they must.  Returns true when the far side of the slab is the top or the bottom of the domain.
+template <class P>
+I3RC_HD bool ray_cross_slab(const P& p, Lane& L) {
+  const int iz = ray_iz(p, L);
+#ifdef __CUDA_ARCH__
+  const float4 s = __ldg(p.zslab + iz);
+#else
+  const float4 s = p.zslab[iz];
+#endif
+  const int ahead = (int)(L.stz > 0 ? s.x : s.y);
+  const float ax = fabsf(L.rx), ay = fabsf(L.ry), az = fabsf(L.rz);
+  const float T = fmaf((float)ahead, L.iaz, az);  // path length to the far face of the last layer of the slab
+  int mx = 0, my = 0;
+  float qx = ax - T, qy = ay - T;
+  if (ax <= T) {
+    mx = (int)I3RC_FDIV(T - ax, L.iax) + 1;
+    qx = fmaxf(fmaf((float)mx, L.iax, ax) - T, 0.0f);
+  }
+  if (ay <= T) {
+    my = (int)I3RC_FDIV(T - ay, L.iay) + 1;
+    qy = fmaxf(fmaf((float)my, L.iay, ay) - T, 0.0f);
+  }
+  int nx_ = (L.cntx - 1 - mx) % p.nx, ny_ = (L.cnty - 1 - my) % p.ny;  // cells left on the axis, minus one, modulo the period
+  if (nx_ < 0) nx_ += p.nx;
+  if (ny_ < 0) ny_ += p.ny;
+  L.cntx = nx_ + 1;
+  L.cnty = ny_ + 1;
+  L.cntz -= ahead + 1;
+  L.rx = qx;
+  L.ry = qy;
+  L.rz = L.iaz;  // (a whole layer ahead, if there is one)
+  L.sp = 1.0f;   // the slab code is an optical path already
+  I3RC_COUNT(L, L.mode == MODE_PHOTON ? CNT_SKIP : CNT_SKIP_LE, mx + my + ahead);  // cells passed without a look
+  if (L.cntz <= 0) {
+    L.cntz = 0;
+    return true;
+  }
+  L.idx = ext_index(p, ray_ix(p, L), ray_iy(p, L), ray_iz(p, L));
+  return false;
 }
 // (Re)start the pipeline from the cell the geometry is in, whose extinction is eCell: it becomes the pending cell
 // (in e0: rays always start on an even step) and the gather of the next cell is issued (into e1).
@@ -506,7 +605,7 @@ template <class P>
 I3RC_HD void ray_begin(const P& p, Lane& L, float eCell) {
   L.e0 = eCell;
   L.par = 0;
-  if (!ray_advance(p, L)) L.e1 = ext_gather(p, L.idx, ray_iz(p, L));
+  if (!ray_advance(p, L)) L.e1 = ext_gather_ray(p, L);
 }
 
 // Start a ray in cell (ix,iy,iz) at offset (fx,fy,fz) inside it along direction (dx,dy,dz); ia* = 1/|cosine|;
@@ -558,9 +657,6 @@ I3RC_HD void start_ray(const P& p, Lane& L, float dx, float dy, float dz, float 
 // cell (ray_advance).  A ray that ends -- target optical path reached inside the pending cell (MCRT:1721-1731), or the
 // pending cell was the last one of the domain (MCRT:1793-1804) -- just stops with DONE_STOP; which of the two it was
 // and where the ray is then are worked out by ray_after_steps() / ray_stop_inside(), outside the hot loop.
-// the extinction a (possibly coded) field value stands for
-template <class P>
-I3RC_HD float ext_value(float e) { return P::kJump ? fmaxf(e, 0.0f) : e; }
 // The geometry leaves the cell it is in (which becomes the pending cell); ePending, just consumed, receives the gather of
 // the cell it arrives in.  With empty-space codes: a pending cell that says "the next n cells on every axis are empty"
 // lets the geometry run through all of them at once; they become ONE empty pending stretch (eOther, the value in flight
@@ -573,7 +669,21 @@ I3RC_HD void ray_move_on(const P& p, Lane& L, float& ePending, float& eOther) {
     if (!ray_advance_far(p, L, n)) ePending = ext_gather(p, L.idx, ray_iz(p, L));
     return;
   }
-  if (!ray_advance(p, L)) ePending = ext_gather(p, L.idx, ray_iz(p, L));  // (the register is free now: it becomes the look-ahead)
+  if (SlabJump<P>::on && eOther < 0.0f) {
+    // The cell the geometry is in carries a slab code.  If the ray's optical-path limit lies beyond the slab, the
+    // geometry goes to the far side at once (the next step adds the code's optical path, with path length 1: the very
+    // sum tested here); if not, the ray ends in the slab and walks there cell by cell.
+    if (fmaf(1.0f, -eOther - 1.0f, L.tau) <= L.tauLimit) {
+      if (!ray_cross_slab(p, L)) ePending = ext_gather_ray(p, L);
+      return;
+    }
+#ifdef __CUDA_ARCH__
+    eOther = __int_as_float(__ldg(p.zlut + ray_iz(p, L)).y);
+#else
+    memcpy(&eOther, &p.zlut[ray_iz(p, L)].y, sizeof(float));
+#endif
+  }
+  if (!ray_advance(p, L)) ePending = ext_gather_ray(p, L);  // (the register is free now: it becomes the look-ahead)
 }
 template <int PAR, class P>
 I3RC_HD void dda_step(const P& p, Lane& L) {

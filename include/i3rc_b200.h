@@ -127,8 +127,10 @@ typedef struct {
   int64_t crossings_photon, crossings_intensity;
   int64_t collisions, absorptions, contributions, exits_top, surface_hits;
   int64_t rng_draws, roulette_kills, null_collisions;
-  int64_t cells_skipped; /* cells a ray passed without gathering them (empty-space codes); 0 in the reference's algorithm:
-                            crossings_photon + crossings_intensity + cells_skipped = its number of cell crossings */
+  /* cells a ray passed without gathering them (uniform slabs crossed in one go, empty-space codes), by photon path
+   * segments and by local-estimate rays; 0 in the reference's algorithm: crossings_photon + cells_skipped is its number of
+   * cell crossings of photon paths */
+  int64_t cells_skipped, cells_skipped_intensity;
 } i3rc_counters;
 
 /* ---- device selection -------------------------------------------------------------------- */

@@ -51,7 +51,10 @@ def assert_counter_parity(got, ref_counters, names, label="", sigma=SIGMA, floor
     nb_ref = max(ref_counters["photons"] / max(cb["photons"].mean(), 1.0), 1.0)
     zs = []
     for c in names:
-        rate = cb[c] / np.maximum(cb["photons"], 1.0)
+        events = cb[c]
+        if c == "crossings_photon" and "cells_skipped" in cb:  # cells crossed without a look count as crossed
+            events = events + cb["cells_skipped"]
+        rate = events / np.maximum(cb["photons"], 1.0)
         a, sd = rate.mean(), rate.std(ddof=1)
         b = ref_counters[c] / max(ref_counters["photons"], 1)
         zs.append((a - b) / np.sqrt(sd**2 * (1.0 / nb + 1.0 / nb_ref) + (floor * b) ** 2 + 1e-30))

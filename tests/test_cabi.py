@@ -40,7 +40,7 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(_abi.PhaseTable) == 48
     assert C.sizeof(_abi.Component) == 24 + 16 + 48
     assert C.sizeof(_abi.PhotonSource) == 64 + 40
-    assert C.sizeof(_abi.Counters) == 13 * 8
+    assert C.sizeof(_abi.Counters) == 14 * 8
     assert C.sizeof(_abi.Params) == 112
 
 

@@ -1,0 +1,4 @@
+timeout 900 python -m pytest tests -m gpu -q --tb=short > gpurun_out/r02_o_tests.log 2>&1; tail -25 gpurun_out/r02_o_tests.log
+timeout 300 python tools/gpu_probe.py tune les 2000000 '{}' '{"slab_jump":0}' '{"resident_blocks":5}' '{"resident_blocks":5,"slab_jump":0}' > gpurun_out/r02_o_slab.txt 2>&1
+timeout 300 python tools/gpu_probe.py tune les-small 2000000 '{}' '{"slab_jump":0}' >> gpurun_out/r02_o_slab.txt 2>&1
+cat gpurun_out/r02_o_slab.txt
