@@ -274,8 +274,9 @@ int build_gather_field(i3rc_integrator* h) {
       }
     }
     const int nzc = (int)layers.size();
-    // worth it for a field that does not stay in L2 and of which at least a quarter of the layers is uniform
-    const bool big = ncell * sizeof(float) > ((size_t)48 << 20) || h->splitLayers == 2;
+    // Worth it when at least a quarter of the layers is uniform and either the field does not stay in L2 (the 3-D array
+    // shrinks) or the grid is regular (rays cross runs of uniform layers in one step, Problem::zslab)
+    const bool big = ncell * sizeof(float) > ((size_t)48 << 20) || h->splitLayers == 2 || (h->xyRegular && h->zRegular && h->slabJump);
     if (ncol > 1 && nzc > 0 && nzc * 4 <= nz * 3 && h->splitLayers && big) {
       int* d_layers = nullptr;
       CUDA_OK(h, upload(&d_layers, layers.data(), layers.size(), h->stream));

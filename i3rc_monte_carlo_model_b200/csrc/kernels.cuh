@@ -526,12 +526,14 @@ template <class P>
 __global__ void k_trace_rays(const P p, int n, const float* __restrict__ pos, const float* __restrict__ dir,
                              const float* __restrict__ tauLimit, float* __restrict__ tauOut,
                              float* __restrict__ posOut, int* __restrict__ idxOut) {
+  __shared__ uint32_t s_cnt[CNT_N];  // (event counters are atomics: shared memory, not a thread's local array)
+  if (threadIdx.x < CNT_N) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   Lane L;
-  uint32_t cnt[CNT_N];
-  for (int i = 0; i < CNT_N; i++) cnt[i] = 0;
-  L.cnt = cnt;
+  L.cnt = s_cnt;
+  L.mode = MODE_PHOTON;
   locate_abs(p.xe, p.xyRegular, p.nx, p.x0, p.xmax, p.dx, pos[3 * r], 1, &L.cx, &L.fx);
   locate_abs(p.ye, p.xyRegular, p.ny, p.y0, p.ymax, p.dy, pos[3 * r + 1], 1, &L.cy, &L.fy);
   locate_abs(p.ze, p.zRegular, p.nz, p.z0, p.zmax, p.dz, pos[3 * r + 2], 0, &L.cz, &L.fz);

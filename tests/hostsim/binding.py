@@ -54,6 +54,7 @@ def lib():
     L.hostsim_philox.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
     L.hostsim_trace_rays.argtypes = [C.POINTER(Args), C.c_int, fp, fp, fp, fp, fp, ip]
     L.hostsim_trace_rays_jump.argtypes = [C.POINTER(Args), C.c_int, fp, fp, fp, fp, fp, ip, C.POINTER(C.c_ulonglong)]
+    L.hostsim_trace_rays_slab.argtypes = [C.POINTER(Args), C.c_int, C.c_int, fp, fp, fp, fp, fp, ip, C.POINTER(C.c_ulonglong)]
     L.hostsim_set_jump.argtypes = [C.c_int]
     L.hostsim_set_vertical.argtypes = [C.c_int]
     return L
@@ -185,6 +186,21 @@ class HostSim:
         res["absorbedProfile"] = res["volumeAbsorption"].mean(axis=(0, 1))
         res["counters"] = {n_: int(cnt[i]) for i, n_ in enumerate(CNT_NAMES)}
         return res
+
+    def trace_rays_slab(self, pos, direction, tauLimit=None, jump=True):
+        """The same through the library's layer-compacted field (regular grids with horizontally uniform layers): runs of
+        uniform layers crossed in one go (jump) or cell by cell.  Returns tau, end points, end cells, (skipped, steps)."""
+        from i3rc_monte_carlo_model_b200.monteCarloIllumination import new_PhotonStream
+        a, out, cnt, keep, nD = self._args(new_PhotonStream(0.5, 0.0, numberOfPhotons=1), (0, 0))
+        pos, direction = _abi.f32(pos).reshape(-1, 3), _abi.f32(direction).reshape(-1, 3)
+        n = pos.shape[0]
+        tau, pout, idx = np.zeros(n, np.float32), np.zeros((n, 3), np.float32), np.zeros((n, 3), np.int32)
+        lim = _abi.f32(tauLimit) if tauLimit is not None else None
+        sk = (C.c_ulonglong * 2)()
+        rc = self.L.hostsim_trace_rays_slab(C.byref(a), int(jump), n, _abi.fptr(pos), _abi.fptr(direction), _abi.fptr(lim),
+                                            _abi.fptr(tau), _abi.fptr(pout), _abi.iptr(idx), sk)
+        assert rc == 0, "needs a regular grid with horizontally uniform layers"
+        return tau, pout, idx, (int(sk[0]), int(sk[1]))
 
     def trace_rays(self, pos, direction, tauLimit=None, jump=False):
         """accumulateExtinctionAlongPath for explicit rays; jump=True: through the field with empty-space codes (regular

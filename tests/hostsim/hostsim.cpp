@@ -231,7 +231,76 @@ static void trace_rays_t(P& p, int n, const float* pos, const float* dir, const 
   }
 }
 
+// The layer-compacted gather field of the library (Problem::zlut / zslab: horizontally uniform layers kept out of the 3-D
+// array, runs of them crossed in one go) built on the CPU, to run the regular-grid SPLIT stepping code one lane at a time.
+struct SplitField {
+  std::vector<float> ext;
+  std::vector<int2> lut;
+  std::vector<float4> slab;
+  int nzc = 0;
+};
+static SplitField split_field(const Problem& p) {
+  SplitField f;
+  const int nx = p.nx, ny = p.ny, nz = p.nz;
+  const size_t ncol = (size_t)nx * ny;
+  f.lut.resize(nz);
+  std::vector<int> layers;
+  std::vector<float> uni(nz, 0.0f);
+  for (int k = 0; k < nz; k++) {
+    const float* row = p.ext + (size_t)k * ncol;  // (hostsim's field is x fastest: [z][y][x])
+    bool same = true;
+    for (size_t c = 1; c < ncol && same; c++) same = row[c] == row[0];
+    if (same) {
+      int bits;
+      memcpy(&bits, &row[0], sizeof bits);
+      f.lut[k] = int2{-1, bits};
+      uni[k] = row[0];
+    } else {
+      f.lut[k] = int2{(int)layers.size(), 0};
+      layers.push_back(k);
+    }
+  }
+  f.nzc = (int)layers.size();
+  f.ext.assign(ncol * (f.nzc ? f.nzc : 1), 0.0f);
+  for (int ix = 0; ix < nx; ix++)
+    for (int iy = 0; iy < ny; iy++)
+      for (int k = 0; k < f.nzc; k++) f.ext[((size_t)ix * ny + iy) * f.nzc + k] = p.ext[((size_t)layers[k] * ny + iy) * nx + ix];
+  f.slab.assign(nz, float4{0.f, 0.f, 0.f, 0.f});
+  for (int k = 0; k < nz; k++) {
+    if (f.lut[k].x >= 0) continue;
+    int up = 0, dn = 0;
+    float vUp = 0.0f, vDn = 0.0f;
+    for (int j = k + 1; j < nz && f.lut[j].x < 0; j++) up++, vUp += uni[j] * (p.ze[j + 1] - p.ze[j]);
+    for (int j = k - 1; j >= 0 && f.lut[j].x < 0; j--) dn++, vDn += uni[j] * (p.ze[j + 1] - p.ze[j]);
+    f.slab[k] = float4{(float)up, (float)dn, vUp, vDn};
+  }
+  return f;
+}
+
 extern "C" {
+// the same rays through the layer-compacted field, uniform slabs crossed in one go (jump = 0: walked cell by cell)
+int hostsim_trace_rays_slab(const HostSimArgs* a, int jump, int n, const float* pos, const float* dir, const float* tauLimit,
+                            float* tauOut, float* posOut, int* idxOut, unsigned long long* skipped) {
+  Problem p0;
+  std::vector<TableDesc> td;
+  std::vector<float> dirs;
+  fill(a, p0, td, dirs);
+  if (!(p0.xyRegular && p0.zRegular)) return 1;
+  SplitField f = split_field(p0);
+  if (!f.nzc) return 2;
+  ProblemT<true, false, true> p;
+  static_cast<Problem&>(p) = p0;
+  p.ext = f.ext.data();
+  p.zlut = f.lut.data();
+  p.zslab = jump ? f.slab.data() : nullptr;
+  p.nzc = f.nzc;
+  p.esx = p.ny * f.nzc;
+  p.esy = f.nzc;
+  p.esz = 1;
+  p.extN = (long long)p.nx * p.ny * f.nzc;
+  trace_rays_t(p, n, pos, dir, tauLimit, tauOut, posOut, idxOut, skipped);
+  return 0;
+}
 // the same rays through the field with empty-space codes (regular grids); skipped[0] += cells passed without a look,
 // skipped[1] += DDA steps taken
 int hostsim_trace_rays_jump(const HostSimArgs* a, int n, const float* pos, const float* dir, const float* tauLimit,

@@ -195,3 +195,30 @@ def test_straight_up_directions_from_column_sums_equal_traced_rays(oracle, name,
     for k in ("crossings_photon", "collisions", "contributions", "rng_draws", "exits_top", "surface_hits"):
         assert ca[k] == cb[k], k
     assert cb["crossings_intensity"] < 0.8 * ca["crossings_intensity"]
+
+
+def test_uniform_slabs_crossed_in_one_go_along_fixed_rays(oracle):
+    """Runs of horizontally uniform layers (clear air with gas above and below the clouds) crossed in one step
+    (transport.cuh, ray_cross_slab; the library's layer-compacted field rebuilt on the CPU): against the cell-by-cell walk
+    the end cell of every ray is the same, the optical path agrees to 1e-5, and steps + cells skipped is conserved."""
+    d = fields.synthetic_les(nx=24, ny=16, nz=64, n_entries=3, seed=7, nLegendreCoefficients=8)
+    I = make_integrator(oracle, d, surfaceAlbedo=0.0)
+    oracle.tabulate(I.handle)
+    hs = HostSim(d, I, getTable)
+    rng = np.random.default_rng(21)
+    n = 1500
+    hi = np.array([d.xPosition[-1], d.yPosition[-1], d.zPosition[-1]], np.float64)
+    pos = ((0.01 + 0.98 * rng.random((n, 3))) * hi).astype(np.float32)
+    mu = rng.uniform(0.05, 1.0, n) * rng.choice([-1, 1], n)
+    phi = rng.uniform(0, 2 * np.pi, n)
+    u = np.column_stack([np.sqrt(1 - mu**2) * np.cos(phi), np.sqrt(1 - mu**2) * np.sin(phi), mu]).astype(np.float32)
+    u[:4] = [[0, 0, 1], [0, 0, -1], [0.6, 0, 0.8], [0, -0.8, -0.6]]
+    lim = np.where(rng.random(n) < 0.5, np.inf, rng.exponential(2.0, n)).astype(np.float32)
+    t0, p0, i0 = hs.trace_rays(pos, u, lim)                                   # every layer stored, every cell walked
+    t2, p2, i2, (s2, steps2) = hs.trace_rays_slab(pos, u, lim, jump=False)    # layer table, every cell walked
+    t1, p1, i1, (s1, steps1) = hs.trace_rays_slab(pos, u, lim, jump=True)     # layer table, slabs crossed in one go
+    assert np.array_equal(t0, t2) and np.array_equal(i0, i2) and s2 == 0
+    assert np.array_equal(i0, i1)
+    assert np.max(np.abs(t0 - t1) / np.maximum(np.abs(t0), 1e-3)) < 1e-5
+    assert np.max(np.abs(p0 - p1)) < 5e-3
+    assert steps1 + s1 == steps2 and s1 > steps1
