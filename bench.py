@@ -84,8 +84,10 @@ def make_workload(name):
 def algorithmic_bytes(c, nc):
     """4 B per cell crossing (totalExt) + (4 nC + 16) B per collision (cumExt, ssa, pfIdx, 2 inverse-table
     entries) + 32 B per absorption (two read-modify-writes) + 24 B per local-estimate contribution (2 forward-table
-    entries + one read-modify-write) + 8 B per photon exit (one read-modify-write)."""
-    return (4 * (c["crossings_photon"] + c["crossings_intensity"]) + (4 * nc + 16) * c["collisions"] + 32 * c["absorptions"]
+    entries + one read-modify-write) + 8 B per photon exit (one read-modify-write).  A cell crossing is the reference
+    algorithm's unit: cells the kernel crosses without gathering them (runs of uniform layers taken in one step) count."""
+    cells = (c["crossings_photon"] + c["crossings_intensity"] + c.get("cells_skipped", 0) + c.get("cells_skipped_intensity", 0))
+    return (4 * cells + (4 * nc + 16) * c["collisions"] + 32 * c["absorptions"]
             + 24 * c["contributions"] + 8 * (c["exits_top"] + c["surface_hits"]))
 
 
@@ -563,7 +565,8 @@ def main():
     launches = max(trace_launches, 1)
     kernel_s = trace_ms / launches * 1e-3
     achieved = abytes / launches / kernel_s / 1e9
-    crossings = counters["crossings_photon"] + counters["crossings_intensity"]
+    crossings = counters["crossings_photon"] + counters["crossings_intensity"]  # DDA steps = gathers issued
+    cells_crossed = crossings + counters.get("cells_skipped", 0) + counters.get("cells_skipped_intensity", 0)
     ncell = I.nx * I.ny * I.nz
     nzc = be.get_layout(I.handle, 0)
     gather_field_bytes = 4 * I.nx * I.ny * (nzc if nzc > 0 else I.nz)
@@ -608,7 +611,7 @@ def main():
     roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_source, "peak_source": peak_source,
                 "kernel": "k_transport", "kernel_ms_per_launch": trace_ms / launches, "kernel_share_of_step": trace_ms / max(sum(step_ms), 1e-9),
-                "algorithmic_bytes_per_launch": abytes / launches, "cell_crossings_per_s": crossings / (trace_ms * 1e-3),
+                "algorithmic_bytes_per_launch": abytes / launches, "cell_crossings_per_s": cells_crossed / (trace_ms * 1e-3), "gathers_issued_per_s": crossings / (trace_ms * 1e-3),
                 "bytes_per_crossing_model": "4 B/crossing + (4nC+16) B/collision + 32 B/absorption + 24 B/contribution + 8 B/exit",
                 "gather_field_bytes": gather_field_bytes, "layers_stored_in_3d": nzc if nzc > 0 else I.nz,
                 "measured_ceilings": {"gathers_per_s": meas, "hbm_copy_gbs": hbm_peak,

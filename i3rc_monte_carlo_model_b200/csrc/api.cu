@@ -274,9 +274,10 @@ int build_gather_field(i3rc_integrator* h) {
       }
     }
     const int nzc = (int)layers.size();
-    // Worth it when at least a quarter of the layers is uniform and either the field does not stay in L2 (the 3-D array
-    // shrinks) or the grid is regular (rays cross runs of uniform layers in one step, Problem::zslab)
-    const bool big = ncell * sizeof(float) > ((size_t)48 << 20) || h->splitLayers == 2 || (h->xyRegular && h->zRegular && h->slabJump);
+    // Worth it for a field that does not stay in L2 and of which at least a quarter of the layers is uniform.  (On small
+    // fields the layer table's extra dependent load costs more than the slab crossings of Problem::zslab save: LES
+    // 128x128x64 5.43e7 -> 4.35e7 photons/s, radar 1.93e8 -> 1.32e8, profiles/r02_ab_uniform_slabs.txt.)
+    const bool big = ncell * sizeof(float) > ((size_t)48 << 20) || h->splitLayers == 2;
     if (ncol > 1 && nzc > 0 && nzc * 4 <= nz * 3 && h->splitLayers && big) {
       int* d_layers = nullptr;
       CUDA_OK(h, upload(&d_layers, layers.data(), layers.size(), h->stream));
@@ -732,9 +733,9 @@ int launch_transport(i3rc_integrator* h, const Problem& p) {
     return launch_transport_t<128, false, false, true, 5, 16, 64, 64, true>(h, p);
   }
   if (p.nzc) {  // only the horizontally varying layers are stored (large fields): the gathers look the layer up first
-    if (reg && fast)  // (6 resident blocks: 512x512x256 3.19e7 photons/s against 2.85e7 with 5, profiles/r02_ab_tuning_grid.txt)
-      return h->residentBlocks == 5 ? launch_transport_t<128, true, true, true, 5, 16, 64, 64>(h, p)
-                                    : launch_transport_t<128, true, true, true, 6, 16, 64, 64>(h, p);
+    if (reg && fast)  // (5 resident blocks: 512x512x256 with slab crossings 3.86e7 photons/s against 3.63e7 with 6)
+      return h->residentBlocks == 6 ? launch_transport_t<128, true, true, true, 6, 16, 64, 64>(h, p)
+                                    : launch_transport_t<128, true, true, true, 5, 16, 64, 64>(h, p);
     if (reg) return launch_transport_t<128, true, false, true, 5, 16, 64, 64>(h, p);
     return launch_transport_t<128, false, false, true, 5, 16, 64, 64>(h, p);
   }
