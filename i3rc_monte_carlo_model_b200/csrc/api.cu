@@ -137,6 +137,7 @@ struct i3rc_integrator {
   // tuning
   int blockSize = 128, blocksPerSM = 0, residentBlocks = 0, poolShape = 0, minRunning = 16, padSmem = 0, kSteps = 16;
   int eventThreshold = 16;
+  int stageMaxColumns = 8;  // tallies are staged in shared memory for domains of at most this many columns
   int stageTallies = 1536;  // floats of shared memory per warp for staged tallies (few-column domains); 0 = never
   int splitLayers = 1;  // (0 never, 1 large fields, 2 always) store only the horizontally varying layers of totalExt in 3-D when that pays (Problem::zlut)
   // nccl
@@ -561,7 +562,9 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
     const size_t ncol = (size_t)h->nx * h->ny, ncell = ncol * h->nz;
     const size_t budget = (size_t)h->stageTallies;  // floats per warp (0 switches the staging off)
     const size_t nInt = p.computeIntensity ? ncol * (size_t)p.nDir : 0;
-    if (3 * ncol + nInt <= budget) {
+    // (only a handful of columns: with 32 columns -- the step cloud -- plain global atomics are already the faster way,
+    //  2.96e8 against 2.22e8 photons/s staged, profiles/r02_ab_staged_tallies_step_cloud.txt)
+    if (3 * ncol + nInt <= budget && ncol <= (size_t)h->stageMaxColumns) {
       p.tsmOff[TAL_UP] = 0;
       p.tsmOff[TAL_DOWN] = (int)ncol;
       p.tsmOff[TAL_ABS] = (int)(2 * ncol);
@@ -727,10 +730,16 @@ int launch_transport(i3rc_integrator* h, const Problem& p) {
   const bool fast = p.useRayTracing && p.src.kind != 5 && p.src.kind != 6 && !p.useSurfaceBDRF && !p.useHybrid && !p.limitContrib &&
                     !p.trackByComponent;
   if (p.tsmN > 0) {  // a domain of a few columns: tallies staged per warp in shared memory (warp_tally, kernels.cuh)
-    // (SPLIT = true: these variants honour a layer table when there is one, see ext_gather)
-    if (reg && fast) return launch_transport_t<128, true, true, true, 5, 16, 64, 64, true>(h, p);
-    if (reg) return launch_transport_t<128, true, false, true, 5, 16, 64, 64, true>(h, p);
-    return launch_transport_t<128, false, false, true, 5, 16, 64, 64, true>(h, p);
+    if (p.nzc) {  // (a layer table, forced by `split_layers` = 2 on a small domain: the variants that honour it)
+      if (reg && fast) return launch_transport_t<128, true, true, true, 5, 16, 64, 64, true>(h, p);
+      if (reg) return launch_transport_t<128, true, false, true, 5, 16, 64, 64, true>(h, p);
+      return launch_transport_t<128, false, false, true, 5, 16, 64, 64, true>(h, p);
+    }
+    if (reg && fast)
+      return h->residentBlocks == 4 ? launch_transport_t<128, true, true, false, 4, 16, 64, 64, true>(h, p)
+                                    : launch_transport_t<128, true, true, false, 5, 16, 64, 64, true>(h, p);
+    if (reg) return launch_transport_t<128, true, false, false, 5, 16, 64, 64, true>(h, p);
+    return launch_transport_t<128, false, false, false, 5, 16, 64, 64, true>(h, p);
   }
   if (p.nzc) {  // only the horizontally varying layers are stored (large fields): the gathers look the layer up first
     if (reg && fast)  // (5 resident blocks: 512x512x256 with slab crossings 3.86e7 photons/s against 3.63e7 with 6)

@@ -629,6 +629,7 @@ def test_tallies_staged_in_shared_memory_equal_global_atomics(cuda):
         for stage in (1536, 0):
             I = make_integrator(cuda, make(), surfaceAlbedo=0.3, intensityMus=[1.0, 0.5, 0.5], intensityPhis=[0.0, 0.0, 180.0], **kw)
             assert cuda.set_tuning(I.handle, b"stage_tallies", stage) == 0
+            assert cuda.set_tuning(I.handle, b"stage_max_columns", 64) == 0  # (the step cloud's 32 columns too)
             assert (cuda.get_layout(I.handle, 1) > 0) == (stage > 0)
             ph = new_PhotonStream(0.5, 0.0, numberOfPhotons=60_000)
             computeRadiativeTransfer(I, new_RandomNumberSequence([10, 1]), ph)
