@@ -137,6 +137,9 @@ struct i3rc_integrator {
   // tuning
   int blockSize = 128, blocksPerSM = 0, residentBlocks = 0, poolShape = 0, minRunning = 16, padSmem = 0, kSteps = 16;
   int eventThreshold = 16;
+  float* d_rep = nullptr;   // copies of the tallies of a domain of few columns (Problem::rep)
+  size_t repN = 0;
+  int replicaColumns = 4096;  // (tuning) tallies are replicated in global memory for domains of at most this many columns
   int stageMaxColumns = 8;  // tallies are staged in shared memory for domains of at most this many columns
   int stageTallies = 1536;  // floats of shared memory per warp for staged tallies (few-column domains); 0 = never
   int splitLayers = 1;  // (0 never, 1 large fields, 2 always) store only the horizontally varying layers of totalExt in 3-D when that pays (Problem::zlut)
@@ -556,6 +559,10 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
   // Tallies staged in shared memory, one private copy per warp, when the domain has so few columns that the whole GPU
   // would otherwise hammer a handful of addresses: fluxes and radiances, and the volume absorption too if it fits.
   p.deriveAbs = 1;
+  p.rep = nullptr;
+  p.repK = 1;
+  p.repStride = 0;
+  for (int& o : p.repOff) o = 0;
   p.tsmN = 0;
   for (int& o : p.tsmOff) o = -1;
   {
@@ -572,6 +579,21 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
       if (nInt) p.tsmOff[TAL_INT] = (int)n, n += nInt;
       if (n + ncell <= budget) p.tsmOff[TAL_VOL] = (int)n, n += ncell;
       p.tsmN = (int)n;
+    }
+    if (p.tsmN == 0 && ncol <= (size_t)h->replicaColumns && !h->trackByComponent && !h->limitContrib) {
+      // copies of the tallies in global memory: up | down | intensity | volume absorption (the absorbed flux is derived)
+      const size_t stride = 2 * ncol + nInt + ncell;
+      int K = 64;
+      while (K > 1 && (size_t)(K - 1) * stride * sizeof(float) > ((size_t)32 << 20)) K /= 2;
+      if (K > 1) {
+        p.repK = K;
+        p.repStride = (int)stride;
+        p.repOff[TAL_UP] = 0;
+        p.repOff[TAL_DOWN] = (int)ncol;
+        p.repOff[TAL_ABS] = 0;  // (unused: deriveAbs)
+        p.repOff[TAL_INT] = (int)(2 * ncol);
+        p.repOff[TAL_VOL] = (int)(2 * ncol + nInt);
+      }
     }
   }
 }
@@ -742,9 +764,11 @@ int launch_transport(i3rc_integrator* h, const Problem& p) {
     return launch_transport_t<128, false, false, false, 5, 16, 64, 64, true>(h, p);
   }
   if (p.nzc) {  // only the horizontally varying layers are stored (large fields): the gathers look the layer up first
-    if (reg && fast)  // (5 resident blocks: 512x512x256 with slab crossings 3.86e7 photons/s against 3.63e7 with 6)
+    if (reg && fast) {  // (5 resident blocks: 512x512x256 with slab crossings 3.86e7 photons/s against 3.63e7 with 6)
+      if (h->poolShape == 4) return launch_transport_t<128, true, true, true, 5, 16, 64, 128>(h, p);  // (experiment: longer task ring)
       return h->residentBlocks == 6 ? launch_transport_t<128, true, true, true, 6, 16, 64, 64>(h, p)
                                     : launch_transport_t<128, true, true, true, 5, 16, 64, 64>(h, p);
+    }
     if (reg) return launch_transport_t<128, true, false, true, 5, 16, 64, 64>(h, p);
     return launch_transport_t<128, false, false, true, 5, 16, 64, 64>(h, p);
   }
@@ -807,6 +831,29 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
   p.key0 = key0;
   p.key1 = key1;
   p.firstPhoton = 0;
+  if (p.repK > 1) {  // (copies are left zeroed by k_fold_replicas; a new or larger buffer is zeroed here)
+    const size_t need = (size_t)(p.repK - 1) * p.repStride;
+    if (h->repN < need) {
+      dfree(h->d_rep);
+      CUDA_OK(h, cudaMalloc(&h->d_rep, sizeof(float) * need));
+      h->repN = need;
+    }
+    CUDA_OK(h, cudaMemsetAsync(h->d_rep, 0, sizeof(float) * need, h->stream));
+    p.rep = h->d_rep;
+  }
+  auto fold_replicas = [&]() {  // after every transport launch: the copies join the tally arrays
+    if (p.repK <= 1) return;
+    const int K1 = p.repK - 1;
+    const size_t st = (size_t)p.repStride;
+    auto one = [&](float* main, size_t n, int off) {
+      if (n) k_fold_replicas<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(main, h->d_rep + off, n, K1, st);
+      h->otherLaunches++;
+    };
+    one(h->d_fluxUp, ncol, p.repOff[TAL_UP]);
+    one(h->d_fluxDown, ncol, p.repOff[TAL_DOWN]);
+    if (nD) one(h->d_intensity, ncol * nD, p.repOff[TAL_INT]);
+    if (h->volAbsDirty) one(h->d_volAbs, ncell, p.repOff[TAL_VOL]);
+  };
   // time the transport kernel with CUDA events on this handle's stream
   if (h->evUsed + 2 > h->ev.size()) {
     cudaEvent_t a, b;
@@ -898,6 +945,7 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
     p.firstPhoton = 0;
     rc = launch_transport(h, p);
     h->traceLaunches++;
+    fold_replicas();
     if (rc == I3RC_SUCCESS && h->volAbsDirty) {
       k_abs_from_volume<<<(unsigned)((ncol + 127) / 128), 128, 0, h->stream>>>(h->nz, ncol, h->d_volAbs, h->d_fluxAbs);
       h->otherLaunches++;
@@ -919,6 +967,7 @@ int run_one_batch(i3rc_integrator* h, const SourceDev& src, uint32_t key0, uint3
     p.firstPhoton = off;
     rc = launch_transport(h, p);
     h->traceLaunches++;
+    fold_replicas();
     if (rc == I3RC_SUCCESS && h->volAbsDirty) {  // absorbed flux per column = the column sums of the volume absorption
       k_abs_from_volume<<<(unsigned)((ncol + 127) / 128), 128, 0, h->stream>>>(h->nz, ncol, h->d_volAbs, h->d_fluxAbs);
       h->otherLaunches++;
@@ -1300,6 +1349,7 @@ void i3rc_finalize_Integrator(i3rc_integrator* h) {
     h->copyStream = nullptr;
   }
   dfree(h->d_next);
+  dfree(h->d_rep);
   dfree(h->d_avail);
   if (h->h_avail) cudaFreeHost(h->h_avail);
   h->h_avail = nullptr;
@@ -2110,7 +2160,7 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->padSmem = value;  // experiment: unused dynamic shared memory (shrinks the L1 share of the SM)
   else if (k == "min_running" && value >= 0 && value <= 32)
     h->minRunning = value;
-  else if (k == "pool_shape" && value >= 0 && value <= 3)
+  else if (k == "pool_shape" && value >= 0 && value <= 4)
     h->poolShape = value;
   else if (k == "event_threshold" && value >= 1 && value <= 32)
     h->eventThreshold = value;
@@ -2130,7 +2180,11 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
   else if (k == "skip_empty" && (value == 0 || value == 1)) {
     h->skipEmpty = value;  // 0: drop the coded copy of the field (takes effect at once); 1: at the next new_Integrator
     if (!value) dfree(h->d_extJ);
-  } else if (k == "stage_tallies" && value >= 0 && value <= 4096)
+  } else if (k == "stage_max_columns" && value >= 0)
+    h->stageMaxColumns = value;
+  else if (k == "replica_columns" && value >= 0)
+    h->replicaColumns = value;  // 0: no copies of the tallies in global memory
+  else if (k == "stage_tallies" && value >= 0 && value <= 4096)
     h->stageTallies = value;  // floats of shared memory per warp for staged tallies; 0 = global atomics only
   else
     return fail(h, "set_tuning: unknown key or bad value");

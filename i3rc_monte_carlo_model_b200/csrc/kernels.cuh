@@ -860,6 +860,17 @@ __global__ void k_abs_from_volume(int nz, size_t ncol, const float* __restrict__
   for (int k = 0; k < nz; k++) s += volAbs[(size_t)k * ncol + col];
   fluxAbs[col] = s;
 }
+// main[i] += sum over the K-1 copies of copy[k][i] (in float64), copies zeroed for the next launch (Problem::rep)
+__global__ void k_fold_replicas(float* __restrict__ main, float* __restrict__ rep, size_t n, int copies, size_t stride) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = (double)main[i];
+  for (int k = 0; k < copies; k++) {
+    s += (double)rep[(size_t)k * stride + i];
+    rep[(size_t)k * stride + i] = 0.0f;
+  }
+  main[i] = (float)s;
+}
 // A batch traced in pieces: acc += tally; the tally restarts from zero, or -- after the last piece -- gets the total
 __global__ void k_fold_tally(float* __restrict__ tally, double* __restrict__ acc, size_t n, int last) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
