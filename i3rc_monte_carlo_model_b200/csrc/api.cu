@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/i3rc_b200.h"
@@ -408,20 +409,37 @@ i3rc_integrator* make_handle() {
 // the value checks of validateOpticalComponent (Code/opticalProperties.f95:966-975) on host arrays; the upper bound of the
 // phase function index is checked against the component's table (maxPf is kept for that)
 const char* validate_optical_arrays(const float* ext, const float* ssa, const int32_t* pf, size_t n, int* maxPf, bool* absorbs) {
-  bool badE = false, badS = false, badP = false, ab = false;
-  int mx = 0;
-  for (size_t i = 0; i < n; i++) {
-    badE |= !(ext[i] >= 0.0f);
-    badS |= !(ssa[i] >= 0.0f && ssa[i] <= 1.0f);
-    badP |= pf[i] < 0;
-    ab |= ext[i] > 0.0f && ssa[i] < 1.0f;
-    mx = pf[i] > mx ? pf[i] : mx;
+  // (a 512x512x256 domain is 1e8 values to look at: a few host threads share them)
+  const int nt = n > ((size_t)1 << 22) ? 8 : 1;
+  std::vector<int> mx(nt, 0), flags(nt, 0);
+  auto scan = [&](int t) {
+    const size_t lo = n * t / nt, hi = n * (t + 1) / nt;
+    bool badE = false, badS = false, badP = false, ab = false;
+    int m = 0;
+    for (size_t i = lo; i < hi; i++) {
+      badE |= !(ext[i] >= 0.0f);
+      badS |= !(ssa[i] >= 0.0f && ssa[i] <= 1.0f);
+      badP |= pf[i] < 0;
+      ab |= ext[i] > 0.0f && ssa[i] < 1.0f;
+      m = pf[i] > m ? pf[i] : m;
+    }
+    mx[t] = m;
+    flags[t] = (badE ? 1 : 0) | (badS ? 2 : 0) | (badP ? 4 : 0) | (ab ? 8 : 0);
+  };
+  if (nt == 1) {
+    scan(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back(scan, t);
+    for (auto& x : th) x.join();
   }
-  *maxPf = mx;
-  *absorbs |= ab;
-  if (badE) return "validateOpticalComponent: extinction must be >= 0.";
-  if (badS) return "validateOpticalComponent: singleScatteringAlbedo must be between 0 and 1";
-  if (badP) return "validateOpticalComponent: phase function index is out of bounds";
+  int all = 0, m = 0;
+  for (int t = 0; t < nt; t++) all |= flags[t], m = std::max(m, mx[t]);
+  *maxPf = m;
+  *absorbs |= (all & 8) != 0;
+  if (all & 1) return "validateOpticalComponent: extinction must be >= 0.";
+  if (all & 2) return "validateOpticalComponent: singleScatteringAlbedo must be between 0 and 1";
+  if (all & 4) return "validateOpticalComponent: phase function index is out of bounds";
   return nullptr;
 }
 
