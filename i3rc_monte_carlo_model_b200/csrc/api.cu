@@ -63,6 +63,9 @@ struct i3rc_integrator {
   float *d_xe = nullptr, *d_ye = nullptr, *d_ze = nullptr;
   float *d_ext = nullptr, *d_cum = nullptr, *d_ssa = nullptr;
   float* d_extRaw = nullptr;  // un-normalised extinction of every component (kept from the first profile swap on)
+  float* d_leLB = nullptr;    // lower bounds of the optical path to the top per radiance direction and cell (Problem::leLB)
+  bool leLBValid = false;     // (rebuilt when the field or the directions change)
+  int leLowerBound = 1;       // (tuning) 0: every local-estimate ray that passes the roulette is traced
   float* d_colTau = nullptr;  // column suffix sums of extinction x layer depth (Problem::colTau)
   int l2Persist = 1;          // persisting L2 access window over a gather field of 32 MB or more (512x512x256: +2.5 %,
                               // profiles/r02_ab_l2_persisting_window_les.txt)
@@ -322,6 +325,7 @@ int build_gather_field(i3rc_integrator* h) {
   CUDA_OK(h, cudaMemcpyAsync(&bits, d_max, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(h, cudaStreamSynchronize(h->stream));
   memcpy(&h->maxExt, &bits, sizeof(float));
+  h->leLBValid = false;
   // column suffix sums for the radiance directions that point straight up (Problem::colTau)
   dfree(h->d_colTau);
   CUDA_OK(h, cudaMalloc(&h->d_colTau, sizeof(float) * (size_t)nx * ny * (nz + 1)));
@@ -543,6 +547,7 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
   p.computeIntensity = h->computeIntensity;
   p.nDir = h->computeIntensity ? h->nDir : 0;
   p.dirs = h->d_dirs;
+  p.leLB = (h->leLowerBound && h->leLBValid && h->computeIntensity && h->useRRIntensity) ? h->d_leLB : nullptr;
   p.colTau = h->d_colTau;
   p.vertMask = 0;
   if (h->verticalShortcut && h->d_colTau)
@@ -1049,6 +1054,21 @@ int prepare_compute(i3rc_integrator* h, const i3rc_photon_source* src, SourceDev
     return fail(h, "computeRadiativeTransfer: maximum cross-section needs a domain with extinction > 0.");
   rc = tabulate(h);
   if (rc != I3RC_SUCCESS) return rc;
+  // lower bounds of the optical path to the top, per radiance direction and cell (Problem::leLB): regular grids, roulette
+  // for intensity; at most 8 GB (twelve slanted directions on 512x512x256 are 3.2 GB)
+  if (!h->leLBValid && h->leLowerBound && h->computeIntensity && h->useRRIntensity && h->xyRegular && h->zRegular && h->nDir > 0) {
+    const size_t ncell = (size_t)h->nx * h->ny * h->nz;
+    if (ncell * h->nDir * sizeof(float) <= ((size_t)8 << 30)) {
+      dfree(h->d_leLB);
+      CUDA_OK(h, cudaMalloc(&h->d_leLB, sizeof(float) * ncell * h->nDir));
+      dim3 g((unsigned)((ncell + 127) / 128), (unsigned)h->nDir);
+      k_le_lower_bound<<<g, 128, 0, h->stream>>>(h->nx, h->ny, h->nz, h->deltaX, h->deltaY, h->deltaZ, h->d_ext, h->d_dirs, h->nDir,
+                                                 h->d_leLB);
+      h->otherLaunches++;
+      CUDA_OK(h, cudaGetLastError());
+      h->leLBValid = true;
+    }
+  }
   return fill_source(h, src, sd);
 }
 
@@ -1334,6 +1354,7 @@ void i3rc_finalize_Integrator(i3rc_integrator* h) {
   dfree(h->d_ze);
   dfree(h->d_ext);
   dfree(h->d_extRaw);
+  dfree(h->d_leLB);
   dfree(h->d_colTau);
   dfree(h->d_extJ);
   dfree(h->d_zslab);
@@ -1495,6 +1516,7 @@ int i3rc_specifyParameters(i3rc_integrator* h, const i3rc_params* p) {
       d[7] = 1.0f / d[6];
     }
     CUDA_OK(h, upload(&h->d_dirs, h->dirs.data(), h->dirs.size(), h->stream));
+    h->leLBValid = false;
     dfree(h->d_intensity);
     dfree(h->d_intByComp);
     CUDA_OK(h, cudaMalloc(&h->d_intensity, sizeof(float) * ncol * h->nDir));
@@ -1743,6 +1765,7 @@ int i3rc_copy_Integrator(const i3rc_integrator* s, i3rc_integrator** out) {
     h->dirs = s->dirs;
     size_t ncol = (size_t)h->nx * h->ny;
     upload(&h->d_dirs, h->dirs.data(), h->dirs.size(), h->stream);
+    h->leLBValid = false;
     cudaMalloc(&h->d_intensity, sizeof(float) * ncol * h->nDir);
     cudaMalloc(&h->d_intByComp, sizeof(float) * ncol * h->nDir * (h->nc + 1));
     cudaMemsetAsync(h->d_intensity, 0, sizeof(float) * ncol * h->nDir, h->stream);
@@ -2193,6 +2216,8 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->tablesInSmem = value;
   else if (k == "debug_zero_strides" && (value == 0 || value == 1))
     h->debugZeroStrides = value;
+  else if (k == "le_lower_bound" && (value == 0 || value == 1))
+    h->leLowerBound = value;  // 0: local-estimate rays are traced even when a lower bound says they cannot contribute
   else if (k == "vertical_shortcut" && (value == 0 || value == 1))
     h->verticalShortcut = value;  // 0: straight-up local-estimate rays are traced like the others
   else if (k == "skip_empty" && (value == 0 || value == 1)) {

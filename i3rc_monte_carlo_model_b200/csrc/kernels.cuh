@@ -782,6 +782,22 @@ __global__ void k_empty_code(const float* __restrict__ ext, const uint8_t* __res
   coded[i] = e;
 }
 
+// leLB[d][cell] for the radiance directions (Problem::leLB): one thread per cell and direction; only cells a ray can start
+// from matter (cells with extinction, and the bottom layer where the surface reflects), the others get 0
+__global__ void k_le_lower_bound(int nx, int ny, int nz, float dx, float dy, float dz, const float* __restrict__ ext,
+                                 const float* __restrict__ dirs, int nDir, float* __restrict__ out) {
+  const size_t ncell = (size_t)nx * ny * nz;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int d = blockIdx.y;
+  if (i >= ncell || d >= nDir) return;
+  const int ix = (int)(i % nx), iy = (int)((i / nx) % ny), iz = (int)(i / ((size_t)nx * ny));
+  float v = 0.0f;
+  if (ext[i] > 0.0f || iz == 0)
+    v = le_lower_bound(ext, nx, ny, nz, dx, dy, dz, dirs[d * DIR_STRIDE], dirs[d * DIR_STRIDE + 1], dirs[d * DIR_STRIDE + 2], ix, iy,
+                       iz, LE_LB_LAYERS, 40.0f);
+  out[(size_t)d * ncell + i] = v;
+}
+
 // colTau[k][col] = sum over layers j >= k of totalExt[j][col] * (ze[j+1] - ze[j]), k = 0 .. nz (Problem::colTau)
 __global__ void k_column_suffix(int nz, size_t ncol, const float* __restrict__ ext, const float* __restrict__ ze,
                                 float* __restrict__ S) {

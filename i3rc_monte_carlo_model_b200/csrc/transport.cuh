@@ -142,6 +142,12 @@ struct Problem {
   // layer depth, colTau[k][iy][ix] = sum over layers >= k (k = 0 .. nz), instead of being traced (make_le_task).
   const float* colTau;
   uint32_t vertMask;  // bit d: direction d is (0, 0, 1)
+  // Russian roulette for intensity: a local-estimate ray contributes only if it reaches the top within an optical-path
+  // budget that is known BEFORE it is traced (MCRT:1554-1559: tauFree; :1566-1587: the first-stage limit + tauFree).
+  // leLB[d][iz][iy][ix] is a LOWER BOUND of the optical path to the top along direction d from anywhere in the cell
+  // (le_lower_bound below; regular grids): when it exceeds the budget the ray is known to contribute nothing and is
+  // not traced.  Null: unused.
+  const float* leLB;
   const float* dirs;  // [nDir][DIR_STRIDE]: d.x d.y d.z 1/|d.x| 1/|d.y| 1/|d.z| 4*pi*|mu| 1/(4*pi*|mu|)
   int useRayTracing, useRussianRoulette, useRRIntensity, useHybrid, numOrdersOrig, limitContrib, useSurfaceBDRF;
   int trackByComponent;
@@ -262,6 +268,41 @@ I3RC_HD float ext_gather(const P& p, int idx, int iz) {
 }
 template <class P>
 I3RC_HD float ext_at(const P& p, int ix, int iy, int iz) { return ext_gather(p, ext_index(p, ix, iy, iz), iz); }
+
+// ---- a lower bound of the optical path from a cell to the top along a direction -------------------------------------
+// Regular grid, direction (ux, uy, uz) with uz > 0.  A ray that starts anywhere in cell (ix, iy, iz) crosses every layer
+// above completely; in layer iz + m it lies, horizontally, within x0 + tx * [(m-1) dz, (m+1) dz] with x0 in [0, dx) (and
+// likewise in y), tx = ux / uz.  Its path length in that layer is dz / uz, so the layer adds at least dz / uz times the
+// smallest extinction among the cells of that footprint.  Summed over at most nLayers layers (a truncated sum is still a
+// lower bound) and stopped once it exceeds `enough`.  ext is indexed [iz][iy][ix] (x fastest), periodic in x and y.
+constexpr int LE_LB_LAYERS = 24;
+I3RC_HD float le_lower_bound(const float* ext, int nx, int ny, int nz, float dx, float dy, float dz, float ux, float uy,
+                             float uz, int ix, int iy, int iz, int nLayers, float enough) {
+  if (!(uz > 0.0f)) return INFINITY;  // (the roulette branches only see rays that leave through the top, quirk Q4)
+  const float tx = ux / uz, ty = uy / uz, step = dz / uz;
+  float acc = 0.0f;
+  for (int m = 1; m <= nLayers && iz + m < nz && acc <= enough; m++) {
+    const float ax = tx * dz * (float)(m - 1), bx = tx * dz * (float)(m + 1);
+    const float ay = ty * dz * (float)(m - 1), by = ty * dz * (float)(m + 1);
+    const int cx0 = (int)floorf(fminf(ax, bx) / dx - 1e-3f), cx1 = (int)floorf(fmaxf(ax, bx) / dx + 1.0f + 1e-3f);
+    const int cy0 = (int)floorf(fminf(ay, by) / dy - 1e-3f), cy1 = (int)floorf(fmaxf(ay, by) / dy + 1.0f + 1e-3f);
+    float lo = INFINITY;
+    if (cx1 - cx0 + 1 >= nx || cy1 - cy0 + 1 >= ny) {
+      lo = 0.0f;  // (a footprint as wide as the domain: no statement)
+    } else {
+      const float* layer = ext + (size_t)(iz + m) * nx * ny;
+      for (int cy = cy0; cy <= cy1; cy++) {
+        const int jy = ((iy + cy) % ny + ny) % ny;
+        for (int cx = cx0; cx <= cx1; cx++) {
+          const int jx = ((ix + cx) % nx + nx) % nx;
+          lo = fminf(lo, I3RC_LDG(layer + (size_t)jy * nx + jx));
+        }
+      }
+    }
+    acc = fmaf(step, lo, acc);
+  }
+  return acc * (1.0f - 5e-4f) - 1e-6f;  // (float32 sums on both sides: the bound stays below what the ray will accumulate)
+}
 
 // ---- tallies (MCRT:513, 530, 642-649, 574-579, 662-667) ---------------------------------------------------------
 // The physics functions hand their increments to a policy object: TallyNow adds at once (per-lane scheduler, probes, CPU
@@ -1073,6 +1114,12 @@ I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, L
       mode = MODE_LE_BIG1;  // MCRT:1566-1569
       lim = -I3RC_LOG(I3RC_FDIV(p.zetaMin, fmaxf(F_TINY, F_PI * phat)));
     }
+  }
+  if (p.leLB && mode != MODE_LE_PLAIN && !((p.vertMask >> d) & 1u)) {
+    // the budget the ray has for reaching the top, against the least it will need from this cell
+    const float budget = mode == MODE_LE_SMALL ? lim : lim + tauFree;
+    const size_t cell = ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx;
+    if (I3RC_LDG(p.leLB + (size_t)d * ((size_t)p.nx * p.ny * p.nz) + cell) > budget) return 0;
   }
   if ((p.vertMask >> d) & 1u) {
     // Straight up: the ray never leaves its column.  Same estimator, same deviates, no tracing: the optical path to the

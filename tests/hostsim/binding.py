@@ -57,6 +57,7 @@ def lib():
     L.hostsim_trace_rays_slab.argtypes = [C.POINTER(Args), C.c_int, C.c_int, fp, fp, fp, fp, fp, ip, C.POINTER(C.c_ulonglong)]
     L.hostsim_set_jump.argtypes = [C.c_int]
     L.hostsim_set_vertical.argtypes = [C.c_int]
+    L.hostsim_set_lower_bound.argtypes = [C.c_int]
     return L
 
 
@@ -220,6 +221,10 @@ class HostSim:
         self.L.hostsim_trace_rays(C.byref(a), n, _abi.fptr(pos), _abi.fptr(direction), _abi.fptr(lim), _abi.fptr(tau),
                                   _abi.fptr(pout), _abi.iptr(idx))
         return tau, pout, idx
+
+    def set_lower_bound(self, on):
+        """Local-estimate rays whose lower bound of the optical path to the top exceeds their roulette budget are not traced."""
+        self.L.hostsim_set_lower_bound(int(on))
 
     def set_vertical(self, on):
         """Radiance directions that point straight up are integrated from column suffix sums (Problem::colTau)."""

@@ -114,6 +114,23 @@ static void fill(const HostSimArgs* a, Problem& p, std::vector<TableDesc>& td, s
 // Empty-space codes on the CPU (what k_empty_init / k_empty_grow / k_empty_code do on the device), for a field in any
 // layout given by its strides: Chebyshev distance to the nearest cell with extinction, periodic in x and y.
 static int g_jump = 0;
+static int g_lb = 0;  // lower bounds of the optical path to the top (Problem::leLB) built on the CPU like k_le_lower_bound
+static std::vector<float> g_leLB;
+static void lower_bound_setup(Problem& p) {
+  p.leLB = nullptr;
+  if (!g_lb || !p.computeIntensity || !p.useRRIntensity || !(p.xyRegular && p.zRegular)) return;
+  const size_t ncell = (size_t)p.nx * p.ny * p.nz;
+  g_leLB.assign(ncell * p.nDir, 0.0f);
+  for (int d = 0; d < p.nDir; d++)
+    for (size_t i = 0; i < ncell; i++) {
+      const int ix = (int)(i % p.nx), iy = (int)((i / p.nx) % p.ny), iz = (int)(i / ((size_t)p.nx * p.ny));
+      if (p.ext[i] > 0.0f || iz == 0)
+        g_leLB[(size_t)d * ncell + i] = le_lower_bound(p.ext, p.nx, p.ny, p.nz, p.dx, p.dy, p.dz, p.dirs[d * DIR_STRIDE],
+                                                       p.dirs[d * DIR_STRIDE + 1], p.dirs[d * DIR_STRIDE + 2], ix, iy, iz,
+                                                       LE_LB_LAYERS, 40.0f);
+    }
+  p.leLB = g_leLB.data();
+}
 static int g_vertical = 0;  // straight-up radiance directions from column suffix sums (Problem::colTau) instead of traced
 static std::vector<float> g_colTau;
 static void vertical_setup(Problem& p) {
@@ -192,6 +209,7 @@ int hostsim_run(const HostSimArgs* a) {
   std::vector<float> dirs;
   fill(a, p, td, dirs);
   vertical_setup(p);
+  lower_bound_setup(p);
   // the same specialisation rule as the product's launcher (api.cu)
   if (p.xyRegular && p.zRegular && g_jump && p.useRayTracing) run_lanes<true, true>(a, p);
   else if (p.xyRegular && p.zRegular) run_lanes<true>(a, p);
@@ -201,6 +219,7 @@ int hostsim_run(const HostSimArgs* a) {
 
 void hostsim_set_jump(int on) { g_jump = on; }
 void hostsim_set_vertical(int on) { g_vertical = on; }
+void hostsim_set_lower_bound(int on) { g_lb = on; }
 }  // extern "C"
 
 template <class P>

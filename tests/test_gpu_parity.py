@@ -784,3 +784,30 @@ def test_uniform_slabs_crossed_in_one_go_change_nothing_but_the_number_of_steps(
         assert abs(ca[k] - cb[k]) <= 3e-4 * cb[k] + 2, k
     for k in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed", "meanIntensity"):
         assert np.allclose(a[k], b[k], rtol=3e-4), k
+
+
+def test_rays_that_cannot_contribute_are_not_traced_on_the_device(cuda):
+    """The lower bound of the optical path to the top (Problem::leLB) on the device: with and without it the same photons
+    give the same tallies (float32 summation order aside) and the same number of contributions; only the local-estimate
+    crossings fall.  Landsat cloud with the bench.py parameters, and a two-component field with five directions (one of
+    them downward: under roulette it can never contribute, quirk Q4)."""
+    cases = [(fields.landsat_cloud(1.0, nLegendreCoefficients=32),
+              dict(surfaceAlbedo=0.0, intensityMus=[1.0, 0.5, 0.5], intensityPhis=[0.0, 0.0, 180.0], useRussianRouletteForIntensity=True,
+                   zetaMin=0.3), dict(solarMu=0.5, solarAzimuth=0.0)),
+             (fields.synthetic_les(nx=24, ny=16, nz=32, n_entries=3, seed=7, nLegendreCoefficients=16),
+              dict(surfaceAlbedo=0.2, intensityMus=[1.0, 0.5, 0.5, 0.8, -0.6], intensityPhis=[0.0, 0.0, 180.0, 130.0, 20.0],
+                   useRussianRouletteForIntensity=True, zetaMin=0.3), dict(solarMu=0.5, solarAzimuth=30.0))]
+    for d, kw, src in cases:
+        res = []
+        for lb in (1, 0):
+            I = make_integrator(cuda, d, **kw)
+            assert cuda.set_tuning(I.handle, b"le_lower_bound", lb) == 0
+            computeRadiativeTransfer(I, new_RandomNumberSequence([10, 6]), new_PhotonStream(numberOfPhotons=400_000, **src))
+            res.append((reportResults(I, "meanIntensity", "intensity", "fluxUp", "meanFluxUp"), getCounters(I)))
+        (a, ca), (b, cb) = res
+        for k in ("crossings_photon", "collisions", "contributions", "rng_draws", "exits_top", "surface_hits"):
+            assert ca[k] == cb[k], k
+        assert ca["crossings_intensity"] < 0.85 * cb["crossings_intensity"]
+        assert np.allclose(a["meanIntensity"], b["meanIntensity"], rtol=1e-5)
+        assert np.allclose(a["intensity"], b["intensity"], rtol=2e-3, atol=1e-6)
+        assert np.array_equal(a["fluxUp"] > 0, b["fluxUp"] > 0) and np.allclose(a["fluxUp"], b["fluxUp"], rtol=1e-4, atol=1e-7)

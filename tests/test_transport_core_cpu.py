@@ -222,3 +222,30 @@ def test_uniform_slabs_crossed_in_one_go_along_fixed_rays(oracle):
     assert np.max(np.abs(t0 - t1) / np.maximum(np.abs(t0), 1e-3)) < 1e-5
     assert np.max(np.abs(p0 - p1)) < 5e-3
     assert steps1 + s1 == steps2 and s1 > steps1
+
+
+def test_rays_that_cannot_contribute_are_not_traced_and_nothing_changes(oracle):
+    """Russian roulette for intensity: a local-estimate ray contributes only if it reaches the top within a budget known
+    before it is traced; a per-cell, per-direction LOWER bound of the optical path to the top (transport.cuh,
+    le_lower_bound) lets the kernel drop rays that cannot.  Dropped rays would have contributed exactly nothing: every
+    tally is bit-identical, every counter but the local-estimate crossings is the same."""
+    d = fields.synthetic_les(nx=24, ny=16, nz=32, n_entries=3, seed=7, nLegendreCoefficients=16)
+    kw = dict(surfaceAlbedo=0.2, intensityMus=[1.0, 0.5, 0.5, 0.8, -0.6], intensityPhis=[0.0, 0.0, 180.0, 130.0, 20.0],
+              useRussianRouletteForIntensity=True, zetaMin=0.3)
+    I = make_integrator(oracle, d, **kw)
+    oracle.tabulate(I.handle)
+    hs = HostSim(d, I, getTable)
+    res = []
+    try:
+        for lb in (0, 1):
+            hs.set_lower_bound(lb)
+            res.append(hs.run(new_PhotonStream(0.5, 30.0, numberOfPhotons=6000), (10, 1), **kw))
+    finally:
+        hs.set_lower_bound(0)
+    a, b = res
+    for k in ("intensity", "fluxUp", "fluxDown", "fluxAbsorbed", "volumeAbsorption"):
+        assert np.array_equal(a[k], b[k]), k
+    ca, cb = a["counters"], b["counters"]
+    for k in ("crossings_photon", "collisions", "contributions", "rng_draws", "exits_top", "surface_hits", "absorptions"):
+        assert ca[k] == cb[k], k
+    assert cb["crossings_intensity"] < 0.85 * ca["crossings_intensity"]
