@@ -548,6 +548,7 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
   p.nDir = h->computeIntensity ? h->nDir : 0;
   p.dirs = h->d_dirs;
   p.leLB = (h->leLowerBound && h->leLBValid && h->computeIntensity && h->useRRIntensity) ? h->d_leLB : nullptr;
+  p.leLBBins = 1;
   p.colTau = h->d_colTau;
   p.vertMask = 0;
   if (h->verticalShortcut && h->d_colTau)
@@ -1062,8 +1063,10 @@ int prepare_compute(i3rc_integrator* h, const i3rc_photon_source* src, SourceDev
       dfree(h->d_leLB);
       CUDA_OK(h, cudaMalloc(&h->d_leLB, sizeof(float) * ncell * h->nDir));
       dim3 g((unsigned)((ncell + 127) / 128), (unsigned)h->nDir);
+      // (the full depth of the domain where that is cheap: 2 M cells x 3 directions take ~10 ms; LE_LB_LAYERS layers otherwise)
+      const int nLayers = ncell * h->nDir <= ((size_t)64 << 20) ? h->nz : LE_LB_LAYERS;
       k_le_lower_bound<<<g, 128, 0, h->stream>>>(h->nx, h->ny, h->nz, h->deltaX, h->deltaY, h->deltaZ, h->d_ext, h->d_dirs, h->nDir,
-                                                 h->d_leLB);
+                                                 nLayers, h->d_leLB);
       h->otherLaunches++;
       CUDA_OK(h, cudaGetLastError());
       h->leLBValid = true;

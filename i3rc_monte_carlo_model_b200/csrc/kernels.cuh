@@ -785,7 +785,7 @@ __global__ void k_empty_code(const float* __restrict__ ext, const uint8_t* __res
 // leLB[d][cell] for the radiance directions (Problem::leLB): one thread per cell and direction; only cells a ray can start
 // from matter (cells with extinction, and the bottom layer where the surface reflects), the others get 0
 __global__ void k_le_lower_bound(int nx, int ny, int nz, float dx, float dy, float dz, const float* __restrict__ ext,
-                                 const float* __restrict__ dirs, int nDir, float* __restrict__ out) {
+                                 const float* __restrict__ dirs, int nDir, int nLayers, float* __restrict__ out) {
   const size_t ncell = (size_t)nx * ny * nz;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int d = blockIdx.y;
@@ -794,7 +794,7 @@ __global__ void k_le_lower_bound(int nx, int ny, int nz, float dx, float dy, flo
   float v = 0.0f;
   if (ext[i] > 0.0f || iz == 0)
     v = le_lower_bound(ext, nx, ny, nz, dx, dy, dz, dirs[d * DIR_STRIDE], dirs[d * DIR_STRIDE + 1], dirs[d * DIR_STRIDE + 2], ix, iy,
-                       iz, LE_LB_LAYERS, 40.0f);
+                       iz, nLayers, LE_LB_ENOUGH);
   out[(size_t)d * ncell + i] = v;
 }
 

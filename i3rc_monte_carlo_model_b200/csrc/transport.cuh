@@ -146,8 +146,10 @@ struct Problem {
   // budget that is known BEFORE it is traced (MCRT:1554-1559: tauFree; :1566-1587: the first-stage limit + tauFree).
   // leLB[d][iz][iy][ix] is a LOWER BOUND of the optical path to the top along direction d from anywhere in the cell
   // (le_lower_bound below; regular grids): when it exceeds the budget the ray is known to contribute nothing and is
-  // not traced.  Null: unused.
+  // not traced.  Null: unused.  leLBBins = 8: one bound per octant of the cell the ray starts in, [d][octant][cell], octant
+  // = (fx >= 1/2) + 2 (fy >= 1/2) + 4 (fz >= 1/2); 1: one bound per cell.
   const float* leLB;
+  int leLBBins;
   const float* dirs;  // [nDir][DIR_STRIDE]: d.x d.y d.z 1/|d.x| 1/|d.y| 1/|d.z| 4*pi*|mu| 1/(4*pi*|mu|)
   int useRayTracing, useRussianRoulette, useRRIntensity, useHybrid, numOrdersOrig, limitContrib, useSurfaceBDRF;
   int trackByComponent;
@@ -275,17 +277,22 @@ I3RC_HD float ext_at(const P& p, int ix, int iy, int iz) { return ext_gather(p, 
 // likewise in y), tx = ux / uz.  Its path length in that layer is dz / uz, so the layer adds at least dz / uz times the
 // smallest extinction among the cells of that footprint.  Summed over at most nLayers layers (a truncated sum is still a
 // lower bound) and stopped once it exceeds `enough`.  ext is indexed [iz][iy][ix] (x fastest), periodic in x and y.
-constexpr int LE_LB_LAYERS = 24;
+constexpr int LE_LB_LAYERS = 32;       // layers summed on domains too large for the full depth
+constexpr float LE_LB_ENOUGH = 20.0f;  // no roulette budget is that large (tauFree = -log(deviate), first-stage limit < 5)
+// The start point may be confined to a sub-box of the cell, [fx0, fx1] x [fy0, fy1] x [fz0, fz1] in fractions of the cell
+// (Problem::leLB keeps one bound per octant of the cell: half the uncertainty of the start point, narrower footprints).
 I3RC_HD float le_lower_bound(const float* ext, int nx, int ny, int nz, float dx, float dy, float dz, float ux, float uy,
-                             float uz, int ix, int iy, int iz, int nLayers, float enough) {
+                             float uz, int ix, int iy, int iz, int nLayers, float enough, float fx0 = 0.0f, float fx1 = 1.0f,
+                             float fy0 = 0.0f, float fy1 = 1.0f, float fz0 = 0.0f, float fz1 = 1.0f) {
   if (!(uz > 0.0f)) return INFINITY;  // (the roulette branches only see rays that leave through the top, quirk Q4)
   const float tx = ux / uz, ty = uy / uz, step = dz / uz;
   float acc = 0.0f;
   for (int m = 1; m <= nLayers && iz + m < nz && acc <= enough; m++) {
-    const float ax = tx * dz * (float)(m - 1), bx = tx * dz * (float)(m + 1);
-    const float ay = ty * dz * (float)(m - 1), by = ty * dz * (float)(m + 1);
-    const int cx0 = (int)floorf(fminf(ax, bx) / dx - 1e-3f), cx1 = (int)floorf(fmaxf(ax, bx) / dx + 1.0f + 1e-3f);
-    const int cy0 = (int)floorf(fminf(ay, by) / dy - 1e-3f), cy1 = (int)floorf(fmaxf(ay, by) / dy + 1.0f + 1e-3f);
+    // height above the start point while the ray is in layer iz + m: between (m - fz1) dz and (m + 1 - fz0) dz
+    const float h0 = dz * ((float)m - fz1), h1 = dz * ((float)(m + 1) - fz0);
+    const float ax = tx * h0, bx = tx * h1, ay = ty * h0, by = ty * h1;
+    const int cx0 = (int)floorf(fminf(ax, bx) / dx + fx0 - 1e-3f), cx1 = (int)floorf(fmaxf(ax, bx) / dx + fx1 + 1e-3f);
+    const int cy0 = (int)floorf(fminf(ay, by) / dy + fy0 - 1e-3f), cy1 = (int)floorf(fmaxf(ay, by) / dy + fy1 + 1e-3f);
     float lo = INFINITY;
     if (cx1 - cx0 + 1 >= nx || cy1 - cy0 + 1 >= ny) {
       lo = 0.0f;  // (a footprint as wide as the domain: no statement)
@@ -1118,8 +1125,9 @@ I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, L
   if (p.leLB && mode != MODE_LE_PLAIN && !((p.vertMask >> d) & 1u)) {
     // the budget the ray has for reaching the top, against the least it will need from this cell
     const float budget = mode == MODE_LE_SMALL ? lim : lim + tauFree;
-    const size_t cell = ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx;
-    if (I3RC_LDG(p.leLB + (size_t)d * ((size_t)p.nx * p.ny * p.nz) + cell) > budget) return 0;
+    const size_t ncell = (size_t)p.nx * p.ny * p.nz, cell = ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx;
+    const int oct = p.leLBBins == 8 ? (L.fx >= 0.5f ? 1 : 0) + (L.fy >= 0.5f ? 2 : 0) + (L.fz >= 0.5f ? 4 : 0) : 0;
+    if (I3RC_LDG(p.leLB + ((size_t)d * p.leLBBins + oct) * ncell + cell) > budget) return 0;
   }
   if ((p.vertMask >> d) & 1u) {
     // Straight up: the ray never leaves its column.  Same estimator, same deviates, no tracing: the optical path to the

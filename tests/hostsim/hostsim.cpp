@@ -120,16 +120,21 @@ static void lower_bound_setup(Problem& p) {
   p.leLB = nullptr;
   if (!g_lb || !p.computeIntensity || !p.useRRIntensity || !(p.xyRegular && p.zRegular)) return;
   const size_t ncell = (size_t)p.nx * p.ny * p.nz;
-  g_leLB.assign(ncell * p.nDir, 0.0f);
+  const int bins = g_lb == 8 ? 8 : 1;
+  g_leLB.assign(ncell * p.nDir * bins, 0.0f);
   for (int d = 0; d < p.nDir; d++)
-    for (size_t i = 0; i < ncell; i++) {
-      const int ix = (int)(i % p.nx), iy = (int)((i / p.nx) % p.ny), iz = (int)(i / ((size_t)p.nx * p.ny));
-      if (p.ext[i] > 0.0f || iz == 0)
-        g_leLB[(size_t)d * ncell + i] = le_lower_bound(p.ext, p.nx, p.ny, p.nz, p.dx, p.dy, p.dz, p.dirs[d * DIR_STRIDE],
-                                                       p.dirs[d * DIR_STRIDE + 1], p.dirs[d * DIR_STRIDE + 2], ix, iy, iz,
-                                                       LE_LB_LAYERS, 40.0f);
-    }
+    for (int o = 0; o < bins; o++)
+      for (size_t i = 0; i < ncell; i++) {
+        const int ix = (int)(i % p.nx), iy = (int)((i / p.nx) % p.ny), iz = (int)(i / ((size_t)p.nx * p.ny));
+        if (!(p.ext[i] > 0.0f || iz == 0)) continue;
+        const float x0 = bins == 8 ? 0.5f * (o & 1) : 0.0f, y0 = bins == 8 ? 0.5f * ((o >> 1) & 1) : 0.0f,
+                    z0 = bins == 8 ? 0.5f * ((o >> 2) & 1) : 0.0f, w = bins == 8 ? 0.5f : 1.0f;
+        g_leLB[((size_t)d * bins + o) * ncell + i] =
+            le_lower_bound(p.ext, p.nx, p.ny, p.nz, p.dx, p.dy, p.dz, p.dirs[d * DIR_STRIDE], p.dirs[d * DIR_STRIDE + 1],
+                           p.dirs[d * DIR_STRIDE + 2], ix, iy, iz, p.nz, LE_LB_ENOUGH, x0, x0 + w, y0, y0 + w, z0, z0 + w);
+      }
   p.leLB = g_leLB.data();
+  p.leLBBins = bins;
 }
 static int g_vertical = 0;  // straight-up radiance directions from column suffix sums (Problem::colTau) instead of traced
 static std::vector<float> g_colTau;
