@@ -63,6 +63,8 @@ struct i3rc_integrator {
   float *d_xe = nullptr, *d_ye = nullptr, *d_ze = nullptr;
   float *d_ext = nullptr, *d_cum = nullptr, *d_ssa = nullptr;
   float* d_extRaw = nullptr;  // un-normalised extinction of every component (kept from the first profile swap on)
+  float* d_leUB = nullptr;    // upper bounds (domains small enough for the full depth), Problem::leUB
+  int leUpperBound = 1;       // (tuning) 0: rays that are certain to survive the roulette are traced all the same
   float* d_leLB = nullptr;    // lower bounds of the optical path to the top per radiance direction and cell (Problem::leLB)
   bool leLBValid = false;     // (rebuilt when the field or the directions change)
   int leLowerBound = 1;       // (tuning) 0: every local-estimate ray that passes the roulette is traced
@@ -549,6 +551,7 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
   p.dirs = h->d_dirs;
   p.leLB = (h->leLowerBound && h->leLBValid && h->computeIntensity && h->useRRIntensity) ? h->d_leLB : nullptr;
   p.leLBBins = 1;
+  p.leUB = (p.leLB && h->leUpperBound) ? h->d_leUB : nullptr;
   p.colTau = h->d_colTau;
   p.vertMask = 0;
   if (h->verticalShortcut && h->d_colTau)
@@ -1061,12 +1064,15 @@ int prepare_compute(i3rc_integrator* h, const i3rc_photon_source* src, SourceDev
     const size_t ncell = (size_t)h->nx * h->ny * h->nz;
     if (ncell * h->nDir * sizeof(float) <= ((size_t)8 << 30)) {
       dfree(h->d_leLB);
+      dfree(h->d_leUB);
       CUDA_OK(h, cudaMalloc(&h->d_leLB, sizeof(float) * ncell * h->nDir));
       dim3 g((unsigned)((ncell + 127) / 128), (unsigned)h->nDir);
-      // (the full depth of the domain where that is cheap: 2 M cells x 3 directions take ~10 ms; LE_LB_LAYERS layers otherwise)
-      const int nLayers = ncell * h->nDir <= ((size_t)64 << 20) ? h->nz : LE_LB_LAYERS;
-      k_le_lower_bound<<<g, 128, 0, h->stream>>>(h->nx, h->ny, h->nz, h->deltaX, h->deltaY, h->deltaZ, h->d_ext, h->d_dirs, h->nDir,
-                                                 nLayers, h->d_leLB);
+      // (the full depth of the domain where that is cheap: 2 M cells x 3 directions take ~10 ms -- then the upper bound
+      //  exists too --; LE_LB_LAYERS layers otherwise)
+      const bool full = ncell * h->nDir <= ((size_t)64 << 20);
+      if (full) CUDA_OK(h, cudaMalloc(&h->d_leUB, sizeof(float) * ncell * h->nDir));
+      k_le_path_bounds<<<g, 128, 0, h->stream>>>(h->nx, h->ny, h->nz, h->deltaX, h->deltaY, h->deltaZ, h->d_ext, h->d_dirs, h->nDir,
+                                                 full ? h->nz : LE_LB_LAYERS, h->d_leLB, h->d_leUB);
       h->otherLaunches++;
       CUDA_OK(h, cudaGetLastError());
       h->leLBValid = true;
@@ -1358,6 +1364,7 @@ void i3rc_finalize_Integrator(i3rc_integrator* h) {
   dfree(h->d_ext);
   dfree(h->d_extRaw);
   dfree(h->d_leLB);
+  dfree(h->d_leUB);
   dfree(h->d_colTau);
   dfree(h->d_extJ);
   dfree(h->d_zslab);
@@ -2219,6 +2226,8 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->tablesInSmem = value;
   else if (k == "debug_zero_strides" && (value == 0 || value == 1))
     h->debugZeroStrides = value;
+  else if (k == "le_upper_bound" && (value == 0 || value == 1))
+    h->leUpperBound = value;  // 0: rays that are certain to survive the roulette are traced all the same
   else if (k == "le_lower_bound" && (value == 0 || value == 1))
     h->leLowerBound = value;  // 0: local-estimate rays are traced even when a lower bound says they cannot contribute
   else if (k == "vertical_shortcut" && (value == 0 || value == 1))

@@ -310,10 +310,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
           const unsigned m = __ballot_sync(full, push);
           if (push) q[(tail + __popc(m & lt)) & (QCAP - 1)] = t;
           tail += __popc(m);
-          if ((p.vertMask >> dcur) & 1u) {  // straight up: worked out on the spot, tallied in the event's own column
+          if (((p.vertMask >> dcur) & 1u) || p.leUB) {  // contributions worked out on the spot (make_le_task returned 2)
             Tally tv;
             if constexpr (TSM) tv.n = 0;
-            if (what == 2) tally_intensity_at(p, E, dcur, E.comp, E.cy * p.nx + E.cx, t.cw, tv);
+            if (what == 2) tally_intensity_at(p, E, dcur, E.comp, (int)(t.xy >> 16) * p.nx + (int)(t.xy & 0xffffu), t.cw, tv);
             if constexpr (TSM) warp_tally<TSM>(p, wt, tv.n > 0, tv.w0, tv.o0, tv.v0);
           }
           dcur++;
@@ -782,20 +782,22 @@ __global__ void k_empty_code(const float* __restrict__ ext, const uint8_t* __res
   coded[i] = e;
 }
 
-// leLB[d][cell] for the radiance directions (Problem::leLB): one thread per cell and direction; only cells a ray can start
+// leLB[d][cell] and leUB[d][cell] for the radiance directions (Problem::leLB, leUB): one thread per cell and direction; only cells a ray can start
 // from matter (cells with extinction, and the bottom layer where the surface reflects), the others get 0
-__global__ void k_le_lower_bound(int nx, int ny, int nz, float dx, float dy, float dz, const float* __restrict__ ext,
-                                 const float* __restrict__ dirs, int nDir, int nLayers, float* __restrict__ out) {
+__global__ void k_le_path_bounds(int nx, int ny, int nz, float dx, float dy, float dz, const float* __restrict__ ext,
+                                 const float* __restrict__ dirs, int nDir, int nLayers, float* __restrict__ lower,
+                                 float* __restrict__ upper) {
   const size_t ncell = (size_t)nx * ny * nz;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int d = blockIdx.y;
   if (i >= ncell || d >= nDir) return;
   const int ix = (int)(i % nx), iy = (int)((i / nx) % ny), iz = (int)(i / ((size_t)nx * ny));
-  float v = 0.0f;
+  float lo = 0.0f, hi = INFINITY;
   if (ext[i] > 0.0f || iz == 0)
-    v = le_lower_bound(ext, nx, ny, nz, dx, dy, dz, dirs[d * DIR_STRIDE], dirs[d * DIR_STRIDE + 1], dirs[d * DIR_STRIDE + 2], ix, iy,
-                       iz, nLayers, LE_LB_ENOUGH);
-  out[(size_t)d * ncell + i] = v;
+    le_path_bounds(ext, nx, ny, nz, dx, dy, dz, dirs[d * DIR_STRIDE], dirs[d * DIR_STRIDE + 1], dirs[d * DIR_STRIDE + 2], ix, iy, iz,
+                   nLayers, LE_LB_ENOUGH, &lo, &hi);
+  lower[(size_t)d * ncell + i] = lo;
+  if (upper) upper[(size_t)d * ncell + i] = hi;
 }
 
 // colTau[k][col] = sum over layers j >= k of totalExt[j][col] * (ze[j+1] - ze[j]), k = 0 .. nz (Problem::colTau)

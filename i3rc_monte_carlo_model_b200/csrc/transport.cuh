@@ -150,6 +150,10 @@ struct Problem {
   // = (fx >= 1/2) + 2 (fy >= 1/2) + 4 (fz >= 1/2); 1: one bound per cell.
   const float* leLB;
   int leLBBins;
+  // ... and leUB[d][cell] an UPPER bound: when even that fits the budget the ray is known to reach the top, and where its
+  // contribution does not depend on the optical path (the roulette's survivors, MCRT:1556, 1584) it is tallied without
+  // tracing, in the column where the straight line leaves the domain.  Null: unused.
+  const float* leUB;
   const float* dirs;  // [nDir][DIR_STRIDE]: d.x d.y d.z 1/|d.x| 1/|d.y| 1/|d.z| 4*pi*|mu| 1/(4*pi*|mu|)
   int useRayTracing, useRussianRoulette, useRRIntensity, useHybrid, numOrdersOrig, limitContrib, useSurfaceBDRF;
   int trackByComponent;
@@ -279,36 +283,52 @@ I3RC_HD float ext_at(const P& p, int ix, int iy, int iz) { return ext_gather(p, 
 // lower bound) and stopped once it exceeds `enough`.  ext is indexed [iz][iy][ix] (x fastest), periodic in x and y.
 constexpr int LE_LB_LAYERS = 32;       // layers summed on domains too large for the full depth
 constexpr float LE_LB_ENOUGH = 20.0f;  // no roulette budget is that large (tauFree = -log(deviate), first-stage limit < 5)
-// The start point may be confined to a sub-box of the cell, [fx0, fx1] x [fy0, fy1] x [fz0, fz1] in fractions of the cell
-// (Problem::leLB keeps one bound per octant of the cell: half the uncertainty of the start point, narrower footprints).
-I3RC_HD float le_lower_bound(const float* ext, int nx, int ny, int nz, float dx, float dy, float dz, float ux, float uy,
-                             float uz, int ix, int iy, int iz, int nLayers, float enough, float fx0 = 0.0f, float fx1 = 1.0f,
-                             float fy0 = 0.0f, float fy1 = 1.0f, float fz0 = 0.0f, float fz1 = 1.0f) {
-  if (!(uz > 0.0f)) return INFINITY;  // (the roulette branches only see rays that leave through the top, quirk Q4)
+// An UPPER bound comes the same way, with the largest extinction of each footprint and with the layer the ray starts in
+// (whose footprint reaches from the start point's own cell to where the ray leaves the layer); it is only valid when
+// every layer up to the top has been summed, so it is INFINITY when the sum was cut short.
+// The start point may be confined to a sub-box of the cell, [fx0, fx1] x [fy0, fy1] x [fz0, fz1] in fractions of the cell.
+I3RC_HD void le_path_bounds(const float* ext, int nx, int ny, int nz, float dx, float dy, float dz, float ux, float uy, float uz,
+                            int ix, int iy, int iz, int nLayers, float enough, float* lower, float* upper, float fx0 = 0.0f,
+                            float fx1 = 1.0f, float fy0 = 0.0f, float fy1 = 1.0f, float fz0 = 0.0f, float fz1 = 1.0f) {
+  *lower = INFINITY;  // (the roulette branches only see rays that leave through the top, quirk Q4)
+  *upper = INFINITY;
+  if (!(uz > 0.0f)) return;
   const float tx = ux / uz, ty = uy / uz, step = dz / uz;
-  float acc = 0.0f;
-  for (int m = 1; m <= nLayers && iz + m < nz && acc <= enough; m++) {
-    // height above the start point while the ray is in layer iz + m: between (m - fz1) dz and (m + 1 - fz0) dz
-    const float h0 = dz * ((float)m - fz1), h1 = dz * ((float)(m + 1) - fz0);
+  float lo = 0.0f, hi = 0.0f;
+  bool whole = true;  // every layer up to the top has been looked at
+  for (int m = 0; iz + m < nz; m++) {
+    if (m > nLayers || lo > enough) {
+      whole = false;
+      break;
+    }
+    // height above the start point while the ray is in layer iz + m: between (m - fz1) dz and (m + 1 - fz0) dz (from 0 in
+    // the layer it starts in)
+    const float h0 = m == 0 ? 0.0f : dz * ((float)m - fz1), h1 = dz * ((float)(m + 1) - fz0);
     const float ax = tx * h0, bx = tx * h1, ay = ty * h0, by = ty * h1;
     const int cx0 = (int)floorf(fminf(ax, bx) / dx + fx0 - 1e-3f), cx1 = (int)floorf(fmaxf(ax, bx) / dx + fx1 + 1e-3f);
     const int cy0 = (int)floorf(fminf(ay, by) / dy + fy0 - 1e-3f), cy1 = (int)floorf(fmaxf(ay, by) / dy + fy1 + 1e-3f);
-    float lo = INFINITY;
+    float mn = INFINITY, mx = 0.0f;
     if (cx1 - cx0 + 1 >= nx || cy1 - cy0 + 1 >= ny) {
-      lo = 0.0f;  // (a footprint as wide as the domain: no statement)
+      mn = 0.0f;  // (a footprint as wide as the domain: no statement)
+      mx = INFINITY;
     } else {
       const float* layer = ext + (size_t)(iz + m) * nx * ny;
       for (int cy = cy0; cy <= cy1; cy++) {
         const int jy = ((iy + cy) % ny + ny) % ny;
         for (int cx = cx0; cx <= cx1; cx++) {
           const int jx = ((ix + cx) % nx + nx) % nx;
-          lo = fminf(lo, I3RC_LDG(layer + (size_t)jy * nx + jx));
+          const float e = I3RC_LDG(layer + (size_t)jy * nx + jx);
+          mn = fminf(mn, e);
+          mx = fmaxf(mx, e);
         }
       }
     }
-    acc = fmaf(step, lo, acc);
+    if (m > 0) lo = fmaf(step, mn, lo);          // (the path in the layer the ray starts in may be arbitrarily short)
+    hi = fmaf(step * (m == 0 ? 1.0f - fz0 : 1.0f), mx, hi);
   }
-  return acc * (1.0f - 5e-4f) - 1e-6f;  // (float32 sums on both sides: the bound stays below what the ray will accumulate)
+  // (float32 sums on both sides: the bounds stay clear of what the ray itself will accumulate)
+  *lower = lo * (1.0f - 5e-4f) - 1e-6f;
+  if (whole) *upper = hi * (1.0f + 5e-4f) + 1e-6f;
 }
 
 // ---- tallies (MCRT:513, 530, 642-649, 574-579, 662-667) ---------------------------------------------------------
@@ -1090,8 +1110,9 @@ struct LeTask {
 
 // Build the local-estimate task towards direction d from the lane's event point (MCRT:1473-1510, 1540-1569); xiTau and
 // xiAcc are the two deviates Iwabuchi's roulette may need.  Returns 0 when the contribution is known to be zero
-// without tracing, 1 when the task has to be traced, 2 when the direction points straight up and the contribution has
-// been worked out on the spot (in t.cw; to be tallied in the event's own column by tally_intensity_at).
+// without tracing, 1 when the task has to be traced, 2 when the contribution has been worked out on the spot (a direction
+// that points straight up, or a ray that is certain to survive the roulette): in t.cw, to be tallied in the column t.xy by
+// tally_intensity_at.
 template <class P>
 I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, LeTask& t) {
   const float* dv = p.dirs + d * DIR_STRIDE;
@@ -1123,11 +1144,25 @@ I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, L
     }
   }
   if (p.leLB && mode != MODE_LE_PLAIN && !((p.vertMask >> d) & 1u)) {
-    // the budget the ray has for reaching the top, against the least it will need from this cell
+    // the budget the ray has for reaching the top, against the least and the most it can need from this cell
     const float budget = mode == MODE_LE_SMALL ? lim : lim + tauFree;
     const size_t ncell = (size_t)p.nx * p.ny * p.nz, cell = ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx;
     const int oct = p.leLBBins == 8 ? (L.fx >= 0.5f ? 1 : 0) + (L.fy >= 0.5f ? 2 : 0) + (L.fz >= 0.5f ? 4 : 0) : 0;
-    if (I3RC_LDG(p.leLB + ((size_t)d * p.leLBBins + oct) * ncell + cell) > budget) return 0;
+    const float lb = I3RC_LDG(p.leLB + ((size_t)d * p.leLBBins + oct) * ncell + cell);
+    if (lb > budget) return 0;
+    if (p.leUB && I3RC_LDG(p.leUB + (size_t)d * ncell + cell) <= budget && (mode == MODE_LE_SMALL || lb > lim)) {
+      // Certain to reach the top, and not within the first stage's limit: the contribution is the survivors' fixed one.
+      // The exit column is where the straight line from the event point meets the top of the domain.
+      const float h = (float)(p.nz - L.cz) - L.fz;  // layers to the top
+      const float gx = (float)L.cx + L.fx + h * I3RC_FDIV(p.dz * I3RC_LDG(dv + 0), p.dx * I3RC_LDG(dv + 2));
+      const float gy = (float)L.cy + L.fy + h * I3RC_FDIV(p.dz * I3RC_LDG(dv + 1), p.dy * I3RC_LDG(dv + 2));
+      int ex = (int)floorf(gx) % p.nx, ey = (int)floorf(gy) % p.ny;
+      if (ex < 0) ex += p.nx;
+      if (ey < 0) ey += p.ny;
+      t.cw = L.w * p.zetaMin * (1.0f / F_PI);
+      t.xy = (uint32_t)ex | ((uint32_t)ey << 16);
+      return 2;
+    }
   }
   if ((p.vertMask >> d) & 1u) {
     // Straight up: the ray never leaves its column.  Same estimator, same deviates, no tracing: the optical path to the
@@ -1145,6 +1180,7 @@ I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, L
     else
       c = tauTop <= lim ? L.w * phat * I3RC_EXP(-tauTop) : (tauTop - lim <= tauFree ? cfix : 0.0f);
     t.cw = c;
+    t.xy = (uint32_t)L.cx | ((uint32_t)L.cy << 16);
     return 2;
   }
   t.xy = (uint32_t)L.cx | ((uint32_t)L.cy << 16);
@@ -1369,7 +1405,7 @@ I3RC_HD void advance_le(const P& p, Lane& L) {
     }
     if (what == 2) {
       TallyNow now;
-      tally_intensity_at(p, L, d, L.comp, L.cy * p.nx + L.cx, t.cw, now);
+      tally_intensity_at(p, L, d, L.comp, (int)(t.xy >> 16) * p.nx + (int)(t.xy & 0xffffu), t.cw, now);
     }
   }
   continue_photon(p, L, L.ev1, L.ev2, L.ev3);

@@ -114,27 +114,26 @@ static void fill(const HostSimArgs* a, Problem& p, std::vector<TableDesc>& td, s
 // Empty-space codes on the CPU (what k_empty_init / k_empty_grow / k_empty_code do on the device), for a field in any
 // layout given by its strides: Chebyshev distance to the nearest cell with extinction, periodic in x and y.
 static int g_jump = 0;
-static int g_lb = 0;  // lower bounds of the optical path to the top (Problem::leLB) built on the CPU like k_le_lower_bound
-static std::vector<float> g_leLB;
+static int g_lb = 0;  // bounds of the optical path to the top (Problem::leLB / leUB) built on the CPU like k_le_path_bounds
+static std::vector<float> g_leLB, g_leUB;   // g_lb: 1 = lower bound only, 2 = lower and upper bound
 static void lower_bound_setup(Problem& p) {
   p.leLB = nullptr;
+  p.leUB = nullptr;
+  p.leLBBins = 1;
   if (!g_lb || !p.computeIntensity || !p.useRRIntensity || !(p.xyRegular && p.zRegular)) return;
   const size_t ncell = (size_t)p.nx * p.ny * p.nz;
-  const int bins = g_lb == 8 ? 8 : 1;
-  g_leLB.assign(ncell * p.nDir * bins, 0.0f);
+  g_leLB.assign(ncell * p.nDir, 0.0f);
+  g_leUB.assign(ncell * p.nDir, INFINITY);
   for (int d = 0; d < p.nDir; d++)
-    for (int o = 0; o < bins; o++)
-      for (size_t i = 0; i < ncell; i++) {
-        const int ix = (int)(i % p.nx), iy = (int)((i / p.nx) % p.ny), iz = (int)(i / ((size_t)p.nx * p.ny));
-        if (!(p.ext[i] > 0.0f || iz == 0)) continue;
-        const float x0 = bins == 8 ? 0.5f * (o & 1) : 0.0f, y0 = bins == 8 ? 0.5f * ((o >> 1) & 1) : 0.0f,
-                    z0 = bins == 8 ? 0.5f * ((o >> 2) & 1) : 0.0f, w = bins == 8 ? 0.5f : 1.0f;
-        g_leLB[((size_t)d * bins + o) * ncell + i] =
-            le_lower_bound(p.ext, p.nx, p.ny, p.nz, p.dx, p.dy, p.dz, p.dirs[d * DIR_STRIDE], p.dirs[d * DIR_STRIDE + 1],
-                           p.dirs[d * DIR_STRIDE + 2], ix, iy, iz, p.nz, LE_LB_ENOUGH, x0, x0 + w, y0, y0 + w, z0, z0 + w);
-      }
+    for (size_t i = 0; i < ncell; i++) {
+      const int ix = (int)(i % p.nx), iy = (int)((i / p.nx) % p.ny), iz = (int)(i / ((size_t)p.nx * p.ny));
+      if (!(p.ext[i] > 0.0f || iz == 0)) continue;
+      le_path_bounds(p.ext, p.nx, p.ny, p.nz, p.dx, p.dy, p.dz, p.dirs[d * DIR_STRIDE], p.dirs[d * DIR_STRIDE + 1],
+                     p.dirs[d * DIR_STRIDE + 2], ix, iy, iz, p.nz, LE_LB_ENOUGH, &g_leLB[(size_t)d * ncell + i],
+                     &g_leUB[(size_t)d * ncell + i]);
+    }
   p.leLB = g_leLB.data();
-  p.leLBBins = bins;
+  if (g_lb == 2) p.leUB = g_leUB.data();
 }
 static int g_vertical = 0;  // straight-up radiance directions from column suffix sums (Problem::colTau) instead of traced
 static std::vector<float> g_colTau;
