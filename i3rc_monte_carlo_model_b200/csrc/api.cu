@@ -63,8 +63,12 @@ struct i3rc_integrator {
   float *d_xe = nullptr, *d_ye = nullptr, *d_ze = nullptr;
   float *d_ext = nullptr, *d_cum = nullptr, *d_ssa = nullptr;
   float* d_extRaw = nullptr;  // un-normalised extinction of every component (kept from the first profile swap on)
+  float maxForward = -1.0f;   // largest value of any forward phase-function table in use (< 0: not known)
   float* d_leUB = nullptr;    // upper bounds (domains small enough for the full depth), Problem::leUB
-  int leUpperBound = 1;       // (tuning) 0: rays that are certain to survive the roulette are traced all the same
+  int leUpperBound = 0;       // (tuning) 1: rays that are certain to survive the roulette are tallied without tracing.  Off:
+                              // measured slower (Landsat 2.44e8 against 2.48e8 photons/s; the extra code in the event
+                              // batch costs more than the 6 % of the steps it saves, profiles/r02_ab_le_bounds.txt)
+  int leEarlyExit = 1;        // (tuning) 0: no test against the largest possible budget before the phase-function lookup
   float* d_leLB = nullptr;    // lower bounds of the optical path to the top per radiance direction and cell (Problem::leLB)
   bool leLBValid = false;     // (rebuilt when the field or the directions change)
   int leLowerBound = 1;       // (tuning) 0: every local-estimate ray that passes the roulette is traced
@@ -99,6 +103,7 @@ struct i3rc_integrator {
   std::vector<DevMatrix> inv, fwd, fwdOrig;
   TableDesc* d_tableDesc = nullptr;
   bool tableDescDirty = true;
+  bool tableDescDirtyForMax = true;  // the forward tables changed since maxForward was taken
   int nDir = 0;
   std::vector<float> dirs;  // [nDir][DIR_STRIDE]
   float* d_dirs = nullptr;
@@ -489,6 +494,7 @@ int tabulate(i3rc_integrator* h) {
       h->inv[c].nEntries = t.nEntries;
       h->otherLaunches += 4;
       h->tableDescDirty = true;
+  h->tableDescDirtyForMax = true;
     }
     if (h->computeIntensity && !(h->fwd[c].d && h->fwd[c].nSteps >= h->minForwardTableSize)) {
       if (t.kind == 0) return fail(h, "tabulatePhaseFunctions: failed on component (no phase function table)");
@@ -507,7 +513,22 @@ int tabulate(i3rc_integrator* h) {
       h->fwd[c].nEntries = h->fwdOrig[c].nEntries = t.nEntries;
       h->otherLaunches += 3;
       h->tableDescDirty = true;
+      h->tableDescDirtyForMax = true;
     }
+  }
+  if (h->computeIntensity && h->tableDescDirtyForMax) {  // the largest forward-table value (for Problem::limMax)
+    float mx = 0.0f;
+    for (int c = 0; c < h->nc; c++) {
+      for (const DevMatrix* m : {&h->fwd[c], &h->fwdOrig[c]}) {
+        if (!m->d) continue;
+        std::vector<float> tmp((size_t)m->nSteps * m->nEntries);
+        CUDA_OK(h, cudaMemcpyAsync(tmp.data(), m->d, sizeof(float) * tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+        for (float v : tmp) mx = std::max(mx, v);
+      }
+    }
+    h->maxForward = mx;
+    h->tableDescDirtyForMax = false;
   }
   return upload_table_desc(h);
 }
@@ -552,6 +573,14 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
   p.leLB = (h->leLowerBound && h->leLBValid && h->computeIntensity && h->useRRIntensity) ? h->d_leLB : nullptr;
   p.leLBBins = 1;
   p.leUB = (p.leLB && h->leUpperBound) ? h->d_leUB : nullptr;
+  p.limMax = -1.0f;
+  if (h->leLowerBound && h->leEarlyExit && h->computeIntensity && h->useRRIntensity && h->maxForward >= 0.0f && h->zetaMin > 0.0f) {
+    // the largest normalised phase function any direction can see: maxForward / (4 pi |mu|) with the smallest |mu|
+    float inv = 0.0f;
+    for (int d = 0; d < h->nDir; d++) inv = std::max(inv, h->dirs[d * DIR_STRIDE + 7]);
+    const float phatMax = h->maxForward * inv;
+    p.limMax = F_PI * phatMax > h->zetaMin ? -logf(h->zetaMin / (F_PI * phatMax)) * (1.0f + 1e-5f) + 1e-5f : 0.0f;
+  }
   p.colTau = h->d_colTau;
   p.vertMask = 0;
   if (h->verticalShortcut && h->d_colTau)
@@ -1349,6 +1378,7 @@ int i3rc_set_phase_table(i3rc_integrator* h, int comp, const i3rc_phase_table* t
   free_matrix(h->fwd[comp]);
   free_matrix(h->fwdOrig[comp]);
   h->tableDescDirty = true;
+  h->tableDescDirtyForMax = true;
   h->message.clear();
   return I3RC_SUCCESS;
 }
@@ -1505,6 +1535,7 @@ int i3rc_specifyParameters(i3rc_integrator* h, const i3rc_params* p) {
       h->hybridWidth = 7.0f;
     for (auto& mtx : h->fwd) free_matrix(mtx);  // MCRT:996-1004: re-tabulate
     h->tableDescDirty = true;
+  h->tableDescDirtyForMax = true;
   }
   if (has(I3RC_P_numOrdersOrigPhaseFunIntenCalcs))
     h->numOrdersOrig = p->numOrdersOrigPhaseFunIntenCalcs >= 0 ? p->numOrdersOrigPhaseFunIntenCalcs : 0;
@@ -1580,6 +1611,7 @@ int i3rc_set_inverse_table(i3rc_integrator* h, int comp, int nSteps, int nEntrie
   h->inv[comp].nEntries = nEntries;
   if (nSteps > h->minInverseTableSize) h->minInverseTableSize = nSteps;
   h->tableDescDirty = true;
+  h->tableDescDirtyForMax = true;
   return I3RC_SUCCESS;
 }
 int i3rc_set_forward_table(i3rc_integrator* h, int comp, int nSteps, int nEntries, const float* tabulated,
@@ -1594,6 +1626,7 @@ int i3rc_set_forward_table(i3rc_integrator* h, int comp, int nSteps, int nEntrie
   h->fwd[comp].nEntries = h->fwdOrig[comp].nEntries = nEntries;
   if (nSteps > h->minForwardTableSize) h->minForwardTableSize = nSteps;
   h->tableDescDirty = true;
+  h->tableDescDirtyForMax = true;
   return I3RC_SUCCESS;
 }
 
@@ -2226,6 +2259,8 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->tablesInSmem = value;
   else if (k == "debug_zero_strides" && (value == 0 || value == 1))
     h->debugZeroStrides = value;
+  else if (k == "le_early_exit" && (value == 0 || value == 1))
+    h->leEarlyExit = value;
   else if (k == "le_upper_bound" && (value == 0 || value == 1))
     h->leUpperBound = value;  // 0: rays that are certain to survive the roulette are traced all the same
   else if (k == "le_lower_bound" && (value == 0 || value == 1))

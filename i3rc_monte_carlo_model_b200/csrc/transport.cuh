@@ -154,6 +154,7 @@ struct Problem {
   // contribution does not depend on the optical path (the roulette's survivors, MCRT:1556, 1584) it is tallied without
   // tracing, in the column where the straight line leaves the domain.  Null: unused.
   const float* leUB;
+  float limMax;  // largest first-stage limit of the roulette any event can get, -log(zetaMin / (pi phatMax)) or 0; < 0: unknown
   const float* dirs;  // [nDir][DIR_STRIDE]: d.x d.y d.z 1/|d.x| 1/|d.y| 1/|d.z| 4*pi*|mu| 1/(4*pi*|mu|)
   int useRayTracing, useRussianRoulette, useRRIntensity, useHybrid, numOrdersOrig, limitContrib, useSurfaceBDRF;
   int trackByComponent;
@@ -1116,6 +1117,19 @@ struct LeTask {
 template <class P>
 I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, LeTask& t) {
   const float* dv = p.dirs + d * DIR_STRIDE;
+  if (p.useRRIntensity && p.limMax >= 0.0f && (p.leLB || ((p.vertMask >> d) & 1u))) {
+    // Before anything is looked up: under the roulette no ray has a larger budget than tauFree + limMax (the first-stage
+    // limit of the largest phase-function value there is); deep inside a cloud the least the ray needs is far more.
+    float need;
+    if ((p.vertMask >> d) & 1u) {
+      need = I3RC_LDG(p.colTau + (size_t)(L.cz + 1) * ((size_t)p.nx * p.ny) + (size_t)(L.cy * p.nx + L.cx));
+    } else {
+      const size_t ncell = (size_t)p.nx * p.ny * p.nz, cell = ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx;
+      need = I3RC_LDG(p.leLB + (size_t)d * p.leLBBins * ncell + cell);  // (octant 0 of 8 is not the bound of the others:
+      if (p.leLBBins != 1) need = 0.0f;                                 //  the early exit is for one bound per cell)
+    }
+    if (need > tau_of(xiTau) + p.limMax) return 0;
+  }
   float phat;
   if (L.comp < 1) {
     phat = 1.0f / F_PI;  // quirk Q10 (MCRT:1479)

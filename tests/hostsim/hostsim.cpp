@@ -107,6 +107,7 @@ static void fill(const HostSimArgs* a, Problem& p, std::vector<TableDesc>& td, s
   p.fluxUp = a->fluxUp; p.fluxDown = a->fluxDown; p.fluxAbs = a->fluxAbs; p.volAbs = a->volAbs;
   p.intensity = a->intensity; p.intByComp = a->intByComp; p.excess = a->excess;
   p.counters = a->counters; p.nextPhoton = nullptr; p.firstPhoton = 0;
+  p.limMax = -1.0f;  // (unknown: no early exit before the phase-function lookup)
 }
 
 }  // extern "C"
@@ -134,6 +135,15 @@ static void lower_bound_setup(Problem& p) {
     }
   p.leLB = g_leLB.data();
   if (g_lb == 2) p.leUB = g_leUB.data();
+  // the largest first-stage limit any event can get (Problem::limMax), like fill_problem of the library
+  float mx = 0.0f, inv = 0.0f;
+  for (int c = 0; c < p.nc; c++)
+    for (const float* tab : {p.tables[c].fwd, p.tables[c].fwdOrig})
+      if (tab)
+        for (size_t i = 0; i < (size_t)p.tables[c].nFwd * p.tables[c].nEntries; i++) mx = mx > tab[i] ? mx : tab[i];
+  for (int d = 0; d < p.nDir; d++) inv = inv > p.dirs[d * DIR_STRIDE + 7] ? inv : p.dirs[d * DIR_STRIDE + 7];
+  const float phatMax = mx * inv;
+  p.limMax = F_PI * phatMax > p.zetaMin ? -logf(p.zetaMin / (F_PI * phatMax)) * (1.0f + 1e-5f) + 1e-5f : 0.0f;
 }
 static int g_vertical = 0;  // straight-up radiance directions from column suffix sums (Problem::colTau) instead of traced
 static std::vector<float> g_colTau;

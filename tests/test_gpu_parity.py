@@ -813,9 +813,11 @@ def test_rays_that_cannot_contribute_are_not_traced_on_the_device(cuda):
         #  ray may leave one column further when that point lies within an ulp of a column boundary)
         assert np.mean(~np.isclose(a["intensity"], b["intensity"], rtol=2e-3, atol=1e-6)) < 1e-3
         assert np.array_equal(a["fluxUp"] > 0, b["fluxUp"] > 0) and np.allclose(a["fluxUp"], b["fluxUp"], rtol=1e-4, atol=1e-7)
-        # the upper bound alone: fewer crossings again, same contributions
+        # with the upper bound as well (off by default): fewer crossings again, same contributions
         I = make_integrator(cuda, d, **kw)
-        assert cuda.set_tuning(I.handle, b"le_upper_bound", 0) == 0
+        assert cuda.set_tuning(I.handle, b"le_upper_bound", 1) == 0
         computeRadiativeTransfer(I, new_RandomNumberSequence([10, 6]), new_PhotonStream(numberOfPhotons=400_000, **src))
-        cc = getCounters(I)
-        assert cc["contributions"] == ca["contributions"] and ca["crossings_intensity"] < cc["crossings_intensity"] < cb["crossings_intensity"]
+        cc, rc = getCounters(I), reportResults(I, "meanIntensity", "intensity")
+        assert cc["contributions"] == ca["contributions"] and cc["crossings_intensity"] < ca["crossings_intensity"]
+        assert np.allclose(rc["meanIntensity"], b["meanIntensity"], rtol=1e-5)
+        assert np.mean(~np.isclose(rc["intensity"], b["intensity"], rtol=2e-3, atol=1e-6)) < 1e-3
