@@ -1089,7 +1089,10 @@ int prepare_compute(i3rc_integrator* h, const i3rc_photon_source* src, SourceDev
   if (rc != I3RC_SUCCESS) return rc;
   // lower bounds of the optical path to the top, per radiance direction and cell (Problem::leLB): regular grids, roulette
   // for intensity; at most 8 GB (twelve slanted directions on 512x512x256 are 3.2 GB)
-  if (!h->leLBValid && h->leLowerBound && h->computeIntensity && h->useRRIntensity && h->xyRegular && h->zRegular && h->nDir > 0) {
+  // (few-column domains -- step cloud, radar cloud -- have rays of a handful of crossings: tracing them is as cheap as
+  //  asking, measured -2.5 %; `le_lower_bound` = 2 forces the bounds there too)
+  if (!h->leLBValid && h->leLowerBound && h->computeIntensity && h->useRRIntensity && h->xyRegular && h->zRegular && h->nDir > 0 &&
+      ((size_t)h->nx * h->ny >= 4096 || h->leLowerBound == 2)) {
     const size_t ncell = (size_t)h->nx * h->ny * h->nz;
     if (ncell * h->nDir * sizeof(float) <= ((size_t)8 << 30)) {
       dfree(h->d_leLB);
@@ -2263,7 +2266,7 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->leEarlyExit = value;
   else if (k == "le_upper_bound" && (value == 0 || value == 1))
     h->leUpperBound = value;  // 0: rays that are certain to survive the roulette are traced all the same
-  else if (k == "le_lower_bound" && (value == 0 || value == 1))
+  else if (k == "le_lower_bound" && value >= 0 && value <= 2)
     h->leLowerBound = value;  // 0: local-estimate rays are traced even when a lower bound says they cannot contribute
   else if (k == "vertical_shortcut" && (value == 0 || value == 1))
     h->verticalShortcut = value;  // 0: straight-up local-estimate rays are traced like the others

@@ -1117,18 +1117,19 @@ struct LeTask {
 template <class P>
 I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, LeTask& t) {
   const float* dv = p.dirs + d * DIR_STRIDE;
-  if (p.useRRIntensity && p.limMax >= 0.0f && (p.leLB || ((p.vertMask >> d) & 1u))) {
-    // Before anything is looked up: under the roulette no ray has a larger budget than tauFree + limMax (the first-stage
-    // limit of the largest phase-function value there is); deep inside a cloud the least the ray needs is far more.
-    float need;
-    if ((p.vertMask >> d) & 1u) {
-      need = I3RC_LDG(p.colTau + (size_t)(L.cz + 1) * ((size_t)p.nx * p.ny) + (size_t)(L.cy * p.nx + L.cx));
-    } else {
-      const size_t ncell = (size_t)p.nx * p.ny * p.nz, cell = ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx;
-      need = I3RC_LDG(p.leLB + (size_t)d * p.leLBBins * ncell + cell);  // (octant 0 of 8 is not the bound of the others:
-      if (p.leLBBins != 1) need = 0.0f;                                 //  the early exit is for one bound per cell)
-    }
-    if (need > tau_of(xiTau) + p.limMax) return 0;
+  const bool vertical = ((p.vertMask >> d) & 1u) != 0;
+  // What is known about the optical path to the top before anything else is looked up: for a direction that points
+  // straight up the column's suffix sum above the event cell (the rest of the path is in the cell itself), otherwise
+  // the lower bound of Problem::leLB.  Both loads are issued here and used further down.
+  float tauFree = 0.0f, above = 0.0f, lb = 0.0f;
+  const bool bounded = p.useRRIntensity && p.leLB && !vertical && p.leLBBins == 1;
+  if (vertical) above = I3RC_LDG(p.colTau + (size_t)(L.cz + 1) * ((size_t)p.nx * p.ny) + (size_t)(L.cy * p.nx + L.cx));
+  if (bounded) lb = I3RC_LDG(p.leLB + (size_t)d * ((size_t)p.nx * p.ny * p.nz) + ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx);
+  if (p.useRRIntensity) {
+    tauFree = tau_of(xiTau);  // MCRT:1542
+    // Under the roulette no ray has a larger budget than tauFree + limMax (the first-stage limit of the largest
+    // phase-function value there is); deep inside a cloud the least the ray needs is far more: no lookup at all.
+    if (p.limMax >= 0.0f && (vertical ? above : lb) > tauFree + p.limMax) return 0;
   }
   float phat;
   if (L.comp < 1) {
@@ -1143,9 +1144,8 @@ I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, L
     phat = val * I3RC_LDG(dv + 7);  // 1 / (4 pi |mu|), MCRT:1509
   }
   int mode = MODE_LE_PLAIN;
-  float lim = INFINITY, tauFree = 0.0f;
+  float lim = INFINITY;
   if (p.useRRIntensity) {
-    tauFree = tau_of(xiTau);  // MCRT:1542
     if (F_PI * phat <= p.zetaMin) {
       // Iwabuchi Eq 13 (MCRT:1546-1559).  The acceptance draw does not depend on the ray, so it is taken
       // first and rejected rays are never traced (the reference traces them and then discards them).
@@ -1157,13 +1157,11 @@ I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, L
       lim = -I3RC_LOG(I3RC_FDIV(p.zetaMin, fmaxf(F_TINY, F_PI * phat)));
     }
   }
-  if (p.leLB && mode != MODE_LE_PLAIN && !((p.vertMask >> d) & 1u)) {
+  if (bounded) {
     // the budget the ray has for reaching the top, against the least and the most it can need from this cell
     const float budget = mode == MODE_LE_SMALL ? lim : lim + tauFree;
-    const size_t ncell = (size_t)p.nx * p.ny * p.nz, cell = ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx;
-    const int oct = p.leLBBins == 8 ? (L.fx >= 0.5f ? 1 : 0) + (L.fy >= 0.5f ? 2 : 0) + (L.fz >= 0.5f ? 4 : 0) : 0;
-    const float lb = I3RC_LDG(p.leLB + ((size_t)d * p.leLBBins + oct) * ncell + cell);
     if (lb > budget) return 0;
+    const size_t ncell = (size_t)p.nx * p.ny * p.nz, cell = ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx;
     if (p.leUB && I3RC_LDG(p.leUB + (size_t)d * ncell + cell) <= budget && (mode == MODE_LE_SMALL || lb > lim)) {
       // Certain to reach the top, and not within the first stage's limit: the contribution is the survivors' fixed one.
       // The exit column is where the straight line from the event point meets the top of the domain.
@@ -1178,13 +1176,11 @@ I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, L
       return 2;
     }
   }
-  if ((p.vertMask >> d) & 1u) {
+  if (vertical) {
     // Straight up: the ray never leaves its column.  Same estimator, same deviates, no tracing: the optical path to the
     // top is the rest of the event cell plus the suffix sum of the layers above; the roulette stages (MCRT:1554-1559,
     // 1570-1587) only ask whether that path fits into their optical-path limits.
-    const size_t ncol = (size_t)p.nx * p.ny;
-    const float tauTop = (1.0f - L.fz) * cell_w(p.ze, p.zRegular, p.dz, L.cz) * ext_value<P>(L.eCell) +
-                         I3RC_LDG(p.colTau + (size_t)(L.cz + 1) * ncol + (size_t)(L.cy * p.nx + L.cx));
+    const float tauTop = (1.0f - L.fz) * cell_w(p.ze, p.zRegular, p.dz, L.cz) * ext_value<P>(L.eCell) + above;
     const float cfix = L.w * p.zetaMin * (1.0f / F_PI);
     float c;
     if (mode == MODE_LE_PLAIN)
