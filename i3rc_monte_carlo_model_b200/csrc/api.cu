@@ -148,6 +148,7 @@ struct i3rc_integrator {
   // tuning
   int blockSize = 128, blocksPerSM = 0, residentBlocks = 0, poolShape = 0, minRunning = 16, padSmem = 0, kSteps = 16;
   int eventThreshold = 16;
+  int birthMin = 16;  // (tuning) a warp starts new photons when this many of its slots are empty (1: at once, one by one)
   float* d_rep = nullptr;   // copies of the tallies of a domain of few columns (Problem::rep)
   size_t repN = 0;
   int replicaColumns = 4096;  // (tuning) tallies are replicated in global memory for domains of at most this many columns
@@ -761,7 +762,7 @@ int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   ProblemT<REG, FAST, SPLIT, JUMP, TABSM> pt;
   static_cast<Problem&>(pt) = p;
   if (JUMP) pt.ext = h->d_extJ;  // the copy of the gather field that carries the empty-space codes
-  kern<<<(unsigned)grid, BLOCK, dynSmem, h->stream>>>(pt, h->eventThreshold, h->minRunning);
+  kern<<<(unsigned)grid, BLOCK, dynSmem, h->stream>>>(pt, h->eventThreshold, h->minRunning, h->birthMin);
   return I3RC_SUCCESS;
 }
 // MINB = resident blocks per SM the kernel is compiled for (register cap 65536 / (MINB * BLOCK));
@@ -1824,6 +1825,7 @@ int i3rc_copy_Integrator(const i3rc_integrator* s, i3rc_integrator** out) {
   h->blocksPerSM = s->blocksPerSM;
   h->kSteps = s->kSteps;
   h->eventThreshold = s->eventThreshold;
+  h->birthMin = s->birthMin;
   h->residentBlocks = s->residentBlocks;
   h->poolShape = s->poolShape;
   h->minRunning = s->minRunning;
@@ -2251,6 +2253,8 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->poolShape = value;
   else if (k == "event_threshold" && value >= 1 && value <= 32)
     h->eventThreshold = value;
+  else if (k == "birth_min" && value >= 1 && value <= 32)
+    h->birthMin = value;
   else if (k == "track_by_component")
     h->trackByComponent = value != 0;
   else if (k == "slab_jump" && (value == 0 || value == 1))

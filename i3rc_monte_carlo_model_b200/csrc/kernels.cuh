@@ -128,7 +128,8 @@ __device__ __forceinline__ void flush_staged_tallies(const P& p, const float* sd
 
 template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP, bool TSM = false, bool JUMP = false,
           bool TABSM = false>
-__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, FAST, SPLIT, JUMP, TABSM> p, const int lowWater, const int minRunning) {
+__global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, FAST, SPLIT, JUMP, TABSM> p, const int lowWater, const int minRunning,
+                                                               const int birthMin) {
   constexpr int NW = BLOCK / 32;
   extern __shared__ float s_dyn[];  // TSM: NW private copies of the staged tallies (Problem::tsmN floats each)
   using Tally = typename std::conditional<TSM, TallyLater, TallyNow>::type;
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
 
   // warp-uniform bookkeeping (registers): ring positions [head, tail), number of due events
   int head = 0, tail = 0, npend = NSLOT;
+  int nempty = 0;  // slots whose photon is finished and that wait for the next round of births (pend[NSLOT - 1 - i])
   bool exhausted = false;
   for (int k = lane; k < NSLOT; k += 32) {  // every slot starts by asking for a photon
     pend[k] = (uint8_t)k;
@@ -205,6 +207,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
     if (stage == 0) {
       const int busy = __popc(__ballot_sync(full, R.done != DONE_IDLE));
       const int queued = tail - head;
+      // Births in groups: enough empty slots (or nothing else to do) -> they go on top of the due events, so that the
+      // next batch starts their photons with many lanes at once (one request to the device photon counter for all).
+      if (nempty >= birthMin || (nempty > 0 && queued == 0 && busy <= lowWater)) {
+        const int m = min(nempty, 32);
+        const uint8_t s = lane < m ? pend[NSLOT - 1 - (nempty - m + lane)] : (uint8_t)0;
+        __syncwarp();
+        if (lane < m) pend[npend + lane] = s;
+        __syncwarp();
+        npend += m;
+        nempty -= m;
+      }
       if (npend >= 32 || (npend > 0 && queued == 0 && busy <= lowWater)) {
         const int k = min(32, npend);
         has = lane < k;
@@ -327,8 +340,20 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
           scatter_photon(p, E, a1, a2);  // roulette, new direction (MCRT:670-688)
           go = E.active != 0;
         }
-        // slots whose photon is finished (or that never had one) take the next photon of the batch
-        const bool need = has && !go && !exhausted;
+        // Slots that come without a photon take the next photons of the batch.  A slot whose photon has just finished
+        // waits among the empty ones until there are birthMin of them (above): the start of a photon's life -- a request
+        // to the device counter, which the whole warp waits for, and a good 250 instructions -- is then run by many
+        // lanes at once instead of by the one or two photons that finish in any given batch.
+        const bool fresh = has && !go && !exhausted;
+        const bool need = fresh && (E.segDone == DONE_NEW || birthMin <= 1);
+        const unsigned md = __ballot_sync(full, fresh && !need);
+        if (md) {
+          if (fresh && !need) {
+            pend[NSLOT - 1 - (nempty + __popc(md & lt))] = (uint8_t)eslot;
+            pool.zs[eslot] = (uint32_t)DONE_NEW << 16;
+          }
+          nempty += __popc(md);
+        }
         const unsigned mn = __ballot_sync(full, need);
         if (mn) {
           unsigned long long base = 0;
