@@ -258,9 +258,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
             T.stx = E.ux >= 0.0f ? 1 : -1;  // (only the signs matter here)
             T.sty = E.uy >= 0.0f ? 1 : -1;
             T.stz = E.uz >= 0.0f ? 1 : -1;
-            T.iax = inv_abs(E.ux) * (REG ? p.dx : 1.0f);
-            T.iay = inv_abs(E.uy) * (REG ? p.dy : 1.0f);
-            T.iaz = inv_abs(E.uz) * (REG ? p.dz : 1.0f);
+            T.nax = -inv_abs(E.ux) * (REG ? p.dx : 1.0f);
+            T.nay = -inv_abs(E.uy) * (REG ? p.dy : 1.0f);
+            T.naz = -inv_abs(E.uz) * (REG ? p.dz : 1.0f);
             T.rx = E.fx;
             T.ry = E.fy;
             T.rz = E.fz;
@@ -461,9 +461,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
         I3RC_COUNT(R, CNT_CROSS_PH, R.nsteps);
         if (FAST || p.useRayTracing) {
           const bool inside = done == DONE_INSIDE;
-          if (!isinf(R.iax)) pool.fx[R.slot] = R.rx;  // (an axis the ray does not move along keeps its offset)
-          if (!isinf(R.iay)) pool.fy[R.slot] = R.ry;
-          if (!isinf(R.iaz)) pool.fz[R.slot] = R.rz;
+          if (!isinf(R.nax)) pool.fx[R.slot] = R.rx;  // (an axis the ray does not move along keeps its offset)
+          if (!isinf(R.nay)) pool.fy[R.slot] = R.ry;
+          if (!isinf(R.naz)) pool.fz[R.slot] = R.rz;
           pool.xy[R.slot] = (uint32_t)R.cntx | ((uint32_t)R.cnty << 16);
           pool.zs[R.slot] = (uint32_t)R.cntz | ((uint32_t)done << 16) | SLOT_RAW;
           if (inside) {

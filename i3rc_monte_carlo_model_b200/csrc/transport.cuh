@@ -387,7 +387,10 @@ struct Lane {
   // register move ever waits for it.  e = extinction of the pending cell of a ray that has stopped.
   float sp, e0, e1, e;
   int par;  // which of e0 / e1 holds the pending cell (run-time copy for callers that step one lane at a time)
-  float iax, iay, iaz;  // kRegular: path length per cell along the ray (cell width / |direction cosine|); else 1/|cosine|
+  // MINUS the path length per cell along the ray (kRegular: cell width / |direction cosine|; else 1 / |cosine|, times the
+  // cell's width when used).  Negative because that is the form the cell-crossing loop consumes (ray_advance: a crossed
+  // face is recorded as a negative distance): the loop then keeps no second, sign-flipped copy of the three in registers.
+  float nax, nay, naz;
   int done;
   int nsteps;
   int segDone;  // how the photon's last own segment ended (DONE_*), kept until its event is processed
@@ -563,10 +566,10 @@ I3RC_HD bool ray_advance(const P& p, Lane& L) {
   L.cnty = ny_;
   L.cntz = nz_;
   const float qx = ax - s, qy = ay - s, qz = az - s;
-  L.rx = cx ? -ray_dt(p, L.iax, p.xe, p.xyRegular, p.dx, ray_ix(p, L)) : qx;
-  L.ry = cy ? -ray_dt(p, L.iay, p.ye, p.xyRegular, p.dy, ray_iy(p, L)) : qy;
+  L.rx = cx ? ray_dt(p, L.nax, p.xe, p.xyRegular, p.dx, ray_ix(p, L)) : qx;
+  L.ry = cy ? ray_dt(p, L.nay, p.ye, p.xyRegular, p.dy, ray_iy(p, L)) : qy;
   // (outside the domain there is no cell width to look up: any negative value records the crossing)
-  L.rz = cz ? ((P::kRegular || !out) ? -ray_dt(p, L.iaz, p.ze, p.zRegular, p.dz, ray_iz(p, L)) : -1.0f) : qz;
+  L.rz = cz ? ((P::kRegular || !out) ? ray_dt(p, L.naz, p.ze, p.zRegular, p.dz, ray_iz(p, L)) : -1.0f) : qz;
   L.sp = s;
   return out;
 }
@@ -577,22 +580,23 @@ I3RC_HD bool ray_advance(const P& p, Lane& L) {
 template <class P>
 I3RC_HD bool ray_advance_far(const P& p, Lane& L, int n) {
   const float ax = fabsf(L.rx), ay = fabsf(L.ry), az = fabsf(L.rz);
+  const float iax = -L.nax, iay = -L.nay, iaz = -L.naz;
   const float fn = (float)(n - 1);
-  float T = fminf(fmaf(fn, L.iax, ax), fminf(fmaf(fn, L.iay, ay), fmaf(fn, L.iaz, az)));
-  T = fminf(T, fmaf((float)(L.cntz - 1), L.iaz, az));  // not beyond the top / the bottom of the domain
+  float T = fminf(fmaf(fn, iax, ax), fminf(fmaf(fn, iay, ay), fmaf(fn, iaz, az)));
+  T = fminf(T, fmaf((float)(L.cntz - 1), iaz, az));  // not beyond the top / the bottom of the domain
   int mx = 0, my = 0, mz = 0;
   float qx = ax - T, qy = ay - T, qz = az - T;
   if (ax <= T) {
-    mx = (int)I3RC_FDIV(T - ax, L.iax) + 1;
-    qx = fmaxf(fmaf((float)mx, L.iax, ax) - T, 0.0f);
+    mx = (int)I3RC_FDIV(T - ax, iax) + 1;
+    qx = fmaxf(fmaf((float)mx, iax, ax) - T, 0.0f);
   }
   if (ay <= T) {
-    my = (int)I3RC_FDIV(T - ay, L.iay) + 1;
-    qy = fmaxf(fmaf((float)my, L.iay, ay) - T, 0.0f);
+    my = (int)I3RC_FDIV(T - ay, iay) + 1;
+    qy = fmaxf(fmaf((float)my, iay, ay) - T, 0.0f);
   }
   if (az <= T) {
-    mz = (int)I3RC_FDIV(T - az, L.iaz) + 1;
-    qz = fmaxf(fmaf((float)mz, L.iaz, az) - T, 0.0f);
+    mz = (int)I3RC_FDIV(T - az, iaz) + 1;
+    qz = fmaxf(fmaf((float)mz, iaz, az) - T, 0.0f);
   }
   mz = mz < L.cntz ? mz : L.cntz;
   int nx_ = L.cntx - mx, ny_ = L.cnty - my, idx = L.idx + mx * L.stx + my * L.sty + mz * L.stz;
@@ -632,9 +636,9 @@ I3RC_HD float ext_gather_ray(const P& p, const Lane& L) {
 #endif
         const bool up = L.stz > 0;
         const int ahead = (int)(up ? s.x : s.y);
-        if (ahead >= SLAB_MIN && !isinf(L.iaz)) {
+        if (ahead >= SLAB_MIN && !isinf(L.naz)) {
           // rest of this layer + the layers ahead: vertical optical depth / |cosine| (iaz = dz / |cosine| on a regular grid)
-          const float tauB = fmaf(e, fabsf(L.rz), (up ? s.z : s.w) * I3RC_FDIV(L.iaz, p.dz));
+          const float tauB = fmaf(e, fabsf(L.rz), (up ? s.z : s.w) * I3RC_FDIV(-L.naz, p.dz));
           return -(tauB + 1.0f);
         }
         return e;
@@ -657,16 +661,17 @@ I3RC_HD bool ray_cross_slab(const P& p, Lane& L) {
 #endif
   const int ahead = (int)(L.stz > 0 ? s.x : s.y);
   const float ax = fabsf(L.rx), ay = fabsf(L.ry), az = fabsf(L.rz);
-  const float T = fmaf((float)ahead, L.iaz, az);  // path length to the far face of the last layer of the slab
+  const float iax = -L.nax, iay = -L.nay, iaz = -L.naz;
+  const float T = fmaf((float)ahead, iaz, az);  // path length to the far face of the last layer of the slab
   int mx = 0, my = 0;
   float qx = ax - T, qy = ay - T;
   if (ax <= T) {
-    mx = (int)I3RC_FDIV(T - ax, L.iax) + 1;
-    qx = fmaxf(fmaf((float)mx, L.iax, ax) - T, 0.0f);
+    mx = (int)I3RC_FDIV(T - ax, iax) + 1;
+    qx = fmaxf(fmaf((float)mx, iax, ax) - T, 0.0f);
   }
   if (ay <= T) {
-    my = (int)I3RC_FDIV(T - ay, L.iay) + 1;
-    qy = fmaxf(fmaf((float)my, L.iay, ay) - T, 0.0f);
+    my = (int)I3RC_FDIV(T - ay, iay) + 1;
+    qy = fmaxf(fmaf((float)my, iay, ay) - T, 0.0f);
   }
   int nx_ = (L.cntx - 1 - mx) % p.nx, ny_ = (L.cnty - 1 - my) % p.ny;  // cells left on the axis, minus one, modulo the period
   if (nx_ < 0) nx_ += p.nx;
@@ -676,7 +681,7 @@ I3RC_HD bool ray_cross_slab(const P& p, Lane& L) {
   L.cntz -= ahead + 1;
   L.rx = qx;
   L.ry = qy;
-  L.rz = L.iaz;  // (a whole layer ahead, if there is one)
+  L.rz = iaz;  // (a whole layer ahead, if there is one)
   L.sp = 1.0f;   // the slab code is an optical path already
   I3RC_COUNT(L, L.mode == MODE_PHOTON ? CNT_SKIP : CNT_SKIP_LE, mx + my + ahead);  // cells passed without a look
   if (L.cntz <= 0) {
@@ -713,9 +718,9 @@ I3RC_HD void start_ray_at(const P& p, Lane& L, int ix, int iy, int iz, float fx,
     iay *= p.dy;
     iaz *= p.dz;
   }
-  L.iax = iax;
-  L.iay = iay;
-  L.iaz = iaz;
+  L.nax = -iax;
+  L.nay = -iay;
+  L.naz = -iaz;
   L.rx = isinf(iax) ? INFINITY : (px ? (1.0f - fx) : fx) * ray_dt(p, iax, p.xe, p.xyRegular, p.dx, ix);
   L.ry = isinf(iay) ? INFINITY : (py ? (1.0f - fy) : fy) * ray_dt(p, iay, p.ye, p.xyRegular, p.dy, iy);
   L.rz = isinf(iaz) ? INFINITY : (pz ? (1.0f - fz) : fz) * ray_dt(p, iaz, p.ze, p.zRegular, p.dz, iz);
@@ -862,18 +867,18 @@ I3RC_HD void ray_restart(const P& p, Lane& L) {
 // offset inside the current cell of the ray's current point, per axis (keeps f where the ray does not move)
 template <class P>
 I3RC_HD void ray_local(const P& p, const Lane& L, float* fx, float* fy, float* fz) {
-  if (!isinf(L.iax)) {
-    float rem = I3RC_FDIV(fabsf(L.rx), ray_dt(p, L.iax, p.xe, p.xyRegular, p.dx, ray_ix(p, L)));
+  if (!isinf(L.nax)) {
+    float rem = I3RC_FDIV(fabsf(L.rx), ray_dt(p, -L.nax, p.xe, p.xyRegular, p.dx, ray_ix(p, L)));
     rem = fminf(fmaxf(rem, 0.0f), 1.0f);
     *fx = L.stx > 0 ? 1.0f - rem : rem;
   }
-  if (!isinf(L.iay)) {
-    float rem = I3RC_FDIV(fabsf(L.ry), ray_dt(p, L.iay, p.ye, p.xyRegular, p.dy, ray_iy(p, L)));
+  if (!isinf(L.nay)) {
+    float rem = I3RC_FDIV(fabsf(L.ry), ray_dt(p, -L.nay, p.ye, p.xyRegular, p.dy, ray_iy(p, L)));
     rem = fminf(fmaxf(rem, 0.0f), 1.0f);
     *fy = L.sty > 0 ? 1.0f - rem : rem;
   }
-  if (L.cntz != 0 && !isinf(L.iaz)) {
-    float rem = I3RC_FDIV(fabsf(L.rz), ray_dt(p, L.iaz, p.ze, p.zRegular, p.dz, ray_iz(p, L)));
+  if (L.cntz != 0 && !isinf(L.naz)) {
+    float rem = I3RC_FDIV(fabsf(L.rz), ray_dt(p, -L.naz, p.ze, p.zRegular, p.dz, ray_iz(p, L)));
     rem = fminf(fmaxf(rem, 0.0f), 1.0f);
     *fz = L.stz > 0 ? 1.0f - rem : rem;
   }
