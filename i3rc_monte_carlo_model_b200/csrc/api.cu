@@ -147,7 +147,8 @@ struct i3rc_integrator {
   long long traceLaunches = 0, otherLaunches = 0;
   // tuning
   int blockSize = 128, blocksPerSM = 0, residentBlocks = 0, poolShape = 0, minRunning = 16, padSmem = 0, kSteps = 16;
-  int eventThreshold = 16;
+  int eventThreshold = 4;  // (tuning) an event batch of fewer than 32 events starts only when the ring is empty and at most this many lanes trace
+  int birthLow = 4;  // (tuning) ... or when the task ring is empty and at most this many lanes are tracing
   int birthMin = 16;  // (tuning) a warp starts new photons when this many of its slots are empty (1: at once, one by one)
   float* d_rep = nullptr;   // copies of the tallies of a domain of few columns (Problem::rep)
   size_t repN = 0;
@@ -762,7 +763,7 @@ int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   ProblemT<REG, FAST, SPLIT, JUMP, TABSM> pt;
   static_cast<Problem&>(pt) = p;
   if (JUMP) pt.ext = h->d_extJ;  // the copy of the gather field that carries the empty-space codes
-  kern<<<(unsigned)grid, BLOCK, dynSmem, h->stream>>>(pt, h->eventThreshold, h->minRunning, h->birthMin);
+  kern<<<(unsigned)grid, BLOCK, dynSmem, h->stream>>>(pt, h->eventThreshold, h->minRunning, h->birthMin | (h->birthLow << 8));
   return I3RC_SUCCESS;
 }
 // MINB = resident blocks per SM the kernel is compiled for (register cap 65536 / (MINB * BLOCK));
@@ -852,6 +853,12 @@ int launch_transport(i3rc_integrator* h, const Problem& p) {
         return launch_transport_fast<4, 64, 64>(h, p);
       case 52:
         return launch_transport_fast<5, 48, 64>(h, p);
+      case 55:  // (experiments: more photons per warp, so that the task ring runs dry less often)
+        return launch_transport_t<128, true, true, false, 5, 16, 96, 64>(h, p);
+      case 56:
+        return launch_transport_t<128, true, true, false, 5, 16, 80, 64>(h, p);
+      case 65:
+        return launch_transport_t<128, true, true, false, 6, 16, 80, 64>(h, p);
       case 72:  // (experiments: more resident warps at the price of registers)
         return launch_transport_t<128, true, true, false, 7, 16, 48, 64>(h, p);
       case 83:
@@ -1133,6 +1140,20 @@ int fetch_counters(i3rc_integrator* h) {
   o.null_collisions = c[CNT_NULL];
   o.cells_skipped = c[CNT_SKIP];
   o.cells_skipped_intensity = c[CNT_SKIP_LE];
+#ifdef I3RC_SCHED_STATS
+  {
+    const double rounds = (double)c[ST_ROUNDS], pairs = (double)c[ST_PAIRS], batch = (double)c[ST_BATCH];
+    fprintf(stderr,
+            "[sched] rounds %.4g  lanes running at round start %.2f  step pairs per round %.2f  lanes per step pair %.2f\n"
+            "[sched] idle lanes left without a task per round %.2f  tasks left in the ring per round %.2f\n"
+            "[sched] event batches %.4g (%.3f per round)  events per batch %.2f  alive after the event %.2f  "
+            "local-estimate tasks per batch %.2f  suspensions per batch %.3f  births per batch with births %.2f (%.3f of the batches)\n",
+            rounds, c[ST_START_RUN] / rounds, pairs / rounds, c[ST_LANE_PAIRS] / pairs, c[ST_STARVED] / rounds,
+            c[ST_RING_LEFT] / rounds, batch, batch / rounds, c[ST_BATCH_HAS] / batch, c[ST_BATCH_ALIVE] / batch,
+            c[ST_LE_PUSH] / batch, c[ST_SUSP] / batch, c[ST_BIRTHS] / (double)(c[ST_BIRTH_BATCH] ? c[ST_BIRTH_BATCH] : 1),
+            c[ST_BIRTH_BATCH] / batch);
+  }
+#endif
   return I3RC_SUCCESS;
 }
 
@@ -1826,6 +1847,7 @@ int i3rc_copy_Integrator(const i3rc_integrator* s, i3rc_integrator** out) {
   h->kSteps = s->kSteps;
   h->eventThreshold = s->eventThreshold;
   h->birthMin = s->birthMin;
+  h->birthLow = s->birthLow;
   h->residentBlocks = s->residentBlocks;
   h->poolShape = s->poolShape;
   h->minRunning = s->minRunning;
@@ -2249,12 +2271,14 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->padSmem = value;  // experiment: unused dynamic shared memory (shrinks the L1 share of the SM)
   else if (k == "min_running" && value >= 0 && value <= 32)
     h->minRunning = value;
-  else if (k == "pool_shape" && value >= 0 && value <= 4)
+  else if (k == "pool_shape" && value >= 0 && value <= 6)
     h->poolShape = value;
   else if (k == "event_threshold" && value >= 1 && value <= 32)
     h->eventThreshold = value;
   else if (k == "birth_min" && value >= 1 && value <= 32)
     h->birthMin = value;
+  else if (k == "birth_low" && value >= 0 && value <= 32)
+    h->birthLow = value;
   else if (k == "track_by_component")
     h->trackByComponent = value != 0;
   else if (k == "slab_jump" && (value == 0 || value == 1))

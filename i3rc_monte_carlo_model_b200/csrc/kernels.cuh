@@ -129,7 +129,7 @@ __device__ __forceinline__ void flush_staged_tallies(const P& p, const float* sd
 template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP, bool TSM = false, bool JUMP = false,
           bool TABSM = false>
 __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, FAST, SPLIT, JUMP, TABSM> p, const int lowWater, const int minRunning,
-                                                               const int birthMin) {
+                                                               const int births) {
   constexpr int NW = BLOCK / 32;
   extern __shared__ float s_dyn[];  // TSM: NW private copies of the staged tallies (Problem::tsmN floats each)
   using Tally = typename std::conditional<TSM, TallyLater, TallyNow>::type;
@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
 
   // warp-uniform bookkeeping (registers): ring positions [head, tail), number of due events
   int head = 0, tail = 0, npend = NSLOT;
+  const int birthMin = births & 255, birthLow = births >> 8;
   int nempty = 0;  // slots whose photon is finished and that wait for the next round of births (pend[NSLOT - 1 - i])
   bool exhausted = false;
   for (int k = lane; k < NSLOT; k += 32) {  // every slot starts by asking for a photon
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
       const int queued = tail - head;
       // Births in groups: enough empty slots (or nothing else to do) -> they go on top of the due events, so that the
       // next batch starts their photons with many lanes at once (one request to the device photon counter for all).
-      if (nempty >= birthMin || (nempty > 0 && queued == 0 && busy <= lowWater)) {
+      if (nempty >= birthMin || (nempty > 0 && queued == 0 && busy <= birthLow)) {
         const int m = min(nempty, 32);
         const uint8_t s = lane < m ? pend[NSLOT - 1 - (nempty - m + lane)] : (uint8_t)0;
         __syncwarp();
@@ -286,6 +287,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
         }
       }
       if (stage == 0) {  // boundary / collision handling (MCRT:499-561, 581-649)
+        I3RC_STAT(W, ST_BATCH, 1);
+        I3RC_STAT(W, ST_BATCH_HAS, __popc(__ballot_sync(full, has)));
         alive = false;
         Tally tal;
         if constexpr (TSM) tal.n = 0;
@@ -300,6 +303,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
           if (__any_sync(full, t.n > 1)) warp_tally<TSM>(p, wt, t.n > 1, t.w1, t.o1, t.v1);
         }
         dcur = 0;
+        I3RC_STAT(W, ST_BATCH_ALIVE, __popc(__ballot_sync(full, alive)));
         stage = (p.computeIntensity && __any_sync(full, alive)) ? 1 : 2;
       } else {  // resume: the rest of the batch state comes back from shared memory
         const uint32_t* sv = W.susp[0] + lane;
@@ -323,6 +327,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
           const unsigned m = __ballot_sync(full, push);
           if (push) q[(tail + __popc(m & lt)) & (QCAP - 1)] = t;
           tail += __popc(m);
+          I3RC_STAT(W, ST_LE_PUSH, __popc(m));
           if (((p.vertMask >> dcur) & 1u) || p.leUB) {  // contributions worked out on the spot (make_le_task returned 2)
             Tally tv;
             if constexpr (TSM) tv.n = 0;
@@ -355,6 +360,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
           nempty += __popc(md);
         }
         const unsigned mn = __ballot_sync(full, need);
+        I3RC_STAT(W, ST_BIRTHS, __popc(mn));
+        I3RC_STAT(W, ST_BIRTH_BATCH, mn != 0u);
         if (mn) {
           unsigned long long base = 0;
           const int leader = __ffs(mn) - 1;
@@ -406,6 +413,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
         stage = 0;
       }
       if (stage != 0) {  // suspended: park the photon in its slot, the rest of the batch state in the scratch
+        I3RC_STAT(W, ST_SUSP, 1);
         if (has) {
           pool.xy[eslot] = (uint32_t)E.cx | ((uint32_t)E.cy << 16);
           pool.zs[eslot] = ((uint32_t)E.cz & 0xffffu) | ((uint32_t)(E.active ? DONE_INSIDE : DONE_NEW) << 16);
@@ -437,11 +445,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
     // enough lanes wait for the (divergent, per-ray) bookkeeping below to make it worth its price.
     // (UNROLL pairs per loop body: unrolling keeps a ray's gathers in flight across pairs -- at a back-edge the compiler
     // waits for every outstanding load -- but measured slower, 2.05e8 vs 2.21e8 photons/s at 4 vs 1: instruction cache.)
+    I3RC_STAT(W, ST_ROUNDS, 1);
+    I3RC_STAT(W, ST_START_RUN, __popc(__ballot_sync(full, R.done == DONE_RUN)));
 #pragma unroll 1
     for (int k = 0; k < STEPS / (2 * UNROLL); k++) {
       bool few = false;
 #pragma unroll
       for (int u = 0; u < UNROLL; u++) {
+        I3RC_STAT(W, ST_PAIRS, 1);
+        I3RC_STAT(W, ST_LANE_PAIRS, __popc(__ballot_sync(full, R.done == DONE_RUN)));
         if (R.done == DONE_RUN) dda_step_pair(p, R);
         few = __popc(__ballot_sync(full, R.done == DONE_RUN)) < minRunning;
         if (few) break;
@@ -537,6 +549,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
         max_cross_section_flight(p, R, t.tauFree);
       }
     }
+    I3RC_STAT(W, ST_STARVED, max(__popc(mi) - avail, 0));
+    I3RC_STAT(W, ST_RING_LEFT, max(avail - __popc(mi), 0));
     head += min(__popc(mi), avail);
     __syncwarp();
   }

@@ -72,7 +72,22 @@ constexpr int DIR_STRIDE = 8;
 constexpr int MAX_RAY_STEPS = 1 << 26;  // hang protection: a ray that long is dropped as "bad"
 
 enum { CNT_PHOTONS = 0, CNT_BAD, CNT_CROSS_PH, CNT_CROSS_LE, CNT_COLL, CNT_ABS, CNT_CONTRIB, CNT_TOP, CNT_SURF,
-       CNT_RNG, CNT_KILL, CNT_NULL, CNT_SKIP, CNT_SKIP_LE, CNT_N };
+       CNT_RNG, CNT_KILL, CNT_NULL, CNT_SKIP, CNT_SKIP_LE,
+#ifdef I3RC_SCHED_STATS  // make STATS=1: what the warps of k_transport do with their lanes (printed by fetch_counters)
+       ST_ROUNDS, ST_START_RUN, ST_PAIRS, ST_LANE_PAIRS, ST_STARVED, ST_RING_LEFT, ST_BATCH, ST_BATCH_HAS, ST_BATCH_ALIVE, ST_SUSP, ST_LE_PUSH,
+       ST_BIRTHS, ST_BIRTH_BATCH,
+#endif
+       CNT_N };
+// (the value is worked out by ALL lanes -- it may be a ballot --, lane 0 adds it)
+#ifdef I3RC_SCHED_STATS
+#define I3RC_STAT(W, k, v)                                          \
+  do {                                                              \
+    const uint32_t i3rc_stat_v = (uint32_t)(v);                     \
+    if ((threadIdx.x & 31) == 0) (W).cnt[k] += i3rc_stat_v;         \
+  } while (0)
+#else
+#define I3RC_STAT(W, k, v) ((void)0)
+#endif
 // Empty-space codes (Problem::ext of a JUMP kernel): an empty cell whose whole Chebyshev neighbourhood of radius n + 1 is
 // empty (periodic in x and y; beyond the top and the bottom counts as empty) holds -n instead of 0, for n in
 // [JUMP_MIN, JUMP_MAX].  A ray that has just crossed such a cell may cross up to n further cells on every axis without

@@ -644,6 +644,29 @@ def test_tallies_staged_in_shared_memory_equal_global_atomics(cuda):
             assert np.allclose(a[k], b[k], rtol=2e-3, atol=1e-7), (k, np.max(np.abs(a[k] - b[k])))
 
 
+def test_births_in_groups_trace_the_same_photons(cuda):
+    """A warp starts new photons when `birth_min` of its slots are empty (k_transport, kernels.cuh) instead of refilling
+    every slot at once: which slot and which lane a photon gets changes, its Philox stream does not, so every counter is
+    the same and the results agree to float32 summation order -- on a small domain (staged tallies), on a domain of a
+    few columns and on the Landsat field, with a photon count that does not fill the last group."""
+    kw = dict(surfaceAlbedo=0.2, intensityMus=[1.0, 0.5, 0.5], intensityPhis=[0.0, 0.0, 180.0], useRussianRouletteForIntensity=True,
+              zetaMin=0.3)
+    for make, nph in ((lambda: fields.plane_parallel(nX=3, nY=2, nLayers=4, SSA=0.9), 70_001),
+                      (lambda: fields.step_cloud(0.99), 100_003), (lambda: fields.landsat_cloud(0.98, nLegendreCoefficients=16), 300_007)):
+        res = []
+        for bmin, blow in ((1, 16), (16, 4), (32, 0)):
+            I = make_integrator(cuda, make(), **kw)
+            assert cuda.set_tuning(I.handle, b"birth_min", bmin) == 0 and cuda.set_tuning(I.handle, b"birth_low", blow) == 0
+            computeRadiativeTransfer(I, new_RandomNumberSequence([7, 2]), new_PhotonStream(0.5, 30.0, numberOfPhotons=nph))
+            res.append((reportResults(I, "fluxUp", "fluxDown", "fluxAbsorbed", "intensity", "volumeAbsorption"), getCounters(I)))
+        (a, ca) = res[0]
+        assert ca["photons"] == nph and ca["bad"] == 0
+        for b, cb in res[1:]:
+            assert ca == cb
+            for k in a:
+                assert np.allclose(a[k], b[k], rtol=2e-3, atol=1e-6), (k, np.max(np.abs(a[k] - b[k])))
+
+
 def test_empty_space_codes_change_nothing_but_the_number_of_gathers(cuda, monkeypatch):
     """Rays that jump through empty space (the coded copy of the gather field, transport.cuh JUMP_*) trace the same
     photons as rays that look at every cell: same Philox streams, so the batch results agree to float32 rounding (a jump
