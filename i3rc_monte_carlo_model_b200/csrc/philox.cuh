@@ -29,7 +29,12 @@ I3RC_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
-I3RC_HD u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1) {
+#if defined(__CUDACC__) && defined(I3RC_PHILOX_NOINLINE)  // (experiment: one copy of the ten rounds in the kernel instead of four)
+__host__ __device__ __noinline__
+#else
+I3RC_HD
+#endif
+u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 10; r++) {
