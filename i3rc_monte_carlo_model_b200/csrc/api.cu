@@ -1106,7 +1106,7 @@ int prepare_compute(i3rc_integrator* h, const i3rc_photon_source* src, SourceDev
       dfree(h->d_leLB);
       dfree(h->d_leUB);
       CUDA_OK(h, cudaMalloc(&h->d_leLB, sizeof(float) * ncell * h->nDir));
-      dim3 g((unsigned)((ncell + 127) / 128), (unsigned)h->nDir);
+      const unsigned g = (unsigned)((ncell + 127) / 128);
       // (the full depth of the domain where that is cheap: 2 M cells x 3 directions take ~10 ms -- then the upper bound
       //  exists too --; LE_LB_LAYERS layers otherwise)
       const bool full = ncell * h->nDir <= ((size_t)64 << 20);

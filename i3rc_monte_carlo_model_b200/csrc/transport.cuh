@@ -1144,7 +1144,7 @@ I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, L
   float tauFree = 0.0f, above = 0.0f, lb = 0.0f;
   const bool bounded = p.useRRIntensity && p.leLB && !vertical && p.leLBBins == 1;
   if (vertical) above = I3RC_LDG(p.colTau + (size_t)(L.cz + 1) * ((size_t)p.nx * p.ny) + (size_t)(L.cy * p.nx + L.cx));
-  if (bounded) lb = I3RC_LDG(p.leLB + (size_t)d * ((size_t)p.nx * p.ny * p.nz) + ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx);
+  if (bounded) lb = I3RC_LDG(p.leLB + (((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx) * p.nDir + d);  // (direction-fastest)
   if (p.useRRIntensity) {
     tauFree = tau_of(xiTau);  // MCRT:1542
     // Under the roulette no ray has a larger budget than tauFree + limMax (the first-stage limit of the largest
@@ -1181,8 +1181,8 @@ I3RC_HD int make_le_task(const P& p, Lane& L, int d, float xiTau, float xiAcc, L
     // the budget the ray has for reaching the top, against the least and the most it can need from this cell
     const float budget = mode == MODE_LE_SMALL ? lim : lim + tauFree;
     if (lb > budget) return 0;
-    const size_t ncell = (size_t)p.nx * p.ny * p.nz, cell = ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx;
-    if (p.leUB && I3RC_LDG(p.leUB + (size_t)d * ncell + cell) <= budget && (mode == MODE_LE_SMALL || lb > lim)) {
+    const size_t cell = ((size_t)L.cz * p.ny + L.cy) * p.nx + L.cx;
+    if (p.leUB && I3RC_LDG(p.leUB + cell * p.nDir + d) <= budget && (mode == MODE_LE_SMALL || lb > lim)) {
       // Certain to reach the top, and not within the first stage's limit: the contribution is the survivors' fixed one.
       // The exit column is where the straight line from the event point meets the top of the domain.
       const float h = (float)(p.nz - L.cz) - L.fz;  // layers to the top

@@ -130,8 +130,8 @@ static void lower_bound_setup(Problem& p) {
       const int ix = (int)(i % p.nx), iy = (int)((i / p.nx) % p.ny), iz = (int)(i / ((size_t)p.nx * p.ny));
       if (!(p.ext[i] > 0.0f || iz == 0)) continue;
       le_path_bounds(p.ext, p.nx, p.ny, p.nz, p.dx, p.dy, p.dz, p.dirs[d * DIR_STRIDE], p.dirs[d * DIR_STRIDE + 1],
-                     p.dirs[d * DIR_STRIDE + 2], ix, iy, iz, p.nz, LE_LB_ENOUGH, &g_leLB[(size_t)d * ncell + i],
-                     &g_leUB[(size_t)d * ncell + i]);
+                     p.dirs[d * DIR_STRIDE + 2], ix, iy, iz, p.nz, LE_LB_ENOUGH, &g_leLB[i * p.nDir + d],
+                     &g_leUB[i * p.nDir + d]);
     }
   p.leLB = g_leLB.data();
   if (g_lb == 2) p.leUB = g_leUB.data();
