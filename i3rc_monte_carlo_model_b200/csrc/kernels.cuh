@@ -53,6 +53,9 @@ struct SlotPool {  // structure of arrays: lane i touches slot[k] of every array
   float sp[NSLOT], spd[NSLOT];
 };
 constexpr uint32_t SLOT_RAW = 1u << 24;
+#ifndef I3RC_SPLIT_SINGLE_STEP
+#define I3RC_SPLIT_SINGLE_STEP 1  // 0: the layer-table kernels step in pairs like the others (A/B)
+#endif
 
 // everything a warp keeps in shared memory (8 KB with NSLOT = QCAP = 64)
 template <int NSLOT, int QCAP>
@@ -454,7 +457,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
       for (int u = 0; u < UNROLL; u++) {
         I3RC_STAT(W, ST_PAIRS, 1);
         I3RC_STAT(W, ST_LANE_PAIRS, __popc(__ballot_sync(full, R.done == DONE_RUN)));
-        if (R.done == DONE_RUN) dda_step_pair(p, R);
+        if constexpr (SPLIT && I3RC_SPLIT_SINGLE_STEP) {
+          // (the layer-table kernels carry the slab code in every step: one copy of the step in the loop instead of the
+          //  two of a pair -- the extinction registers change places instead of roles -- halves a loop body that no longer
+          //  fitted the instruction cache)
+#pragma unroll 1
+          for (int hstep = 0; hstep < 2; hstep++) {
+            if (R.done == DONE_RUN) {
+              dda_step<0>(p, R);
+              if (R.done == DONE_RUN) {
+                const float t = R.e0;
+                R.e0 = R.e1;
+                R.e1 = t;
+              }
+            }
+          }
+        } else if (R.done == DONE_RUN) {
+          dda_step_pair(p, R);
+        }
         few = __popc(__ballot_sync(full, R.done == DONE_RUN)) < minRunning;
         if (few) break;
       }

@@ -776,21 +776,25 @@ I3RC_HD void ray_move_on(const P& p, Lane& L, float& ePending, float& eOther) {
     if (!ray_advance_far(p, L, n)) ePending = ext_gather(p, L.idx, ray_iz(p, L));
     return;
   }
+  bool out;
   if (SlabJump<P>::on && eOther < 0.0f) {
     // The cell the geometry is in carries a slab code.  If the ray's optical-path limit lies beyond the slab, the
     // geometry goes to the far side at once (the next step adds the code's optical path, with path length 1: the very
     // sum tested here); if not, the ray ends in the slab and walks there cell by cell.
     if (fmaf(1.0f, -eOther - 1.0f, L.tau) <= L.tauLimit) {
-      if (!ray_cross_slab(p, L)) ePending = ext_gather_ray(p, L);
-      return;
-    }
+      out = ray_cross_slab(p, L);
+    } else {
 #ifdef __CUDA_ARCH__
-    eOther = __int_as_float(__ldg(p.zlut + ray_iz(p, L)).y);
+      eOther = __int_as_float(__ldg(p.zlut + ray_iz(p, L)).y);
 #else
-    memcpy(&eOther, &p.zlut[ray_iz(p, L)].y, sizeof(float));
+      memcpy(&eOther, &p.zlut[ray_iz(p, L)].y, sizeof(float));
 #endif
+      out = ray_advance(p, L);
+    }
+  } else {
+    out = ray_advance(p, L);
   }
-  if (!ray_advance(p, L)) ePending = ext_gather_ray(p, L);  // (the register is free now: it becomes the look-ahead)
+  if (!out) ePending = ext_gather_ray(p, L);  // (the register is free now: it becomes the look-ahead; one call site)
 }
 template <int PAR, class P>
 I3RC_HD void dda_step(const P& p, Lane& L) {
