@@ -119,6 +119,8 @@ struct i3rc_integrator {
   float *d_fluxUp = nullptr, *d_fluxDown = nullptr, *d_fluxAbs = nullptr, *d_volAbs = nullptr;
   float *d_intensity = nullptr, *d_intByComp = nullptr, *d_excess = nullptr;
   unsigned long long *d_counters = nullptr, *d_next = nullptr;
+  uint32_t* d_susp = nullptr;  // Problem::susp: 7 x 32 words per warp of the grid (sized at the launch)
+  size_t suspN = 0;
   double* d_fold = nullptr;  // float64 sums of the tallies of a batch that is traced in pieces (run_one_batch)
   size_t foldN = 0;
   double* d_scratch = nullptr;  // slab sums
@@ -148,6 +150,7 @@ struct i3rc_integrator {
   // tuning
   int blockSize = 128, blocksPerSM = 0, residentBlocks = 0, poolShape = 0, minRunning = 16, padSmem = 0, kSteps = 16;
   int eventThreshold = 4;  // (tuning) an event batch of fewer than 32 events starts only when the ring is empty and at most this many lanes trace
+  int slots80 = 1;  // (tuning `slots_80`) 0: 64 photon slots per warp on domains of many columns too
   int birthLow = 4;  // (tuning) ... or when the task ring is empty and at most this many lanes are tracing
   int birthMin = 16;  // (tuning) a warp starts new photons when this many of its slots are empty (1: at once, one by one)
   float* d_rep = nullptr;   // copies of the tallies of a domain of few columns (Problem::rep)
@@ -614,6 +617,7 @@ void fill_problem(i3rc_integrator* h, Problem& p) {
   p.excess = h->d_excess;
   p.counters = h->d_counters;
   p.nextPhoton = h->d_next;
+  p.susp = h->d_susp;
   // Tallies staged in shared memory, one private copy per warp, when the domain has so few columns that the whole GPU
   // would otherwise hammer a handful of addresses: fluxes and radiances, and the volume absorption too if it fits.
   p.deriveAbs = 1;
@@ -760,8 +764,16 @@ int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   long long grid = (long long)h->numSMs * perSM;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
+  const size_t suspNeed = (size_t)grid * (BLOCK / 32) * SUSP_WORDS;
+  if (h->suspN < suspNeed) {  // (scratch of suspended event batches, Problem::susp)
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    dfree(h->d_susp);
+    h->suspN = std::max(suspNeed, (size_t)h->numSMs * 32 * SUSP_WORDS);
+    CUDA_OK(h, cudaMalloc(&h->d_susp, sizeof(uint32_t) * h->suspN));
+  }
   ProblemT<REG, FAST, SPLIT, JUMP, TABSM> pt;
   static_cast<Problem&>(pt) = p;
+  pt.susp = h->d_susp;
   if (JUMP) pt.ext = h->d_extJ;  // the copy of the gather field that carries the empty-space codes
   kern<<<(unsigned)grid, BLOCK, dynSmem, h->stream>>>(pt, h->eventThreshold, h->minRunning, h->birthMin | (h->birthLow << 8));
   return I3RC_SUCCESS;
@@ -805,42 +817,43 @@ void set_l2_window(i3rc_integrator* h) {
 }
 
 int launch_transport(i3rc_integrator* h, const Problem& p) {
+  constexpr int NS = 64;  // photon slots per warp
   set_l2_window(h);
   const bool reg = p.xyRegular && p.zRegular;
   const bool fast = p.useRayTracing && p.src.kind != 5 && p.src.kind != 6 && !p.useSurfaceBDRF && !p.useHybrid && !p.limitContrib &&
                     !p.trackByComponent;
   if (p.tsmN > 0) {  // a domain of a few columns: tallies staged per warp in shared memory (warp_tally, kernels.cuh)
     if (p.nzc) {  // (a layer table, forced by `split_layers` = 2 on a small domain: the variants that honour it)
-      if (reg && fast) return launch_transport_t<128, true, true, true, 5, 16, 64, 64, true>(h, p);
-      if (reg) return launch_transport_t<128, true, false, true, 5, 16, 64, 64, true>(h, p);
-      return launch_transport_t<128, false, false, true, 5, 16, 64, 64, true>(h, p);
+      if (reg && fast) return launch_transport_t<128, true, true, true, 5, 16, NS, 64, true>(h, p);
+      if (reg) return launch_transport_t<128, true, false, true, 5, 16, NS, 64, true>(h, p);
+      return launch_transport_t<128, false, false, true, 5, 16, NS, 64, true>(h, p);
     }
     if (reg && fast)
-      return h->residentBlocks == 4 ? launch_transport_t<128, true, true, false, 4, 16, 64, 64, true>(h, p)
-                                    : launch_transport_t<128, true, true, false, 5, 16, 64, 64, true>(h, p);
-    if (reg) return launch_transport_t<128, true, false, false, 5, 16, 64, 64, true>(h, p);
-    return launch_transport_t<128, false, false, false, 5, 16, 64, 64, true>(h, p);
+      return h->residentBlocks == 4 ? launch_transport_t<128, true, true, false, 4, 16, NS, 64, true>(h, p)
+                                    : launch_transport_t<128, true, true, false, 5, 16, NS, 64, true>(h, p);
+    if (reg) return launch_transport_t<128, true, false, false, 5, 16, NS, 64, true>(h, p);
+    return launch_transport_t<128, false, false, false, 5, 16, NS, 64, true>(h, p);
   }
   if (p.nzc) {  // only the horizontally varying layers are stored (large fields): the gathers look the layer up first
     if (reg && fast) {  // (5 resident blocks: 512x512x256 with slab crossings 3.86e7 photons/s against 3.63e7 with 6)
-      if (h->poolShape == 4) return launch_transport_t<128, true, true, true, 5, 16, 64, 128>(h, p);  // (experiment: longer task ring)
-      return h->residentBlocks == 6 ? launch_transport_t<128, true, true, true, 6, 16, 64, 64>(h, p)
-                                    : launch_transport_t<128, true, true, true, 5, 16, 64, 64>(h, p);
+      if (h->poolShape == 4) return launch_transport_t<128, true, true, true, 5, 16, NS, 128>(h, p);  // (experiment: longer task ring)
+      return h->residentBlocks == 6 ? launch_transport_t<128, true, true, true, 6, 16, NS, 64>(h, p)
+                                    : launch_transport_t<128, true, true, true, 5, 16, NS, 64>(h, p);
     }
-    if (reg) return launch_transport_t<128, true, false, true, 5, 16, 64, 64>(h, p);
-    return launch_transport_t<128, false, false, true, 5, 16, 64, 64>(h, p);
+    if (reg) return launch_transport_t<128, true, false, true, 5, 16, NS, 64>(h, p);
+    return launch_transport_t<128, false, false, true, 5, 16, NS, 64>(h, p);
   }
   if (reg && h->d_extJ && p.useRayTracing) {  // enough empty space for the rays to jump through it
     const int blocks = h->residentBlocks ? h->residentBlocks : 6;
-    if (fast) return blocks == 5 ? launch_transport_t<128, true, true, false, 5, 16, 64, 64, false, true>(h, p)
-                                 : launch_transport_t<128, true, true, false, 6, 16, 64, 64, false, true>(h, p);
-    return launch_transport_t<128, true, false, false, 5, 16, 64, 64, false, true>(h, p);
+    if (fast) return blocks == 5 ? launch_transport_t<128, true, true, false, 5, 16, NS, 64, false, true>(h, p)
+                                 : launch_transport_t<128, true, true, false, 6, 16, NS, 64, false, true>(h, p);
+    return launch_transport_t<128, true, false, false, 5, 16, NS, 64, false, true>(h, p);
   }
   // (experiment, `tables_in_smem`) one block of 16 warps per SM with the inverse and the forward phase-function table of the
   // single component staged in shared memory: measured against the default in profiles/r02_summary.md
   if (reg && fast && h->tablesInSmem && p.nc == 1 && p.computeIntensity && h->inv[0].nEntries == 1 && h->fwd[0].d &&
       sizeof(float) * ((size_t)h->inv[0].nSteps + h->fwd[0].nSteps) <= 90 * 1024)
-    return launch_transport_t<512, true, true, false, 1, 16, 64, 64, false, false, true>(h, p);
+    return launch_transport_t<512, true, true, false, 1, 16, NS, 64, false, false, true>(h, p);
   if (reg && fast) {
     // resident blocks per SM, 0 = automatic: 6 while the extinction field is L2-resident; 5 (more of the 256 KB left as
     // L1) when the gathers go to HBM
@@ -848,9 +861,15 @@ int launch_transport(i3rc_integrator* h, const Problem& p) {
     const int blocks = h->residentBlocks ? h->residentBlocks : (ncell * sizeof(float) <= (size_t)48 << 20 ? 6 : 5);
     switch (blocks * 10 + h->poolShape) {  // (blocks per SM, photon slots and ring entries per warp)
       case 60:
-        return launch_transport_fast<6, 64, 64>(h, p);
+        // Domains of many columns (long rays; the ring is not what limits the warp): 80 slots per warp, the scratch of
+        // suspended batches in global memory instead -- same shared memory, same L1.  Landsat 2.71e8 -> 2.77e8 photons/s.
+        // Domains of few columns keep 64: with 80 photons the ring of 64 tasks is full most of the time and the event
+        // batches get suspended (step cloud 3.0e8 -> 2.4e8, profiles/r02_ab_builds_late.txt).
+        // Many radiance directions fill the ring as well (16 directions on 128x128x64: 7.3e7 -> 7.1e7): 64 slots there too.
+        if ((size_t)p.nx * p.ny >= 4096 && p.nDir <= 4 && h->slots80) return launch_transport_t<128, true, true, false, 6, 16, 80, 64>(h, p);
+        return launch_transport_fast<6, NS, 64>(h, p);
       case 40:
-        return launch_transport_fast<4, 64, 64>(h, p);
+        return launch_transport_fast<4, NS, 64>(h, p);
       case 52:
         return launch_transport_fast<5, 48, 64>(h, p);
       case 55:  // (experiments: more photons per warp, so that the task ring runs dry less often)
@@ -864,11 +883,11 @@ int launch_transport(i3rc_integrator* h, const Problem& p) {
       case 83:
         return launch_transport_t<128, true, true, false, 8, 16, 32, 64>(h, p);
       default:  // the shared-memory footprint is kept small on purpose: what is left of the 256 KB is L1 for the gathers
-        return launch_transport_fast<5, 64, 64>(h, p);
+        return launch_transport_fast<5, NS, 64>(h, p);
     }
   }
-  if (reg) return launch_transport_t<128, true, false, false, 5, 16, 64, 64>(h, p);
-  return fast ? launch_transport_t<128, false, true, false, 5, 16, 64, 64>(h, p) : launch_transport_t<128, false, false, false, 5, 16, 64, 64>(h, p);
+  if (reg) return launch_transport_t<128, true, false, false, 5, 16, NS, 64>(h, p);
+  return fast ? launch_transport_t<128, false, true, false, 5, 16, NS, 64>(h, p) : launch_transport_t<128, false, false, false, 5, 16, NS, 64>(h, p);
 }
 
 // zero tallies, trace one batch, post-process (MCRT:296-395); no host synchronisation
@@ -1453,6 +1472,7 @@ void i3rc_finalize_Integrator(i3rc_integrator* h) {
     h->copyStream = nullptr;
   }
   dfree(h->d_next);
+  dfree(h->d_susp);
   dfree(h->d_rep);
   dfree(h->d_avail);
   if (h->h_avail) cudaFreeHost(h->h_avail);
@@ -1848,6 +1868,7 @@ int i3rc_copy_Integrator(const i3rc_integrator* s, i3rc_integrator** out) {
   h->eventThreshold = s->eventThreshold;
   h->birthMin = s->birthMin;
   h->birthLow = s->birthLow;
+  h->slots80 = s->slots80;
   h->residentBlocks = s->residentBlocks;
   h->poolShape = s->poolShape;
   h->minRunning = s->minRunning;
@@ -2279,6 +2300,8 @@ int i3rc_set_tuning(i3rc_integrator* h, const char* key, int value) {
     h->birthMin = value;
   else if (k == "birth_low" && value >= 0 && value <= 32)
     h->birthLow = value;
+  else if (k == "slots_80" && (value == 0 || value == 1))
+    h->slots80 = value;
   else if (k == "track_by_component")
     h->trackByComponent = value != 0;
   else if (k == "slab_jump" && (value == 0 || value == 1))

@@ -57,12 +57,18 @@ constexpr uint32_t SLOT_RAW = 1u << 24;
 #define I3RC_SPLIT_SINGLE_STEP 1  // 0: the layer-table kernels step in pairs like the others (A/B)
 #endif
 
-// everything a warp keeps in shared memory (8 KB with NSLOT = QCAP = 64)
+// everything a warp keeps in shared memory (8 KB with NSLOT = QCAP = 64, and with NSLOT = 80)
+// (more than 64 slots: the scratch of suspended batches moves to global memory, Problem::susp, and its 896 bytes are the
+//  sixteen extra slots -- the warp's block stays at 8 KB and the SM's L1 share unchanged)
+template <int NSLOT>
+struct SuspScratch {
+  uint32_t w[NSLOT > 64 ? 1 : 7 * 32];  // per-lane state of a suspended event batch
+};
 template <int NSLOT, int QCAP>
 struct WarpShared {
   LeTask task[QCAP];
   SlotPool<NSLOT> pool;
-  uint32_t susp[7][32];  // per-lane state of a suspended event batch
+  SuspScratch<NSLOT> susp;
   uint32_t ray[4][32];   // per lane: what its ray is for (photon slot, or local-estimate parameters)
   uint32_t cnt[CNT_N];
   uint8_t pend[NSLOT];
@@ -127,6 +133,16 @@ __device__ __forceinline__ void flush_staged_tallies(const P& p, const float* sd
       atomicAdd(tally_ptr(p, which) + (i - best), x);
     }
   }
+}
+
+// the 7 x 32 words of this warp in the scratch of suspended event batches (global memory; lane-private entries)
+constexpr int SUSP_WORDS = 7 * 32;
+template <int NSLOT, class P, class WS>
+__device__ __forceinline__ uint32_t* susp_of(const P& p, WS& W, int warp) {
+  if constexpr (NSLOT > 64)
+    return p.susp + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * SUSP_WORDS;
+  else
+    return W.susp.w;
 }
 
 template <int BLOCK, bool REG, bool FAST, bool SPLIT, int MINB, int STEPS, int NSLOT, int QCAP, bool TSM = false, bool JUMP = false,
@@ -234,7 +250,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
     }
     if (run) {
       if (stage != 0) {  // resuming a suspended batch
-        const uint32_t w = W.susp[6][lane];
+        const uint32_t w = susp_of<NSLOT>(p, W, warp)[6 * 32 + lane];
         eslot = (int)(w & 0xffu);
         has = (w & 0x100u) != 0;
       }
@@ -309,7 +325,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
         I3RC_STAT(W, ST_BATCH_ALIVE, __popc(__ballot_sync(full, alive)));
         stage = (p.computeIntensity && __any_sync(full, alive)) ? 1 : 2;
       } else {  // resume: the rest of the batch state comes back from shared memory
-        const uint32_t* sv = W.susp[0] + lane;
+        const uint32_t* sv = susp_of<NSLOT>(p, W, warp) + lane;
         alive = (sv[6 * 32] & 0x200u) != 0;
         a1 = __uint_as_float(sv[0 * 32]);
         a2 = __uint_as_float(sv[1 * 32]);
@@ -430,7 +446,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_transport(const ProblemT<REG, F
           pool.order[eslot] = E.order;
           pool.block[eslot] = E.rng.block;
         }
-        uint32_t* sv = W.susp[0] + lane;
+        uint32_t* sv = susp_of<NSLOT>(p, W, warp) + lane;
         sv[0 * 32] = __float_as_uint(a1);
         sv[1 * 32] = __float_as_uint(a2);
         sv[2 * 32] = __float_as_uint(a3);

@@ -194,6 +194,7 @@ struct Problem {
   int deriveAbs;
   unsigned long long* counters;
   unsigned long long* nextPhoton;
+  uint32_t* susp;  // scratch of suspended event batches: SUSP_WORDS per warp of the grid (k_transport)
   long long firstPhoton;  // photon ids of this launch are firstPhoton + [0, src.n)
 };
 

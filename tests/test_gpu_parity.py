@@ -667,6 +667,28 @@ def test_births_in_groups_trace_the_same_photons(cuda):
                 assert np.allclose(a[k], b[k], rtol=2e-3, atol=1e-6), (k, np.max(np.abs(a[k] - b[k])))
 
 
+def test_eighty_slots_per_warp_trace_the_same_photons(cuda):
+    """Domains of many columns run a kernel with 80 photon slots per warp whose scratch of suspended event batches lives in
+    global memory (k_transport, SuspScratch): same photons, same Philox streams as with 64 slots -- on the Landsat field
+    and on a two-component field with four radiance directions (the kernel is chosen for domains of at least 4096 columns
+    and at most four directions)."""
+    cases = ((lambda: fields.landsat_cloud(0.98, nLegendreCoefficients=16),
+              dict(intensityMus=[1.0, 0.5, 0.5], intensityPhis=[0.0, 0.0, 180.0]), 300_007),
+             (lambda: fields.synthetic_les(nx=64, ny=64, nz=32),
+              dict(intensityMus=[1.0, 0.8, 0.6, 0.4], intensityPhis=[0.0, 90.0, 180.0, 270.0]), 100_003))
+    for make, dirs, nph in cases:
+        res = []
+        for s80 in (1, 0):
+            I = make_integrator(cuda, make(), surfaceAlbedo=0.2, useRussianRouletteForIntensity=True, zetaMin=0.3, **dirs)
+            assert cuda.set_tuning(I.handle, b"slots_80", s80) == 0
+            computeRadiativeTransfer(I, new_RandomNumberSequence([7, 3]), new_PhotonStream(0.5, 30.0, numberOfPhotons=nph))
+            res.append((reportResults(I, "fluxUp", "fluxDown", "fluxAbsorbed", "intensity", "volumeAbsorption"), getCounters(I)))
+        (a, ca), (b, cb) = res
+        assert ca["photons"] == nph and ca["bad"] == 0 and ca == cb
+        for k in a:
+            assert np.allclose(a[k], b[k], rtol=2e-3, atol=1e-6), (k, np.max(np.abs(a[k] - b[k])))
+
+
 def test_empty_space_codes_change_nothing_but_the_number_of_gathers(cuda, monkeypatch):
     """Rays that jump through empty space (the coded copy of the gather field, transport.cuh JUMP_*) trace the same
     photons as rays that look at every cell: same Philox streams, so the batch results agree to float32 rounding (a jump
