@@ -775,7 +775,9 @@ int launch_transport_t(i3rc_integrator* h, const Problem& p) {
   static_cast<Problem&>(pt) = p;
   pt.susp = h->d_susp;
   if (JUMP) pt.ext = h->d_extJ;  // the copy of the gather field that carries the empty-space codes
-  kern<<<(unsigned)grid, BLOCK, dynSmem, h->stream>>>(pt, h->eventThreshold, h->minRunning, h->birthMin | (h->birthLow << 8));
+  // (the default group of births grows with the pool: 16 of 64 slots, 24 of 80 -- measured, profiles/r02_ab_builds_late.txt)
+  const int birthMin = (NSLOT > 64 && h->birthMin == 16) ? 24 : h->birthMin;
+  kern<<<(unsigned)grid, BLOCK, dynSmem, h->stream>>>(pt, h->eventThreshold, h->minRunning, birthMin | (h->birthLow << 8));
   return I3RC_SUCCESS;
 }
 // MINB = resident blocks per SM the kernel is compiled for (register cap 65536 / (MINB * BLOCK));
