@@ -25,14 +25,18 @@ namespace i3rc {
 //                  lanes pop the next tasks from the ring;
 //   EVENT batches: when 32 events are due (or the ring has run dry and at most lowWater lanes trace) lane i takes the
 //                  i-th due slot: the raw ray becomes the event point, boundary or collision handling, then a warp-uniform loop over the radiance directions in which every lane
-//                  turns its local-estimate ray into a task, then roulette + scattering, refill of dead slots from the
-//                  device photon counter (one warp-aggregated atomicAdd), and the task of the next path segment.
+//                  turns its local-estimate ray into a task, then roulette + scattering, and the task of the next path
+//                  segment.  A slot whose photon has finished waits among the warp's EMPTY slots; when birthMin of them
+//                  are empty they join the due events and one batch starts all their photons (one warp-aggregated
+//                  atomicAdd on the device photon counter, the birth code run by many lanes).
 // So both the cell-crossing loop and the event code run with (nearly) full warps, whatever the individual photons do.
 // A batch that finds the ring full is suspended between two directions and resumed after more trace rounds.
 // Variants (template flags): TSM = the tallies of a few-column domain are staged per warp in shared memory and committed
 // warp-aggregated (warp_tally, flush_staged_tallies); JUMP = rays use the empty-space codes of the gather field
 // (transport.cuh, ray_advance_far; measured slower, off by default); TABSM = one 16-warp block per SM with the
-// phase-function tables staged in shared memory (measured slower, an experiment).  A radiance direction that points
+// phase-function tables staged in shared memory (measured slower, an experiment); NSLOT = 80 (domains of many columns and
+// few directions) keeps the state of a suspended batch in global memory instead of shared memory; SPLIT (layer table) runs
+// ONE copy of the step per loop iteration instead of a pair.  A radiance direction that points
 // straight up is never traced: make_le_task works its contribution out from the column's suffix sums.
 // The physics functions are the ones of transport.cuh; the per-photon Philox streams make the result independent of
 // which lane traces which ray (up to float summation order in the tallies).
