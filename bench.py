@@ -59,7 +59,7 @@ def make_workload(name):
     if name == "step":
         return dict(workload="i3rcStepCloud 32x1x32, HG g=0.85 (64 moments), ssa=0.99, mu0=0.5, 3 radiance directions, RR",
                     domain=lambda: fields.step_cloud(0.99), params=dict(surfaceAlbedo=0.0, **dirs3, **rr), source=src,
-                    photons=4_000_000, cpu_photons=200_000)
+                    photons=16_000_000, cpu_photons=200_000)
     if name == "planeparallel":
         return dict(workload="planeParallel.nml 1x1x1 tau=1 HG g=0.85, 3 radiance directions, plain local estimate",
                     domain=lambda: fields.plane_parallel(),
@@ -68,7 +68,7 @@ def make_workload(name):
     if name == "radar":
         return dict(workload="i3rcRadarCloud 640x1x54, Deirmendjian C1 (tabulated), ssa=0.99, mu0=0.5, 3 radiance directions, RR",
                     domain=lambda: fields.radar_cloud(0.99, "C1"), params=dict(surfaceAlbedo=0.0, **dirs3, **rr), source=src,
-                    photons=2_000_000, cpu_photons=40_000)
+                    photons=8_000_000, cpu_photons=40_000)
     if name in ("les", "les-small"):
         n = (512, 512, 256) if name == "les" else (128, 128, 64)
         mus = [1.0, 0.8, 0.6, 0.4]
@@ -77,7 +77,7 @@ def make_workload(name):
                     domain=lambda: fields.synthetic_les(nx=n[0], ny=n[1], nz=n[2]),
                     params=dict(surfaceAlbedo=0.05, intensityMus=[m for m in mus for _ in range(4)],
                                 intensityPhis=[p for _ in mus for p in (0.0, 90.0, 180.0, 270.0)], **rr),
-                    source=dict(solarMu=0.5, solarAzimuth=30.0), photons=2_000_000, cpu_photons=20_000)
+                    source=dict(solarMu=0.5, solarAzimuth=30.0), photons=4_000_000, cpu_photons=20_000)
     raise SystemExit(f"unknown workload {name}")
 
 
